@@ -1,0 +1,286 @@
+/*
+ * mwb.h -- C ABI of libmwb.so, the B200-native batched MiniWorld step engine.
+ *
+ * The reference (Farama-Foundation/Miniworld) has no plugin / FFI layer of its own: its
+ * only foreign-function crossing is pyglet's per-GL-call ctypes binding, hit thousands of
+ * times per frame from MiniWorldEnv.step / render_obs.  This header replaces that
+ * crossing with ONE batched call per step over N independent environments.  Every entry
+ * point below names the reference code it stands in for (paths relative to the reference
+ * root, pinned at c660156 / v2.1.0).
+ *
+ * Conventions
+ *   - plain C, no C++ / torch types; loaded with ctypes.CDLL (miniworld_b200/engine.py).
+ *   - every function returns 0 on success, a negative MWB_E* code otherwise;
+ *     mwb_last_error() returns a thread-local, library-owned message.
+ *   - every buffer is caller-owned.  Output / action pointers may be host or device
+ *     memory (detected with cudaPointerGetAttributes); host pointers make the call
+ *     synchronous, device pointers enqueue on `stream` and return.
+ *   - a handle is bound to one CUDA device and is not thread-safe.
+ *   - there is no CPU execution path: mwb_create fails with MWB_ENOCUDA without a GPU.
+ */
+#ifndef MWB_H_
+#define MWB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWB_ABI_VERSION 3
+
+/* error codes */
+#define MWB_OK 0
+#define MWB_EINVAL (-1)
+#define MWB_ENOCUDA (-2)
+#define MWB_ECUDA (-3)
+#define MWB_EABI (-4)
+#define MWB_ECAPACITY (-5)
+#define MWB_ESTATE (-6)
+
+/* fixed capacities of the flat records */
+#define MWB_MAX_EDGES 8   /* outline vertices per room (rect rooms and connectors: 4) */
+#define MWB_MAX_OPS 64    /* reset-program length */
+
+/* entity kinds (reference miniworld/entity.py: Box :386, MeshEnt :124, Agent :455) */
+#define MWB_KIND_NONE 0
+#define MWB_KIND_BOX 1
+#define MWB_KIND_MESH 2
+#define MWB_KIND_AGENT 3
+
+/* level rule evaluated after the base step (reference envs/<level>.py step()) */
+#define MWB_RULE_NONE 0   /* base MiniWorldEnv.step only (miniworld.py:670-730)               */
+#define MWB_RULE_GOAL 1   /* near(box) -> +_reward(), terminated (hallway.py:67-74, oneroom.py */
+                          /* :64-71, fourrooms.py:66-73, maze.py:155-162)                      */
+#define MWB_RULE_PICKUP 2 /* carrying -> remove, reward = 1 (pickupobjects.py:83-95)          */
+
+/* surfaces of a room */
+#define MWB_SURF_WALL 0
+#define MWB_SURF_FLOOR 1
+#define MWB_SURF_CEIL 2
+
+/* reset-program opcodes: a lowered _gen_world() (reference miniworld.py:544-604, 839-909) */
+#define MWB_OP_END 0
+#define MWB_OP_CHOICE 1   /* ireg[a] = np_random.choice(b)            (== integers(0, b))      */
+#define MWB_OP_UNIFORM 2  /* freg[a] = np_random.uniform(f[0], f[1])                           */
+#define MWB_OP_PLACE 3    /* place_entity(); see mwb_op                                         */
+
+typedef struct mwb_handle mwb_handle;
+
+typedef struct mwb_config {
+  int32_t abi_version;       /* must be MWB_ABI_VERSION                                          */
+  int32_t device;            /* CUDA ordinal                                                     */
+  int32_t num_envs;          /* N                                                                */
+  int32_t obs_width;         /* MiniWorldEnv(obs_width=80)  (miniworld.py:473)                   */
+  int32_t obs_height;        /* MiniWorldEnv(obs_height=60) (miniworld.py:474)                   */
+  int32_t msaa_samples;      /* 1, 4 or 8; FrameBuffer(obs_w, obs_h, 8) (miniworld.py:515)       */
+  int32_t shared_geometry;   /* 1: all envs share one static room template; 0: per-env geometry  */
+  int32_t max_rooms, max_quads, max_segs, max_ents;   /* per-env capacities                      */
+  int32_t rule_kind;         /* MWB_RULE_*                                                       */
+  int32_t rule_arg;          /* GOAL: entity slot of the box; PICKUP: num_objs                   */
+  int32_t domain_rand;       /* MiniWorldEnv(domain_rand=...) (miniworld.py:478)                 */
+  int32_t max_episode_steps; /* (miniworld.py:472)                                               */
+  int32_t autoreset;         /* 1: the step after terminated|truncated resets on the device      */
+  int32_t reserved[4];
+} mwb_config;
+
+/* DomainParams table (reference params.py:115-130), lowered: lo and (hi - lo) per element,
+ * as numpy's Generator.uniform consumes them (low + (high - low) * random()). */
+typedef struct mwb_params {
+  double sky_color[3], sky_color_lo[3], sky_color_rng[3];
+  double light_pos[3], light_pos_lo[3], light_pos_rng[3];
+  double light_color[3], light_color_lo[3], light_color_rng[3];
+  double light_ambient[3], light_ambient_lo[3], light_ambient_rng[3];
+  double obj_color_bias[3], obj_color_bias_lo[3], obj_color_bias_rng[3];
+  double forward_step, forward_step_lo, forward_step_rng;
+  double forward_drift, forward_drift_lo, forward_drift_rng;
+  double turn_step, turn_step_lo, turn_step_rng;
+  double cam_pitch, cam_pitch_lo, cam_pitch_rng;
+  double cam_fov_y, cam_fov_y_lo, cam_fov_y_rng;
+  double cam_height, cam_height_lo, cam_height_rng;
+  double cam_fwd_disp, cam_fwd_disp_lo, cam_fwd_disp_rng;
+  double max_forward_step;   /* params.get_max("forward_step") (miniworld.py:581)                */
+} mwb_params;
+
+/* one mip-mapped texture (reference opengl.py:147-184: GL_RGB, rows bottom-up, REPEAT,
+ * LINEAR / LINEAR_MIPMAP_LINEAR); texels passed top row first, RGB8, engine builds mips. */
+typedef struct mwb_tex_desc {
+  int32_t width, height;
+  int64_t offset;            /* byte offset of this texture's level 0 in the texel blob          */
+} mwb_tex_desc;
+
+/* one triangle mesh (reference objmesh.py:36-216): per face-vertex arrays */
+typedef struct mwb_mesh_desc {
+  int32_t num_tris;
+  int32_t reserved;
+  int64_t offset;            /* index of the first triangle in the vertex arrays                 */
+} mwb_mesh_desc;
+
+/* Room (reference miniworld.py:122-194): extents, outline + inward edge normals for
+ * point_inside (:272-284), pick probability for place_entity (:873-880), textures. */
+typedef struct mwb_room {
+  double min_x, max_x, min_z, max_z;
+  double cdf;                               /* cumulative room_probs, as Generator.choice(p=) */
+  double edge_px[MWB_MAX_EDGES], edge_pz[MWB_MAX_EDGES];   /* outline                          */
+  double edge_nx[MWB_MAX_EDGES], edge_nz[MWB_MAX_EDGES];   /* edge_norms                       */
+  int32_t num_edges;
+  int32_t tex_first[3];                     /* first texture id of the wall/floor/ceil family */
+  int32_t tex_count[3];                     /* number of variants (Texture.get, opengl.py:113) */
+  int32_t tex_id[3];                        /* variant in use (host-generated worlds)          */
+  int32_t reserved;
+} mwb_room;
+
+/* One static quad of Room._render (miniworld.py:401-434): floor / ceiling polygon or a wall
+ * piece from _gen_static_data (:313-344).  uvm = texcoords in metres; the engine applies
+ * TEX_DENSITY / tex size (gen_texcs_wall :82-103, gen_texcs_floor :106-119). */
+typedef struct mwb_quad {
+  float pos[4][3];
+  float nrm[3];
+  int32_t room;
+  int32_t surf;              /* MWB_SURF_*                                                       */
+  int32_t num_verts;         /* 4 (3 for a triangular floor fan piece)                          */
+  double uvm[4][2];
+} mwb_quad;
+
+/* collision segment, stored as the reference stores it: [s_p1, s_p0] (miniworld.py:325) */
+typedef struct mwb_seg {
+  double ax, az, bx, bz;
+} mwb_seg;
+
+/* Entity prototype: everything about an entity that does not change during an episode. */
+typedef struct mwb_proto {
+  int32_t kind;              /* MWB_KIND_*                                                       */
+  int32_t is_static;         /* Entity.is_static (entity.py:115-121, :163-165)                   */
+  int32_t mesh_id;           /* MeshEnt: index into the uploaded meshes, else -1                 */
+  int32_t radius_is_f32;     /* MeshEnt radii are np.float32 under numpy >= 2        */
+  double radius, height;
+  double size[3];            /* Box size                                                         */
+  double color[3];           /* COLORS[color] (entity.py:30-40)                                  */
+  float scale;               /* MeshEnt.scale (entity.py:144)                                    */
+  int32_t reserved;
+} mwb_proto;
+
+/* Per-env entity instance (host-generated worlds / state exchange). */
+typedef struct mwb_entity {
+  int32_t proto;             /* index into the handle's proto table, -1 = empty slot             */
+  int32_t reserved;
+  double pos[3];
+  double dir;
+  double color[3];           /* Box.color_vec after randomize (entity.py:405-407)                */
+} mwb_entity;
+
+typedef struct mwb_op {
+  int32_t op;                /* MWB_OP_*                                                         */
+  int32_t a, b;              /* CHOICE: dst ireg, n.  UNIFORM: dst freg.  PLACE: proto base, -   */
+  int32_t ireg_a, stride_a;  /* PLACE: proto = a + ireg[ireg_a]*stride_a + ireg[ireg_b]*stride_b */
+  int32_t ireg_b, stride_b;  /*        (ireg_* = -1: unused)                                     */
+  int32_t room;              /* PLACE: fixed room index or -1 (sample by area)                   */
+  int32_t dir_freg;          /* PLACE: freg holding dir, or -1 (draw uniform(-pi, pi))           */
+  int32_t is_agent;          /* PLACE: this is place_agent()                                     */
+  double f[4];               /* UNIFORM: lo, hi.  PLACE: min_x, max_x, min_z, max_z (NaN = room) */
+} mwb_op;
+
+/* Static template + reset program shared by all envs (shared_geometry = 1), or the
+ * geometry of one env (shared_geometry = 0, via mwb_set_world). */
+typedef struct mwb_geometry {
+  int32_t num_rooms, num_quads, num_segs, reserved;
+  const mwb_room* rooms;
+  const mwb_quad* quads;
+  const mwb_seg* segs;
+} mwb_geometry;
+
+/* Complete per-env world, produced by host-side world generation (reset()). */
+typedef struct mwb_world {
+  mwb_geometry geom;         /* ignored when shared_geometry = 1                                 */
+  int32_t num_slots;         /* length of the entity list (miniworld.py:560)                     */
+  int32_t agent_slot;        /* index of the agent in it                                         */
+  int32_t carrying;          /* slot being carried or -1                                         */
+  int32_t step_count;
+  int32_t num_picked_up;
+  int32_t hold;              /* 1: the next mwb_step reports this env as just reset (reward 0, flags
+                              * 0) instead of stepping it -- host-side "next-step" auto-reset       */
+  const mwb_entity* ents;    /* num_slots entries                                                */
+  double cam_height, cam_fwd_disp, cam_pitch, cam_fov_y;   /* Agent (entity.py:455-516)        */
+  double sky_color[3], light_pos[3], light_color[3], light_ambient[3];
+} mwb_world;
+
+/* numpy Generator(PCG64) state as exposed by bit_generator.state */
+typedef struct mwb_rng_state {
+  uint64_t state_hi, state_lo, inc_hi, inc_lo;
+  int32_t has_uint32;
+  uint32_t uinteger;
+} mwb_rng_state;
+
+/* Readback of the dynamic state (all host pointers, any may be NULL). */
+typedef struct mwb_state_view {
+  double* agent_pos;         /* [N][3]                                                           */
+  double* agent_dir;         /* [N]                                                              */
+  int32_t* step_count;       /* [N]                                                              */
+  int32_t* carrying;         /* [N]                                                              */
+  int32_t* num_slots;        /* [N]                                                              */
+  int32_t* agent_slot;       /* [N]                                                              */
+  mwb_entity* ents;          /* [N][max_ents]                                                    */
+  double* cam;               /* [N][4] height, fwd_disp, pitch, fov_y                            */
+  double* env_params;        /* [N][12] sky, light_pos, light_color, light_ambient               */
+  mwb_rng_state* rng;        /* [N]                                                              */
+  int32_t* room_tex;         /* [N][max_rooms][3] texture id in use per room surface             */
+  int32_t* num_picked_up;    /* [N]                                                              */
+} mwb_state_view;
+
+/* ---- lifetime ------------------------------------------------------------------------
+ * replaces MiniWorldEnv.__init__ GL context + FrameBuffer creation (miniworld.py:508-518,
+ * opengl.py:202-327) */
+int mwb_create(const mwb_config* cfg, mwb_handle** out);
+int mwb_destroy(mwb_handle* h);
+const char* mwb_last_error(void);
+
+/* ---- assets: Texture.load (opengl.py:147-184), ObjMesh.__init__ (objmesh.py:36-216) ---- */
+int mwb_upload_textures(mwb_handle* h, const mwb_tex_desc* descs, int n, const uint8_t* texels_rgb8);
+int mwb_upload_meshes(mwb_handle* h, const mwb_mesh_desc* descs, int n, const float* pos /*[T][3][3]*/,
+                      const float* nrm /*[T][3][3]*/, const float* uv /*[T][3][2]*/,
+                      const float* rgb /*[T][3][3]*/);
+
+/* ---- level definition ------------------------------------------------------------------ */
+int mwb_set_params(mwb_handle* h, const mwb_params* p);                    /* params.py:115-130  */
+int mwb_set_protos(mwb_handle* h, const mwb_proto* protos, int n);         /* entity.py ctor data */
+int mwb_set_template(mwb_handle* h, const mwb_geometry* g);                /* shared static rooms */
+int mwb_set_program(mwb_handle* h, const mwb_op* ops, int n);              /* lowered _gen_world  */
+
+/* ---- reset: MiniWorldEnv.reset (miniworld.py:544-604) ----------------------------------
+ * mwb_seed      = gym.Env.reset(seed=...): installs Generator(PCG64(SeedSequence(seed))) state
+ * mwb_reset     = device-side reset of the listed envs with the lowered program (RNG on device)
+ * mwb_set_world = host-generated world for the listed envs (any level, any _gen_world)       */
+int mwb_seed(mwb_handle* h, const int32_t* env_ids, int n, const mwb_rng_state* states);
+int mwb_reset(mwb_handle* h, const int32_t* env_ids /*NULL = all*/, int n, void* stream);
+int mwb_set_world(mwb_handle* h, const int32_t* env_ids, int n, const mwb_world* worlds);
+
+/* ---- the hot path: MiniWorldEnv.step (miniworld.py:670-730) + level rule + render_obs
+ * (:1177-1221) [+ render_depth (:1223-1236)] for all N envs.
+ *   actions      int32[N]          (host or device)
+ *   step_params  double[N][3] or NULL: forward_step, forward_drift, turn_step drawn by the
+ *                caller (single-env host-RNG path); NULL = defaults / device RNG (:677-680)
+ *   obs          uint8[N][H][W][3] or NULL (skip rendering)
+ *   depth        float[N][H][W]    or NULL
+ *   reward       double[N], terminated / truncated uint8[N]  (may be NULL)                    */
+int mwb_step(mwb_handle* h, const int32_t* actions, const double* step_params, uint8_t* obs,
+             float* depth, double* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
+
+/* render_obs / render_depth without stepping (observation returned by reset()) */
+int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* stream);
+
+/* ---- state exchange (env.agent.pos, env.entities[i].pos ... views; checkpointing) ------ */
+int mwb_get_state(mwb_handle* h, const mwb_state_view* out);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t mwb_launch_count(mwb_handle* h);
+
+/* sizeof() of every ABI struct, in declaration order (config, params, tex_desc, mesh_desc,
+ * room, quad, seg, proto, entity, op, geometry, world, rng_state, state_view): lets a
+ * binding verify its mirror of this header.  Returns the number of entries written. */
+int mwb_abi_sizes(int32_t* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MWB_H_ */

@@ -84,19 +84,26 @@ class Texture:
             return cls._variants[name]
 
     @classmethod
-    def get_variant(cls, name, idx):
-        key = (name, idx)
+    def family(cls, name):
+        """All variants of `name`, registered with consecutive engine ids (the device-side
+        domain-rand draw selects `first_id + integers(0, n)`)."""
+        n = cls.num_variants(name)
         with _lock:
-            tex = cls._by_key.get(key)
-            if tex is None:
-                texels = cls._read_variant(name, idx + 1)
-                if texels is None:
-                    raise ValueError('failed to load texture "%s" variant %d' % (name, idx + 1))
-                tex = Texture(name, idx, texels)
-                tex.tex_id = len(cls.registry)
-                cls.registry.append(tex)
-                cls._by_key[key] = tex
-            return tex
+            if (name, 0) not in cls._by_key:
+                for idx in range(n):
+                    texels = cls._read_variant(name, idx + 1)
+                    tex = Texture(name, idx, texels)
+                    tex.tex_id = len(cls.registry)
+                    cls.registry.append(tex)
+                    cls._by_key[(name, idx)] = tex
+            return [cls._by_key[(name, idx)] for idx in range(n)]
+
+    @classmethod
+    def get_variant(cls, name, idx):
+        fam = cls.family(name)
+        if not 0 <= idx < len(fam):
+            raise ValueError('failed to load texture "%s" variant %d' % (name, idx + 1))
+        return fam[idx]
 
     @classmethod
     def get(cls, tex_name, rng=None):

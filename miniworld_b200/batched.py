@@ -1,0 +1,213 @@
+"""BatchedMiniWorld: N independent MiniWorld environments stepped by one C-ABI call.
+
+This is the hot path of the package: `step(actions)` = K1 (physics / reward / auto-reset,
+one thread per env) + K2 (first-person render, one block per env) through `mwb_step`.
+Per-environment semantics are exactly those of the reference's `MiniWorldEnv.reset/step`
+(miniworld.py:544-604, 670-730) plus the level's own `step()` rule, for every env:
+
+  * env i seeded with `reset(seed=[...])` owns the numpy stream
+    Generator(PCG64(SeedSequence(seed_i))), continued across unseeded resets;
+  * levels with a fixed room layout (Hallway, OneRoom, FourRooms, PickupObjects) reset
+    entirely on the device from the lowered `device_program` (csrc/reset.cuh);
+  * levels whose topology is random per episode (Maze) generate worlds with the level's
+    Python `_gen_world()` on the host (same numpy stream) and upload them (`mwb_set_world`);
+  * `autoreset=True` gives Gymnasium "next-step" auto-reset: the step after a
+    terminated|truncated step resets that env (action ignored, reward 0).
+
+Outputs are torch CUDA tensors by default (zero-copy from the kernels); `step_host`
+performs the same step with pinned host buffers for callers that want numpy.
+"""
+import numpy as np
+
+from . import pack
+from .engine import Engine, RULE_GOAL, RULE_NONE, RULE_PICKUP, generator_from_state, rng_state_of, RNG_DTYPE
+from .envs import LEVELS
+from .program import ResetProgram
+
+
+def _resolve_level(level):
+    if isinstance(level, str):
+        if level not in LEVELS:
+            raise KeyError("unknown level id %r (known: %s)" % (level, ", ".join(sorted(LEVELS))))
+        return LEVELS[level]
+    return level
+
+
+class BatchedMiniWorld:
+    def __init__(self, level, num_envs, obs_width=80, obs_height=60, domain_rand=False, autoreset=True,
+                 msaa_samples=8, device=0, lib_path=None, want_depth=False, level_kwargs=None):
+        self.level_cls = _resolve_level(level)
+        self.level_kwargs = dict(level_kwargs or {})
+        self.num_envs = int(num_envs)
+        self.obs_width, self.obs_height = int(obs_width), int(obs_height)
+        self.domain_rand = bool(domain_rand)
+        self.want_depth = bool(want_depth)
+        self.device = int(device)
+
+        # a definition-only instance of the level: layout, params, rule, action space
+        self.proto_env = self.level_cls(device=None, domain_rand=self.domain_rand, obs_width=obs_width,
+                                        obs_height=obs_height, **self.level_kwargs)
+        pe = self.proto_env
+        self.action_space = pe.action_space
+        self.single_observation_space = pe.observation_space
+        self.max_episode_steps = pe.max_episode_steps
+        rule = getattr(pe, "device_rule", None)
+        if rule is None:
+            raise TypeError("%s has no `device_rule`; use world.MiniWorldEnv (single env) for levels whose "
+                            "step() rule is not lowered" % self.level_cls.__name__)
+        rule = (RULE_GOAL, rule[1]) if rule[0] == "goal" else (RULE_PICKUP, rule[1]) if rule[0] == "pickup" \
+            else (RULE_NONE, 0)
+        self.device_reset = getattr(pe, "device_program", None) is not None
+
+        rooms, quads, segs = pack.pack_geometry(pe)
+        if self.device_reset:
+            self.program = ResetProgram()
+            pe.device_program(self.program)
+            protos = self.program.proto_array()
+            max_ents = max(8, self.program.num_placed)
+            caps = (len(rooms), len(quads), len(segs))
+        else:
+            self.program = None
+            protos = None
+            max_ents = 8
+            caps = tuple(int(1.25 * n) + 4 for n in (len(rooms), len(quads), len(segs)))
+        self.engine = Engine(self.num_envs, obs_width, obs_height, msaa_samples,
+                             shared_geometry=self.device_reset, max_rooms=caps[0], max_quads=caps[1],
+                             max_segs=caps[2], max_ents=max_ents, rule=rule, domain_rand=self.domain_rand,
+                             max_episode_steps=self.max_episode_steps, autoreset=autoreset and self.device_reset,
+                             device=device, lib_path=lib_path)
+        self.autoreset = bool(autoreset)
+        eng = self.engine
+        eng.sync_assets()
+        eng.set_params(pe.params)
+        if self.device_reset:
+            eng.set_protos(protos)
+            eng.set_template(rooms, quads, segs)
+            eng.set_program(self.program.op_array())
+        else:
+            # host-reset levels: one worker env per slot keeps that env's RNG stream
+            self._workers = [None] * self.num_envs
+            self._host_done = np.zeros(self.num_envs, bool)
+        self._seeded = False
+        self._torch = None
+        self._bufs = None
+
+    # ------------------------------------------------------------------ buffers
+    def _ensure_torch(self):
+        if self._torch is None:
+            import torch
+            self._torch = torch
+            dev = torch.device("cuda", self.device)
+            N, H, W = self.num_envs, self.obs_height, self.obs_width
+            self._bufs = dict(
+                obs=torch.zeros((N, H, W, 3), dtype=torch.uint8, device=dev),
+                depth=torch.zeros((N, H, W, 1), dtype=torch.float32, device=dev) if self.want_depth else None,
+                reward=torch.zeros(N, dtype=torch.float64, device=dev),
+                terminated=torch.zeros(N, dtype=torch.uint8, device=dev),
+                truncated=torch.zeros(N, dtype=torch.uint8, device=dev),
+                actions=torch.zeros(N, dtype=torch.int32, device=dev),
+            )
+        return self._torch
+
+    # ------------------------------------------------------------------ reset
+    def reset(self, seed=None, env_ids=None):
+        """Reset all (or the listed) envs.  `seed`: int base (env i gets seed + i), a sequence
+        of per-env seeds, or None to continue each env's stream.  Returns (obs, info)."""
+        ids = np.arange(self.num_envs, dtype=np.int32) if env_ids is None else np.asarray(env_ids, np.int32)
+        if seed is not None:
+            seeds = [int(seed) + int(i) for i in ids] if np.isscalar(seed) else [int(s) for s in seed]
+            assert len(seeds) == len(ids)
+        else:
+            seeds = None
+            if not self._seeded:
+                seeds = [int(s) for s in np.random.SeedSequence().generate_state(len(ids))]
+        if self.device_reset:
+            if seeds is not None:
+                states = np.array([rng_state_of(s) for s in seeds], RNG_DTYPE)
+                self.engine.seed(ids, states)
+            self.engine.reset(None if env_ids is None else ids)
+        else:
+            self._host_reset(ids, seeds)
+        self._seeded = True
+        return self.render(), {}
+
+    def _host_reset(self, ids, seeds, hold=False):
+        worlds = []
+        for k, i in enumerate(ids):
+            w = self._workers[i]
+            if w is None:
+                w = self._workers[i] = self.level_cls.__new__(self.level_cls)
+                w.__dict__.update({k2: v for k2, v in self.proto_env.__dict__.items()
+                                   if k2 not in ("_np_random", "agent", "entities", "rooms", "wall_segs")})
+                w._np_random = None
+            w.reset(seed=None if seeds is None else seeds[k])
+            worlds.append(pack.pack_world(w))
+            worlds[-1]["hold"] = int(hold)
+        # one proto table for the handle: per-env protos are identical for these levels
+        self.engine.sync_assets()
+        self.engine.set_protos(worlds[0]["protos"])
+        self.engine.set_world(ids, worlds)
+
+    # ------------------------------------------------------------------ step / render
+    def step(self, actions):
+        """actions: int tensor / array [N].  Returns (obs, reward, terminated, truncated, info)
+        as torch CUDA tensors; obs is uint8 [N, H, W, 3] (and info['depth'] when want_depth)."""
+        torch = self._ensure_torch()
+        b = self._bufs
+        if isinstance(actions, torch.Tensor):
+            b["actions"].copy_(actions.to(torch.int32), non_blocking=True)
+        else:
+            b["actions"].copy_(torch.as_tensor(np.asarray(actions, np.int32)), non_blocking=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if not self.device_reset and self.autoreset and self._host_done.any():
+            self._host_reset(np.nonzero(self._host_done)[0].astype(np.int32), None, hold=True)
+            self._host_done[:] = False
+        self.engine.step(b["actions"], obs=b["obs"], depth=b["depth"], reward=b["reward"],
+                         terminated=b["terminated"], truncated=b["truncated"], stream=stream)
+        if not self.device_reset and self.autoreset:
+            self._host_done = (b["terminated"] | b["truncated"]).bool().cpu().numpy()
+        info = {"depth": b["depth"]} if self.want_depth else {}
+        return b["obs"], b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
+
+    def step_host(self, actions, out=None, render=True):
+        """Same step with HOST buffers end to end (numpy in, numpy out): actions are copied
+        host->device and obs / reward / flags device->host inside the call."""
+        N, H, W = self.num_envs, self.obs_height, self.obs_width
+        if out is None:
+            out = dict(obs=np.zeros((N, H, W, 3), np.uint8), reward=np.zeros(N), terminated=np.zeros(N, np.uint8),
+                       truncated=np.zeros(N, np.uint8),
+                       depth=np.zeros((N, H, W, 1), np.float32) if self.want_depth else None)
+        acts = np.ascontiguousarray(actions, np.int32)
+        if not self.device_reset and self.autoreset and self._host_done.any():
+            self._host_reset(np.nonzero(self._host_done)[0].astype(np.int32), None, hold=True)
+            self._host_done[:] = False
+        self.engine.step(acts, obs=out["obs"] if render else None, depth=out.get("depth") if render else None,
+                         reward=out["reward"], terminated=out["terminated"], truncated=out["truncated"])
+        if not self.device_reset and self.autoreset:
+            self._host_done = (out["terminated"] | out["truncated"]).astype(bool)
+        return out
+
+    def render(self):
+        torch = self._ensure_torch()
+        b = self._bufs
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.engine.render(obs=b["obs"], depth=b["depth"], stream=stream)
+        return b["obs"]
+
+    def render_depth(self):
+        torch = self._ensure_torch()
+        dev = torch.device("cuda", self.device)
+        d = torch.zeros((self.num_envs, self.obs_height, self.obs_width, 1), dtype=torch.float32, device=dev)
+        self.engine.render(depth=d, stream=torch.cuda.current_stream(self.device).cuda_stream)
+        return d
+
+    # ------------------------------------------------------------------ state views
+    def get_state(self, **kw):
+        return self.engine.get_state(**kw)
+
+    def np_random(self, i):
+        """numpy Generator positioned where env i's device stream currently is."""
+        return generator_from_state(self.engine.get_state(rng=True)["rng"][i])
+
+    def close(self):
+        self.engine.close()

@@ -1,0 +1,128 @@
+// libm_sincos.cuh -- double-precision sin / cos that reproduce this image's glibc 2.39
+// (x86_64, FMA multiarch variant) bit for bit.
+//
+// Why: the reference computes the agent's heading vectors with Python's math.cos / math.sin
+// (reference entity.py:95-113), i.e. glibc libm.  glibc's routines are < 1 ULP but not
+// correctly rounded (about 0.13 % of arguments differ from the correctly rounded value), so
+// neither CUDA's cos() nor a correctly rounded routine gives bit-identical agent poses
+// (hard part 2).  This file restates glibc's algorithm -- the IBM
+// Accurate Mathematical Library scheme: Cody-Waite reduction by pi/2 in four pieces, a
+// 440-entry sin/cos table indexed by `big + |x|`, degree-5/6 polynomial corrections, Taylor
+// branch for |x| < 0.126 -- with every fused multiply-add placed exactly where gcc contracts
+// the glibc sources for -mfma (read off the disassembly of a contracted build).  Validated
+// against libm on 60 M random arguments in +-1e5 with zero mismatches
+// (tests/test_sincos_port.py re-checks it).  Valid for |x| < 105414350.
+#pragma once
+#include "hd.h"
+
+MWB_DEVCONST double mwb_sincostab[1760] = {
+#include "sincos_table.inc"
+};
+
+namespace mwb_libm {
+
+MWB_DEV int lowword(double d) { return (int)(uint32_t)d2bits(d); }
+MWB_DEV int highword(double d) { return (int)(d2bits(d) >> 32); }
+
+// polynomial / reduction constants (bit patterns as in glibc's usncs.h / s_sin.c)
+#define MWB_SN3 (-0x1.5555555555515p-3)
+#define MWB_SN5 (0x1.11110e829872fp-7)
+#define MWB_CS2 (0x1p-1)
+#define MWB_CS4 (-0x1.5555555555535p-5)
+#define MWB_CS6 (0x1.6c16bedd9e239p-10)
+#define MWB_S1 (-0x1.5555555555555p-3)
+#define MWB_S2 (0x1.1111111110ecep-7)
+#define MWB_S3 (-0x1.a01a019db08b8p-13)
+#define MWB_S4 (0x1.71de27b9a7ed9p-19)
+#define MWB_S5 (-0x1.addffc2fcdf59p-26)
+#define MWB_BIG (0x1.8p+45)
+#define MWB_TOINT (0x1.8p+52)
+#define MWB_HPINV (0x1.45f306dc9c883p-1)
+#define MWB_MP1 (0x1.921fb58p+0)
+#define MWB_MP2 (-0x1.dde973cp-27)
+#define MWB_PP3 (-0x1.cb3b398p-55)
+#define MWB_PP4 (-0x1.d747f23e32ed7p-83)
+#define MWB_HP0 (0x1.921fb54442d18p+0)
+#define MWB_HP1 (0x1.1a62633145c07p-54)
+
+MWB_DEV double do_cos(double x, double dx) {
+  if (x < 0) dx = -dx;
+  double ax = fabs(x);
+  double u = d_add(MWB_BIG, ax);
+  x = d_add(d_sub(ax, d_sub(u, MWB_BIG)), dx);
+  int k = lowword(u) * 4;
+  double xx = d_mul(x, x);
+  double s = d_fma(d_mul(x, xx), d_fma(xx, MWB_SN5, MWB_SN3), x);
+  double c = d_mul(xx, d_fma(xx, d_fma(xx, MWB_CS6, MWB_CS4), MWB_CS2));
+  double sn = mwb_sincostab[k], ssn = mwb_sincostab[k + 1], cs = mwb_sincostab[k + 2], ccs = mwb_sincostab[k + 3];
+  double cor = d_fma(-sn, s, d_fma(-cs, c, d_fma(-s, ssn, ccs)));
+  return d_add(cs, cor);
+}
+
+MWB_DEV double do_sin(double x, double dx) {
+  double xold = x;
+  if (fabs(x) < 0.126) {
+    double xx = d_mul(x, x);
+    double p = d_fma(d_fma(d_fma(d_fma(MWB_S5, xx, MWB_S4), xx, MWB_S3), xx, MWB_S2), xx, MWB_S1);
+    double q = d_fma(p, x, -d_mul(0.5, dx));
+    double t = d_fma(xx, q, dx);
+    return d_add(x, t);
+  }
+  if (x <= 0) dx = -dx;
+  double ax = fabs(x);
+  double u = d_add(MWB_BIG, ax);
+  x = d_sub(ax, d_sub(u, MWB_BIG));
+  int k = lowword(u) * 4;
+  double xx = d_mul(x, x);
+  double s = d_add(x, d_fma(d_mul(x, xx), d_fma(xx, MWB_SN5, MWB_SN3), dx));
+  double c = d_fma(x, dx, d_mul(xx, d_fma(xx, d_fma(xx, MWB_CS6, MWB_CS4), MWB_CS2)));
+  double sn = mwb_sincostab[k], ssn = mwb_sincostab[k + 1], cs = mwb_sincostab[k + 2], ccs = mwb_sincostab[k + 3];
+  double cor = d_fma(s, cs, d_fma(-c, sn, d_fma(s, ccs, ssn)));
+  return copysign(d_add(sn, cor), xold);
+}
+
+MWB_DEV int reduce_sincos(double x, double* a, double* da) {
+  double t = d_fma(x, MWB_HPINV, MWB_TOINT);
+  double xn = d_sub(t, MWB_TOINT);
+  int n = lowword(t) & 3;
+  double y = d_fma(-xn, MWB_MP2, d_fma(-xn, MWB_MP1, x));
+  double t2 = d_fma(-MWB_PP3, xn, y);
+  double db = d_fma(-MWB_PP3, xn, d_sub(y, t2));
+  double b = d_fma(-MWB_PP4, xn, t2);
+  double db2 = d_fma(-MWB_PP4, xn, d_sub(t2, b));
+  *a = b;
+  *da = d_add(db2, db);
+  return n;
+}
+
+MWB_DEV double do_sincos(double a, double da, int n) {
+  double r = (n & 1) ? do_cos(a, da) : do_sin(a, da);
+  return (n & 2) ? -r : r;
+}
+
+MWB_DEV double sin_glibc(double x) {
+  int k = 0x7fffffff & highword(x);
+  double a, da;
+  if (k < 0x3e500000) return x;
+  if (k < 0x3feb6000) return do_sin(x, 0);
+  if (k < 0x400368fd) return copysign(do_cos(d_sub(MWB_HP0, fabs(x)), MWB_HP1), x);
+  int n = reduce_sincos(x, &a, &da);
+  return do_sincos(a, da, n);
+}
+
+MWB_DEV double cos_glibc(double x) {
+  int k = 0x7fffffff & highword(x);
+  double a, da;
+  if (k < 0x3e400000) return 1.0;
+  if (k < 0x3feb6000) return do_cos(x, 0);
+  if (k < 0x400368fd) {
+    double y = d_sub(MWB_HP0, fabs(x));
+    a = d_add(y, MWB_HP1);
+    da = d_add(d_sub(y, a), MWB_HP1);
+    return do_sin(a, da);
+  }
+  int n = reduce_sincos(x, &a, &da);
+  return do_sincos(a, da, n + 1);
+}
+
+}  // namespace mwb_libm

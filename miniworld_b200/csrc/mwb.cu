@@ -1,0 +1,788 @@
+// mwb.cu -- libmwb.so: the C ABI of include/mwb.h on top of the CUDA kernels.
+//
+//   step_kernel   (K1)  physics.cuh + reset.cuh   one thread per env
+//   render_kernel (K2)  raster.cuh                one block per env, one warp per 8x8 tile
+//   scatter / gather    host <-> SoA state exchange for host-generated worlds
+//
+// Built for sm_100a only.  The same file can be compiled by g++ with -DMWB_HOSTSIM into the
+// test-only host simulator (tests/hostsim): there every "launch" is a plain loop over the
+// identical MWB_DEV functions.  That build is a debugging aid for a box without a GPU; it is
+// not part of libmwb.so and nothing in the package loads it.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mwb.h"
+#include "raster.cuh"
+#include "reset.cuh"
+
+#ifndef MWB_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+
+#define MWB_MAX_ENTS_CAP 16
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------ memory space shims
+#ifdef MWB_HOSTSIM
+typedef void* stream_t;
+static int dev_alloc(void** p, size_t n) {
+  *p = calloc(1, n ? n : 1);
+  return *p ? 0 : -1;
+}
+static void dev_free(void* p) { free(p); }
+static int h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); return 0; }
+static int d2h(void* h, const void* d, size_t n, stream_t) { memcpy(h, d, n); return 0; }
+static int dev_memset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+static int sync_stream(stream_t) { return 0; }
+static bool is_device_ptr(const void*) { return false; }
+#else
+typedef cudaStream_t stream_t;
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(MWB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+static int dev_alloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+static void dev_free(void* p) { cudaFree(p); }
+static int h2d(void* d, const void* h, size_t n, stream_t s) {
+  return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) == cudaSuccess ? 0 : -1;
+}
+static int d2h(void* h, const void* d, size_t n, stream_t s) {
+  return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) == cudaSuccess ? 0 : -1;
+}
+static int dev_memset(void* d, int v, size_t n) { return cudaMemset(d, v, n) == cudaSuccess ? 0 : -1; }
+static int sync_stream(stream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+#endif
+
+// ------------------------------------------------------------------ exchange records
+struct WorldUpload {   // AoS image of one env's dynamic state (host <-> device staging)
+  int32_t env, num_slots, agent_slot, carrying, step_count, num_picked, hold, pad1;
+  double cam[4];
+  double envp[12];
+  mwb_entity ents[MWB_MAX_ENTS_CAP];
+  mwb_rng_state rng;
+};
+
+struct mwb_handle {
+  mwb_config cfg;
+  DevState S;
+  RenderAssets A;
+  std::vector<void*> allocs;
+  stream_t stream;
+  int64_t launches;
+  // staging
+  int32_t* d_actions;
+  double* d_step_params;
+  double* d_reward;
+  uint8_t* d_term;
+  uint8_t* d_trunc;
+  uint8_t* d_obs;
+  float* d_depth;
+  int32_t* d_ids;
+  int* d_overflow;
+  WorldUpload* d_upload;
+  int tri_cap;
+  bool have_params, have_protos, have_template;
+  // asset storage
+  void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops;
+};
+
+template <typename T>
+static int alloc_arr(mwb_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  if (dev_alloc(&q, count * sizeof(T)) != 0) return fail(MWB_ECUDA, "device allocation failed");
+  dev_memset(q, 0, count * sizeof(T));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+// ------------------------------------------------------------------ kernels / loops
+MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const double* step_params, double* reward,
+                      uint8_t* term, uint8_t* trunc) {
+  StepOut o;
+  const int nr = S.needs_reset[i];
+  if (nr == 2 || (nr == 1 && S.autoreset)) {
+    // "next-step" auto-reset: this step performs the reset instead of stepping.  nr == 2: the
+    // host already uploaded the fresh world (mwb_set_world with hold = 1)
+    if (nr == 1) device_reset(S, i);
+    S.needs_reset[i] = 0;
+    o.reward = 0.0;
+    o.terminated = 0;
+    o.truncated = 0;
+  } else {
+    double fs, fd, ts;
+    if (step_params) {
+      fs = step_params[i * 3 + 0];
+      fd = step_params[i * 3 + 1];
+      ts = step_params[i * 3 + 2];
+    } else if (S.domain_rand) {   // params.sample(rand, ...) x3, always, before the action is read
+      NpRng r = load_rng(S, i);
+      fs = rng_uniform(r, S.params.forward_step_lo, S.params.forward_step_rng);
+      fd = rng_uniform(r, S.params.forward_drift_lo, S.params.forward_drift_rng);
+      ts = rng_uniform(r, S.params.turn_step_lo, S.params.turn_step_rng);
+      store_rng(S, i, r);
+    } else {
+      fs = S.params.forward_step;
+      fd = S.params.forward_drift;
+      ts = S.params.turn_step;
+    }
+    o = physics_step(S, i, actions[i], fs, fd, ts);
+    if (S.autoreset && (o.terminated || o.truncated)) S.needs_reset[i] = 1;
+  }
+  if (reward) reward[i] = o.reward;
+  if (term) term[i] = (uint8_t)o.terminated;
+  if (trunc) trunc[i] = (uint8_t)o.truncated;
+}
+
+MWB_DEV void scatter_one(const DevState& S, const WorldUpload& u) {
+  const size_t N = S.N;
+  const int i = u.env;
+  S.num_slots[i] = u.num_slots;
+  S.agent_slot[i] = u.agent_slot;
+  S.carrying[i] = u.carrying;
+  S.step_count[i] = u.step_count;
+  S.num_picked[i] = u.num_picked;
+  S.needs_reset[i] = u.hold ? 2 : 0;
+  S.ghost_slot[i] = -1;
+  for (int k = 0; k < 4; ++k) S.cam[k * N + i] = u.cam[k];
+  for (int k = 0; k < 12; ++k) S.envp[k * N + i] = u.envp[k];
+  for (int e = 0; e < S.E; ++e) {
+    const bool live = e < u.num_slots && e < MWB_MAX_ENTS_CAP;
+    S.ent_proto[e * N + i] = live ? u.ents[e].proto : -1;
+    if (!live) continue;
+    S.ent_px[e * N + i] = u.ents[e].pos[0];
+    S.ent_py[e * N + i] = u.ents[e].pos[1];
+    S.ent_pz[e * N + i] = u.ents[e].pos[2];
+    S.ent_dir[e * N + i] = u.ents[e].dir;
+    for (int k = 0; k < 3; ++k) S.ent_col[((size_t)e * 3 + k) * N + i] = u.ents[e].color[k];
+  }
+  if (!S.shared_geom) {
+    const mwb_room* rooms = S.rooms + (size_t)i * S.R;
+    for (int r = 0; r < S.num_rooms[i]; ++r)
+      for (int k = 0; k < 3; ++k) S.room_tex[((size_t)i * S.R + r) * 3 + k] = rooms[r].tex_id[k];
+  } else {
+    for (int r = 0; r < S.num_rooms[0]; ++r)
+      for (int k = 0; k < 3; ++k) S.room_tex[((size_t)i * S.R + r) * 3 + k] = S.rooms[r].tex_id[k];
+  }
+}
+
+MWB_DEV void gather_one(const DevState& S, int i, WorldUpload& u) {
+  const size_t N = S.N;
+  u.env = i;
+  u.num_slots = S.num_slots[i];
+  u.agent_slot = S.agent_slot[i];
+  u.carrying = S.carrying[i];
+  u.step_count = S.step_count[i];
+  u.num_picked = S.num_picked[i];
+  for (int k = 0; k < 4; ++k) u.cam[k] = S.cam[k * N + i];
+  for (int k = 0; k < 12; ++k) u.envp[k] = S.envp[k * N + i];
+  for (int e = 0; e < MWB_MAX_ENTS_CAP; ++e) {
+    mwb_entity& d = u.ents[e];
+    if (e >= S.E) {
+      d.proto = -1;
+      continue;
+    }
+    d.proto = S.ent_proto[e * N + i];
+    d.pos[0] = S.ent_px[e * N + i];
+    d.pos[1] = S.ent_py[e * N + i];
+    d.pos[2] = S.ent_pz[e * N + i];
+    d.dir = S.ent_dir[e * N + i];
+    for (int k = 0; k < 3; ++k) d.color[k] = S.ent_col[((size_t)e * 3 + k) * N + i];
+  }
+  u.rng.state_hi = S.rng_s_hi[i];
+  u.rng.state_lo = S.rng_s_lo[i];
+  u.rng.inc_hi = S.rng_inc_hi[i];
+  u.rng.inc_lo = S.rng_inc_lo[i];
+  u.rng.has_uint32 = S.rng_has32[i];
+  u.rng.uinteger = S.rng_cache[i];
+}
+
+#ifndef MWB_HOSTSIM
+__global__ void step_kernel(DevState S, const int32_t* actions, const double* step_params, double* reward,
+                            uint8_t* term, uint8_t* trunc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S.N) step_one(S, i, actions, step_params, reward, term, trunc);
+}
+__global__ void reset_kernel(DevState S, const int32_t* ids, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = ids ? ids[t] : t;
+  device_reset(S, i);
+  S.needs_reset[i] = 0;
+}
+__global__ void scatter_kernel(DevState S, const WorldUpload* u, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) scatter_one(S, u[t]);
+}
+__global__ void gather_kernel(DevState S, WorldUpload* u) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S.N) gather_one(S, i, u[i]);
+}
+__global__ void seed_kernel(DevState S, const WorldUpload* u, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = u[t].env;
+  S.rng_s_hi[i] = u[t].rng.state_hi;
+  S.rng_s_lo[i] = u[t].rng.state_lo;
+  S.rng_inc_hi[i] = u[t].rng.inc_hi;
+  S.rng_inc_lo[i] = u[t].rng.inc_lo;
+  S.rng_has32[i] = u[t].rng.has_uint32;
+  S.rng_cache[i] = u[t].rng.uinteger;
+}
+#else
+// host simulator: sequential stand-in for render_kernel built from the same MWB_DEV functions
+struct VecTris {
+  const TriRec* t;
+  const TriRec& operator()(uint32_t slot) const { return t[slot]; }
+};
+static void hostsim_render(const DevState& S, const RenderAssets& A, uint8_t* obs, float* depth) {
+  const int W = S.obs_w, H = S.obs_h, M = S.msaa;
+  for (int i = 0; i < S.N; ++i) {
+    Camera cam = make_camera(S, i);
+    ItemMap imap = build_item_map(S, i);
+    std::vector<TriRec> tris;
+    for (int idx = 0; idx < imap.n_items; ++idx) {
+      Item it;
+      fetch_item(S, A, i, imap, idx, it);
+      TriRec loc[2];
+      int cnt = item_triangles(cam, it, W, H, loc);
+      for (int k = 0; k < cnt; ++k) tris.push_back(loc[k]);
+    }
+    VecTris fetch{tris.data()};
+    for (int py = 0; py < H; ++py)
+      for (int px = 0; px < W; ++px) {
+        uint32_t keys[16];
+        for (int s = 0; s < M; ++s) keys[s] = MWB_SKY_KEY;
+        for (size_t j = 0; j < tris.size(); ++j) raster_pixel(tris[j], (int)j, px, py, M, keys);
+        if (obs) {
+          uint8_t rgb[3];
+          resolve_pixel(A, cam, fetch, keys, M, px, py, rgb);
+          memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
+        }
+        if (depth) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(keys[0] >> 16);
+      }
+  }
+}
+#endif
+
+// ------------------------------------------------------------------ ABI: lifetime
+extern "C" const char* mwb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
+  if (!cfg || !out) return fail(MWB_EINVAL, "null argument");
+  if (cfg->abi_version != MWB_ABI_VERSION) return fail(MWB_EABI, "abi_version mismatch");
+  if (cfg->num_envs <= 0 || cfg->obs_width <= 0 || cfg->obs_height <= 0) return fail(MWB_EINVAL, "bad sizes");
+  if (cfg->msaa_samples != 1 && cfg->msaa_samples != 4 && cfg->msaa_samples != 8)
+    return fail(MWB_EINVAL, "msaa_samples must be 1, 4 or 8");
+  if (cfg->max_ents <= 0 || cfg->max_ents > MWB_MAX_ENTS_CAP) return fail(MWB_ECAPACITY, "max_ents out of range");
+  if (cfg->max_rooms <= 0 || cfg->max_quads <= 0 || cfg->max_segs <= 0) return fail(MWB_EINVAL, "bad capacities");
+#ifndef MWB_HOSTSIM
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(MWB_ENOCUDA, "no CUDA device: libmwb has no CPU execution path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MWB_EINVAL, "bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+#endif
+  mwb_handle* h = new mwb_handle();
+  h->cfg = *cfg;
+  h->launches = 0;
+  h->have_params = h->have_protos = h->have_template = false;
+  h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
+  h->protos = h->ops = nullptr;
+  memset(&h->S, 0, sizeof(DevState));
+  memset(&h->A, 0, sizeof(RenderAssets));
+#ifndef MWB_HOSTSIM
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(MWB_ECUDA, "cudaStreamCreate failed");
+  }
+#else
+  h->stream = nullptr;
+#endif
+  DevState& S = h->S;
+  const size_t N = cfg->num_envs, E = cfg->max_ents;
+  S.N = cfg->num_envs;
+  S.E = cfg->max_ents;
+  S.R = cfg->max_rooms;
+  S.Q = cfg->max_quads;
+  S.S = cfg->max_segs;
+  S.shared_geom = cfg->shared_geometry;
+  S.obs_w = cfg->obs_width;
+  S.obs_h = cfg->obs_height;
+  S.msaa = cfg->msaa_samples;
+  S.rule_kind = cfg->rule_kind;
+  S.rule_arg = cfg->rule_arg;
+  S.domain_rand = cfg->domain_rand;
+  S.max_episode_steps = cfg->max_episode_steps;
+  S.autoreset = cfg->autoreset;
+  const size_t G = cfg->shared_geometry ? 1 : N;
+  int rc = 0;
+#define AL(field, count) if (!rc) rc = alloc_arr(h, &S.field, (count))
+  AL(ent_proto, E * N); AL(ent_px, E * N); AL(ent_py, E * N); AL(ent_pz, E * N); AL(ent_dir, E * N);
+  AL(ent_col, E * 3 * N); AL(num_slots, N); AL(agent_slot, N); AL(carrying, N); AL(step_count, N);
+  AL(num_picked, N); AL(needs_reset, N); AL(cam, 4 * N); AL(envp, 12 * N); AL(ghost_slot, N);
+  AL(ghost_proto, N); AL(ghost_pose, 4 * N); AL(ghost_col, 3 * N);
+  AL(rng_s_hi, N); AL(rng_s_lo, N); AL(rng_inc_hi, N); AL(rng_inc_lo, N); AL(rng_has32, N); AL(rng_cache, N);
+  AL(num_rooms, G); AL(num_quads, G); AL(num_segs, G);
+  AL(rooms, G * S.R); AL(quads, G * S.Q); AL(segs, G * S.S); AL(room_tex, N * S.R * 3);
+#undef AL
+  if (!rc) rc = alloc_arr(h, &h->d_actions, N);
+  if (!rc) rc = alloc_arr(h, &h->d_step_params, 3 * N);
+  if (!rc) rc = alloc_arr(h, &h->d_reward, N);
+  if (!rc) rc = alloc_arr(h, &h->d_term, N);
+  if (!rc) rc = alloc_arr(h, &h->d_trunc, N);
+  if (!rc) rc = alloc_arr(h, &h->d_obs, N * (size_t)S.obs_w * S.obs_h * 3);
+  if (!rc) rc = alloc_arr(h, &h->d_depth, N * (size_t)S.obs_w * S.obs_h);
+  if (!rc) rc = alloc_arr(h, &h->d_ids, N);
+  if (!rc) rc = alloc_arr(h, &h->d_overflow, 1);
+  if (!rc) rc = alloc_arr(h, &h->d_upload, N);
+  if (rc) {
+    mwb_destroy(h);
+    return rc;
+  }
+  // -1 in every entity slot / ghost
+  dev_memset(S.ent_proto, 0xFF, E * N * sizeof(int32_t));
+  dev_memset(S.ghost_slot, 0xFF, N * sizeof(int32_t));
+  dev_memset(S.carrying, 0xFF, N * sizeof(int32_t));
+  h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);
+  if (h->tri_cap > 1500) h->tri_cap = 1500;
+#ifndef MWB_HOSTSIM
+  const int smem = h->tri_cap * (int)sizeof(TriRec);
+  CK(cudaFuncSetAttribute(render_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#endif
+  *out = h;
+  return MWB_OK;
+}
+
+extern "C" int mwb_destroy(mwb_handle* h) {
+  if (!h) return MWB_OK;
+#ifndef MWB_HOSTSIM
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+#endif
+  for (void* p : h->allocs) dev_free(p);
+  void* extra[] = {h->tex_desc, h->texels, h->mesh_desc, h->mesh_pos, h->mesh_nrm, h->mesh_uv, h->mesh_rgb,
+                   h->protos, h->ops};
+  for (void* p : extra)
+    if (p) dev_free(p);
+#ifndef MWB_HOSTSIM
+  cudaStreamDestroy(h->stream);
+#endif
+  delete h;
+  return MWB_OK;
+}
+
+extern "C" int64_t mwb_launch_count(mwb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int mwb_abi_sizes(int32_t* out, int cap) {
+  const int32_t sz[] = {(int32_t)sizeof(mwb_config), (int32_t)sizeof(mwb_params), (int32_t)sizeof(mwb_tex_desc),
+                        (int32_t)sizeof(mwb_mesh_desc), (int32_t)sizeof(mwb_room), (int32_t)sizeof(mwb_quad),
+                        (int32_t)sizeof(mwb_seg), (int32_t)sizeof(mwb_proto), (int32_t)sizeof(mwb_entity),
+                        (int32_t)sizeof(mwb_op), (int32_t)sizeof(mwb_geometry), (int32_t)sizeof(mwb_world),
+                        (int32_t)sizeof(mwb_rng_state), (int32_t)sizeof(mwb_state_view)};
+  const int n = (int)(sizeof(sz) / sizeof(sz[0]));
+  for (int k = 0; k < n && k < cap; ++k) out[k] = sz[k];
+  return n;
+}
+
+static int replace_buf(void** slot, const void* host, size_t bytes, stream_t s) {
+  if (*slot) dev_free(*slot);
+  *slot = nullptr;
+  if (dev_alloc(slot, bytes) != 0) return fail(MWB_ECUDA, "device allocation failed");
+  if (bytes && h2d(*slot, host, bytes, s) != 0) return fail(MWB_ECUDA, "upload failed");
+  return sync_stream(s) == 0 ? 0 : fail(MWB_ECUDA, "sync failed");
+}
+
+// ------------------------------------------------------------------ ABI: assets
+extern "C" int mwb_upload_textures(mwb_handle* h, const mwb_tex_desc* descs, int n, const uint8_t* rgb) {
+  if (!h || !descs || n <= 0 || !rgb) return fail(MWB_EINVAL, "bad arguments");
+  std::vector<TexDev> td(n);
+  std::vector<uint32_t> pool;
+  for (int t = 0; t < n; ++t) {
+    int w = descs[t].width, hgt = descs[t].height;
+    if (w <= 0 || hgt <= 0) return fail(MWB_EINVAL, "bad texture size");
+    const uint8_t* src = rgb + descs[t].offset;
+    // level 0: flip rows so that row 0 is the image bottom (pyglet uploads bottom-up)
+    std::vector<uint32_t> cur((size_t)w * hgt);
+    for (int y = 0; y < hgt; ++y)
+      for (int x = 0; x < w; ++x) {
+        const uint8_t* p = src + ((size_t)(hgt - 1 - y) * w + x) * 3;
+        cur[(size_t)y * w + x] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | 0xFF000000u;
+      }
+    TexDev& T = td[t];
+    T.w = w;
+    T.h = hgt;
+    T.pad = 0;
+    int lev = 0;
+    for (;;) {
+      T.lw[lev] = w;
+      T.lh[lev] = hgt;
+      T.off[lev] = (int32_t)pool.size();
+      pool.insert(pool.end(), cur.begin(), cur.end());
+      ++lev;
+      if ((w == 1 && hgt == 1) || lev == MWB_MAX_LEVELS) break;
+      // glGenerateMipmap: 2x2 box filter on the 8-bit texels; odd sizes halve with floor and
+      // clamp the second tap to the last row / column
+      int nw = w > 1 ? w / 2 : 1, nh = hgt > 1 ? hgt / 2 : 1;
+      std::vector<uint32_t> nxt((size_t)nw * nh);
+      for (int y = 0; y < nh; ++y)
+        for (int x = 0; x < nw; ++x) {
+          int x0 = w > 1 ? 2 * x : 0, x1 = w > 1 ? (2 * x + 1 < w ? 2 * x + 1 : w - 1) : 0;
+          int y0 = hgt > 1 ? 2 * y : 0, y1 = hgt > 1 ? (2 * y + 1 < hgt ? 2 * y + 1 : hgt - 1) : 0;
+          uint32_t a = cur[(size_t)y0 * w + x0], b = cur[(size_t)y0 * w + x1];
+          uint32_t c = cur[(size_t)y1 * w + x0], d = cur[(size_t)y1 * w + x1];
+          uint32_t o = 0xFF000000u;
+          for (int k = 0; k < 3; ++k) {
+            uint32_t s = ((a >> (8 * k)) & 255u) + ((b >> (8 * k)) & 255u) + ((c >> (8 * k)) & 255u) + ((d >> (8 * k)) & 255u);
+            o |= ((s + 2u) >> 2) << (8 * k);
+          }
+          nxt[(size_t)y * nw + x] = o;
+        }
+      cur.swap(nxt);
+      w = nw;
+      hgt = nh;
+    }
+    T.nlev = lev;
+  }
+  int rc = replace_buf(&h->tex_desc, td.data(), td.size() * sizeof(TexDev), h->stream);
+  if (!rc) rc = replace_buf(&h->texels, pool.data(), pool.size() * sizeof(uint32_t), h->stream);
+  if (rc) return rc;
+  h->A.tex = (const TexDev*)h->tex_desc;
+  h->A.texels = (const uint32_t*)h->texels;
+  h->A.num_tex = n;
+  return MWB_OK;
+}
+
+extern "C" int mwb_upload_meshes(mwb_handle* h, const mwb_mesh_desc* descs, int n, const float* pos, const float* nrm,
+                                 const float* uv, const float* rgb) {
+  if (!h || !descs || n <= 0) return fail(MWB_EINVAL, "bad arguments");
+  std::vector<MeshDev> md(n);
+  size_t total = 0;
+  for (int m = 0; m < n; ++m) {
+    md[m].first = (int32_t)descs[m].offset;
+    md[m].count = descs[m].num_tris;
+    size_t end = (size_t)descs[m].offset + descs[m].num_tris;
+    if (end > total) total = end;
+  }
+  int rc = replace_buf(&h->mesh_desc, md.data(), md.size() * sizeof(MeshDev), h->stream);
+  if (!rc) rc = replace_buf(&h->mesh_pos, pos, total * 9 * sizeof(float), h->stream);
+  if (!rc) rc = replace_buf(&h->mesh_nrm, nrm, total * 9 * sizeof(float), h->stream);
+  if (!rc) rc = replace_buf(&h->mesh_uv, uv, total * 6 * sizeof(float), h->stream);
+  if (!rc) rc = replace_buf(&h->mesh_rgb, rgb, total * 9 * sizeof(float), h->stream);
+  if (rc) return rc;
+  h->A.meshes = (const MeshDev*)h->mesh_desc;
+  h->A.mesh_pos = (const float*)h->mesh_pos;
+  h->A.mesh_nrm = (const float*)h->mesh_nrm;
+  h->A.mesh_uv = (const float*)h->mesh_uv;
+  h->A.mesh_rgb = (const float*)h->mesh_rgb;
+  h->A.num_meshes = n;
+  return MWB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: level definition
+extern "C" int mwb_set_params(mwb_handle* h, const mwb_params* p) {
+  if (!h || !p) return fail(MWB_EINVAL, "null argument");
+  h->S.params = *p;
+  h->S.near_extra = 1.1 * p->max_forward_step;
+  h->have_params = true;
+  return MWB_OK;
+}
+
+extern "C" int mwb_set_protos(mwb_handle* h, const mwb_proto* protos, int n) {
+  if (!h || !protos || n <= 0) return fail(MWB_EINVAL, "bad arguments");
+  int rc = replace_buf(&h->protos, protos, (size_t)n * sizeof(mwb_proto), h->stream);
+  if (rc) return rc;
+  h->S.protos = (const mwb_proto*)h->protos;
+  h->S.num_protos = n;
+  h->have_protos = true;
+  return MWB_OK;
+}
+
+static int upload_geometry(mwb_handle* h, size_t g, const mwb_geometry* geo) {
+  DevState& S = h->S;
+  if (geo->num_rooms > S.R || geo->num_quads > S.Q || geo->num_segs > S.S)
+    return fail(MWB_ECAPACITY, "geometry exceeds max_rooms / max_quads / max_segs");
+  for (int r = 0; r < geo->num_rooms; ++r)
+    if (geo->rooms[r].num_edges > MWB_MAX_EDGES) return fail(MWB_ECAPACITY, "room outline too long");
+  int32_t counts[3] = {geo->num_rooms, geo->num_quads, geo->num_segs};
+  int rc = 0;
+  rc |= h2d(S.num_rooms + g, &counts[0], sizeof(int32_t), h->stream);
+  rc |= h2d(S.num_quads + g, &counts[1], sizeof(int32_t), h->stream);
+  rc |= h2d(S.num_segs + g, &counts[2], sizeof(int32_t), h->stream);
+  if (geo->num_rooms) rc |= h2d(S.rooms + g * S.R, geo->rooms, geo->num_rooms * sizeof(mwb_room), h->stream);
+  if (geo->num_quads) rc |= h2d(S.quads + g * S.Q, geo->quads, geo->num_quads * sizeof(mwb_quad), h->stream);
+  if (geo->num_segs) rc |= h2d(S.segs + g * S.S, geo->segs, geo->num_segs * sizeof(mwb_seg), h->stream);
+  rc |= sync_stream(h->stream);
+  return rc ? fail(MWB_ECUDA, "geometry upload failed") : MWB_OK;
+}
+
+extern "C" int mwb_set_template(mwb_handle* h, const mwb_geometry* g) {
+  if (!h || !g) return fail(MWB_EINVAL, "null argument");
+  if (!h->S.shared_geom) return fail(MWB_ESTATE, "handle was created with shared_geometry = 0");
+  int rc = upload_geometry(h, 0, g);
+  if (!rc) h->have_template = true;
+  return rc;
+}
+
+extern "C" int mwb_set_program(mwb_handle* h, const mwb_op* ops, int n) {
+  if (!h || !ops || n <= 0 || n > MWB_MAX_OPS) return fail(MWB_EINVAL, "bad program");
+  int rc = replace_buf(&h->ops, ops, (size_t)n * sizeof(mwb_op), h->stream);
+  if (rc) return rc;
+  h->S.ops = (const mwb_op*)h->ops;
+  h->S.num_ops = n;
+  return MWB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: reset
+static int launch_upload(mwb_handle* h, const std::vector<WorldUpload>& up, bool seed_only) {
+  const int n = (int)up.size();
+  if (h2d(h->d_upload, up.data(), n * sizeof(WorldUpload), h->stream) != 0) return fail(MWB_ECUDA, "upload failed");
+#ifndef MWB_HOSTSIM
+  if (seed_only)
+    seed_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->S, h->d_upload, n);
+  else
+    scatter_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->S, h->d_upload, n);
+  h->launches++;
+  CK(cudaGetLastError());
+#else
+  for (int t = 0; t < n; ++t) {
+    if (seed_only) {
+      const WorldUpload& u = h->d_upload[t];
+      int i = u.env;
+      h->S.rng_s_hi[i] = u.rng.state_hi;
+      h->S.rng_s_lo[i] = u.rng.state_lo;
+      h->S.rng_inc_hi[i] = u.rng.inc_hi;
+      h->S.rng_inc_lo[i] = u.rng.inc_lo;
+      h->S.rng_has32[i] = u.rng.has_uint32;
+      h->S.rng_cache[i] = u.rng.uinteger;
+    } else {
+      scatter_one(h->S, h->d_upload[t]);
+    }
+  }
+#endif
+  return sync_stream(h->stream) == 0 ? MWB_OK : fail(MWB_ECUDA, "sync failed");
+}
+
+extern "C" int mwb_seed(mwb_handle* h, const int32_t* env_ids, int n, const mwb_rng_state* states) {
+  if (!h || !states || n <= 0 || n > h->S.N) return fail(MWB_EINVAL, "bad arguments");
+  std::vector<WorldUpload> up(n);
+  for (int t = 0; t < n; ++t) {
+    memset(&up[t], 0, sizeof(WorldUpload));
+    up[t].env = env_ids ? env_ids[t] : t;
+    if (up[t].env < 0 || up[t].env >= h->S.N) return fail(MWB_EINVAL, "env id out of range");
+    up[t].rng = states[t];
+  }
+  return launch_upload(h, up, true);
+}
+
+extern "C" int mwb_reset(mwb_handle* h, const int32_t* env_ids, int n, void* stream) {
+  if (!h) return fail(MWB_EINVAL, "null handle");
+  if (!h->have_params || !h->have_protos || !h->S.ops) return fail(MWB_ESTATE, "params / protos / program not set");
+  if (h->S.shared_geom && !h->have_template) return fail(MWB_ESTATE, "template not set");
+  stream_t s = stream ? (stream_t)stream : h->stream;
+  if (!env_ids) n = h->S.N;
+  if (n <= 0 || n > h->S.N) return fail(MWB_EINVAL, "bad count");
+  const int32_t* ids = nullptr;
+  if (env_ids) {
+    if (is_device_ptr(env_ids)) {
+      ids = env_ids;
+    } else {
+      if (h2d(h->d_ids, env_ids, n * sizeof(int32_t), s) != 0) return fail(MWB_ECUDA, "upload failed");
+      ids = h->d_ids;
+    }
+  }
+#ifndef MWB_HOSTSIM
+  reset_kernel<<<(n + 63) / 64, 64, 0, s>>>(h->S, ids, n);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!stream) CK(cudaStreamSynchronize(s));
+#else
+  for (int t = 0; t < n; ++t) {
+    int i = ids ? ids[t] : t;
+    device_reset(h->S, i);
+    h->S.needs_reset[i] = 0;
+  }
+#endif
+  return MWB_OK;
+}
+
+extern "C" int mwb_set_world(mwb_handle* h, const int32_t* env_ids, int n, const mwb_world* worlds) {
+  if (!h || !worlds || n <= 0 || n > h->S.N) return fail(MWB_EINVAL, "bad arguments");
+  if (!h->have_protos) return fail(MWB_ESTATE, "protos not set");
+  std::vector<WorldUpload> up(n);
+  for (int t = 0; t < n; ++t) {
+    const mwb_world& w = worlds[t];
+    WorldUpload& u = up[t];
+    memset(&u, 0, sizeof(u));
+    u.env = env_ids ? env_ids[t] : t;
+    if (u.env < 0 || u.env >= h->S.N) return fail(MWB_EINVAL, "env id out of range");
+    if (w.num_slots > h->S.E || w.num_slots > MWB_MAX_ENTS_CAP) return fail(MWB_ECAPACITY, "too many entities");
+    if (!h->S.shared_geom) {
+      int rc = upload_geometry(h, (size_t)u.env, &w.geom);
+      if (rc) return rc;
+    }
+    u.num_slots = w.num_slots;
+    u.agent_slot = w.agent_slot;
+    u.carrying = w.carrying;
+    u.step_count = w.step_count;
+    u.num_picked = w.num_picked_up;
+    u.hold = w.hold;
+    u.cam[0] = w.cam_height;
+    u.cam[1] = w.cam_fwd_disp;
+    u.cam[2] = w.cam_pitch;
+    u.cam[3] = w.cam_fov_y;
+    for (int k = 0; k < 3; ++k) {
+      u.envp[0 + k] = w.sky_color[k];
+      u.envp[3 + k] = w.light_pos[k];
+      u.envp[6 + k] = w.light_color[k];
+      u.envp[9 + k] = w.light_ambient[k];
+    }
+    for (int e = 0; e < w.num_slots; ++e) u.ents[e] = w.ents[e];
+  }
+  return launch_upload(h, up, false);
+}
+
+// ------------------------------------------------------------------ ABI: the hot path
+static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s) {
+  if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
+#ifndef MWB_HOSTSIM
+  const int smem = h->tri_cap * (int)sizeof(TriRec);
+  switch (h->S.msaa) {
+    case 1: render_kernel<1><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
+    case 4: render_kernel<4><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
+    default: render_kernel<8><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+#else
+  hostsim_render(h->S, h->A, obs, depth);
+#endif
+  return MWB_OK;
+}
+
+static int finish_outputs(mwb_handle* h, uint8_t* obs, bool obs_host, float* depth, bool depth_host, double* reward,
+                          uint8_t* term, uint8_t* trunc, stream_t s, bool user_stream) {
+  const size_t N = h->S.N, px = (size_t)h->S.obs_w * h->S.obs_h;
+  int rc = 0;
+  bool any_host = false;
+  if (obs && obs_host) { rc |= d2h(obs, h->d_obs, N * px * 3, s); any_host = true; }
+  if (depth && depth_host) { rc |= d2h(depth, h->d_depth, N * px * sizeof(float), s); any_host = true; }
+  if (reward && !is_device_ptr(reward)) { rc |= d2h(reward, h->d_reward, N * sizeof(double), s); any_host = true; }
+  if (term && !is_device_ptr(term)) { rc |= d2h(term, h->d_term, N, s); any_host = true; }
+  if (trunc && !is_device_ptr(trunc)) { rc |= d2h(trunc, h->d_trunc, N, s); any_host = true; }
+  if (rc) return fail(MWB_ECUDA, "readback failed");
+  if (any_host || !user_stream)
+    if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
+  return MWB_OK;
+}
+
+extern "C" int mwb_step(mwb_handle* h, const int32_t* actions, const double* step_params, uint8_t* obs, float* depth,
+                        double* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (!h || !actions) return fail(MWB_EINVAL, "null argument");
+  if (!h->have_params || !h->have_protos) return fail(MWB_ESTATE, "params / protos not set");
+  stream_t s = stream ? (stream_t)stream : h->stream;
+  const size_t N = h->S.N;
+  const int32_t* d_act = actions;
+  if (!is_device_ptr(actions)) {
+    if (h2d(h->d_actions, actions, N * sizeof(int32_t), s) != 0) return fail(MWB_ECUDA, "action upload failed");
+    d_act = h->d_actions;
+  }
+  const double* d_sp = nullptr;
+  if (step_params) {
+    if (is_device_ptr(step_params)) {
+      d_sp = step_params;
+    } else {
+      if (h2d(h->d_step_params, step_params, 3 * N * sizeof(double), s) != 0) return fail(MWB_ECUDA, "upload failed");
+      d_sp = h->d_step_params;
+    }
+  }
+  // rewards / flags go to caller device memory directly, else to staging
+  double* d_rew = reward && is_device_ptr(reward) ? reward : h->d_reward;
+  uint8_t* d_te = terminated && is_device_ptr(terminated) ? terminated : h->d_term;
+  uint8_t* d_tr = truncated && is_device_ptr(truncated) ? truncated : h->d_trunc;
+#ifndef MWB_HOSTSIM
+  step_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(h->S, d_act, d_sp, d_rew, d_te, d_tr);
+  h->launches++;
+  CK(cudaGetLastError());
+#else
+  for (size_t i = 0; i < N; ++i) step_one(h->S, (int)i, d_act, d_sp, d_rew, d_te, d_tr);
+#endif
+  const bool obs_host = obs && !is_device_ptr(obs), depth_host = depth && !is_device_ptr(depth);
+  if (obs || depth) {
+    int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s);
+    if (rc) return rc;
+  }
+  return finish_outputs(h, obs, obs_host, depth, depth_host, reward, terminated, truncated, s, stream != nullptr);
+}
+
+extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* stream) {
+  if (!h || (!obs && !depth)) return fail(MWB_EINVAL, "null argument");
+  stream_t s = stream ? (stream_t)stream : h->stream;
+  const bool obs_host = obs && !is_device_ptr(obs), depth_host = depth && !is_device_ptr(depth);
+  int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s);
+  if (rc) return rc;
+  return finish_outputs(h, obs, obs_host, depth, depth_host, nullptr, nullptr, nullptr, s, stream != nullptr);
+}
+
+// ------------------------------------------------------------------ ABI: state exchange
+extern "C" int mwb_get_state(mwb_handle* h, const mwb_state_view* out) {
+  if (!h || !out) return fail(MWB_EINVAL, "null argument");
+  const int N = h->S.N;
+  std::vector<WorldUpload> up(N);
+#ifndef MWB_HOSTSIM
+  gather_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(h->S, h->d_upload);
+  h->launches++;
+  CK(cudaGetLastError());
+#else
+  for (int i = 0; i < N; ++i) gather_one(h->S, i, h->d_upload[i]);
+#endif
+  if (d2h(up.data(), h->d_upload, (size_t)N * sizeof(WorldUpload), h->stream) != 0) return fail(MWB_ECUDA, "readback failed");
+  std::vector<int32_t> rtex;
+  if (out->room_tex) {
+    rtex.resize((size_t)N * h->S.R * 3);
+    if (d2h(rtex.data(), h->S.room_tex, rtex.size() * sizeof(int32_t), h->stream) != 0) return fail(MWB_ECUDA, "readback failed");
+  }
+  if (sync_stream(h->stream) != 0) return fail(MWB_ECUDA, "sync failed");
+  for (int i = 0; i < N; ++i) {
+    const WorldUpload& u = up[i];
+    const int as = u.agent_slot >= 0 && u.agent_slot < MWB_MAX_ENTS_CAP ? u.agent_slot : 0;
+    if (out->agent_pos) for (int k = 0; k < 3; ++k) out->agent_pos[i * 3 + k] = u.ents[as].pos[k];
+    if (out->agent_dir) out->agent_dir[i] = u.ents[as].dir;
+    if (out->step_count) out->step_count[i] = u.step_count;
+    if (out->carrying) out->carrying[i] = u.carrying;
+    if (out->num_slots) out->num_slots[i] = u.num_slots;
+    if (out->agent_slot) out->agent_slot[i] = u.agent_slot;
+    if (out->num_picked_up) out->num_picked_up[i] = u.num_picked;
+    if (out->ents) for (int e = 0; e < h->S.E; ++e) out->ents[(size_t)i * h->S.E + e] = u.ents[e];
+    if (out->cam) for (int k = 0; k < 4; ++k) out->cam[i * 4 + k] = u.cam[k];
+    if (out->env_params) for (int k = 0; k < 12; ++k) out->env_params[i * 12 + k] = u.envp[k];
+    if (out->rng) out->rng[i] = u.rng;
+  }
+  if (out->room_tex) memcpy(out->room_tex, rtex.data(), rtex.size() * sizeof(int32_t));
+  return MWB_OK;
+}

@@ -1,0 +1,210 @@
+// physics.cuh -- K1: one thread per environment, float64, the reference's arithmetic.
+//
+// Restates, operation for operation (no FMA contraction except where numpy's BLAS ddot
+// itself fuses), the step path of the reference:
+//   math.intersect_circle_segs      reference miniworld/math.py:30-62
+//   MiniWorldEnv.intersect          reference miniworld/miniworld.py:937-963
+//   MiniWorldEnv.move_agent         :620-645      MiniWorldEnv.turn_agent :647-668
+//   MiniWorldEnv._get_carry_pos     :606-618      MiniWorldEnv.step       :670-730
+//   MiniWorldEnv.near / _reward     :965-975, :1012-1017
+//   level rules                     envs/hallway.py:67-74 (goal), envs/pickupobjects.py:83-95
+// Outputs are bit-identical to the reference on this image (numpy 2.3.5, glibc 2.39):
+// tests/test_physics_gpu.py compares against trajectories dumped from the reference itself.
+#pragma once
+#include "libm_sincos.cuh"
+#include "state.h"
+
+#define MWB_HIT_NONE (-1)
+#define MWB_HIT_WALL (-2)
+
+// intersect_circle_segs: any(dist(point, seg) < radius), strict.  numpy evaluates
+// sum(ap*ab, axis=1) as (x*x' + 0) + z*z' with separate roundings (ufunc reduce, no FMA).
+MWB_DEV bool circle_hits_walls(const mwb_seg* segs, int n, double px, double pz, double radius) {
+  for (int s = 0; s < n; ++s) {
+    double ax = segs[s].ax, az = segs[s].az;
+    double abx = d_sub(segs[s].bx, ax), abz = d_sub(segs[s].bz, az);
+    double apx = d_sub(px, ax), apz = d_sub(pz, az);
+    double apab = d_add(d_mul(apx, abx), d_mul(apz, abz));
+    double abab = d_add(d_mul(abx, abx), d_mul(abz, abz));
+    double t = d_div(apab, abab);
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    double cx = d_add(ax, d_mul(t, abx)), cz = d_add(az, d_mul(t, abz));
+    double dx = d_sub(cx, px), dz = d_sub(cz, pz);
+    double dist = d_sqrt(d_add(d_mul(dx, dx), d_mul(dz, dz)));
+    if (dist < radius) return true;
+  }
+  return false;
+}
+
+// `radius + ent2.radius` as Python/numpy evaluates it: float32 arithmetic as soon as one of
+// the operands is an np.float32 (MeshEnt radii under numpy >= 2, NEP 50), else float64.
+MWB_DEV double sum_radii(double r0, bool r0_f32, double r1, bool r1_f32) {
+  if (r0_f32 || r1_f32) return (double)f_add((float)r0, (float)r1);
+  return d_add(r0, r1);
+}
+
+// MiniWorldEnv.intersect: walls first, then the entity list in order (skipping `self_slot`).
+// np.linalg.norm of a 1-D vector goes through BLAS ddot, which accumulates with FMA:
+// sqrt(fma(dz, dz, fma(dy, dy, dx*dx))) with dy == 0 here.
+MWB_DEV int world_intersect(const DevState& S, int i, int self_slot, double px, double pz, double radius,
+                            bool radius_f32) {
+  int g = geom_index(S, i);
+  if (circle_hits_walls(S.segs + (size_t)g * S.S, S.num_segs[g], px, pz, radius)) return MWB_HIT_WALL;
+  int n = S.num_slots[i];
+  for (int e = 0; e < n; ++e) {
+    if (e == self_slot) continue;
+    int p = S.ent_proto[(size_t)e * S.N + i];
+    if (p < 0) continue;
+    double dx = d_sub(S.ent_px[(size_t)e * S.N + i], px);
+    double dz = d_sub(S.ent_pz[(size_t)e * S.N + i], pz);
+    double d = d_sqrt(d_fma(dz, dz, d_mul(dx, dx)));
+    const mwb_proto& pr = S.protos[p];
+    if (d < sum_radii(radius, radius_f32, pr.radius, pr.radius_is_f32 != 0)) return e;
+  }
+  return MWB_HIT_NONE;
+}
+
+struct CarryPos {
+  double x, y, z;
+};
+
+// _get_carry_pos(agent_pos, ent): agent_pos + dir_vec * 1.05 * dist, lifted to stay visible
+MWB_DEV CarryPos carry_pos(const DevState& S, int i, double apx, double apz, double c, double s, int slot) {
+  const mwb_proto& pr = S.protos[S.ent_proto[(size_t)slot * S.N + i]];
+  double dist;
+  if (pr.radius_is_f32)
+    dist = (double)f_add(f_add(0.4f, (float)pr.radius), (float)S.params.max_forward_step);
+  else
+    dist = d_add(d_add(0.4, pr.radius), S.params.max_forward_step);
+  CarryPos o;
+  o.x = d_add(apx, d_mul(d_mul(c, 1.05), dist));
+  o.z = d_add(apz, d_mul(d_mul(-s, 1.05), dist));
+  double y = d_sub(d_sub(S.cam[0 * (size_t)S.N + i], pr.height), 0.3);
+  o.y = y > 0.0 ? y : 0.0;
+  return o;
+}
+
+struct StepOut {
+  double reward;
+  int terminated, truncated;
+};
+
+// One MiniWorldEnv.step() (without the render) followed by the lowered level rule.
+// fwd_step / fwd_drift / turn_step are the three per-step parameters of miniworld.py:677-680.
+MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_step, double fwd_drift,
+                             double turn_step) {
+  const size_t N = S.N;
+  const int as = S.agent_slot[i];
+  double px = S.ent_px[as * N + i], pz = S.ent_pz[as * N + i], dir = S.ent_dir[as * N + i];
+  int carrying = S.carrying[i];
+  int sc = S.step_count[i] + 1;
+  S.step_count[i] = sc;
+  S.ghost_slot[i] = -1;
+
+  if (action == 2 || action == 3) {   // move_forward / move_back
+    double fwd = action == 2 ? fwd_step : -fwd_step;
+    double c = mwb_libm::cos_glibc(dir), s = mwb_libm::sin_glibc(dir);
+    double nx = d_add(d_add(px, d_mul(c, fwd)), d_mul(s, fwd_drift));
+    double nz = d_add(d_add(pz, d_mul(-s, fwd)), d_mul(c, fwd_drift));
+    bool ok = world_intersect(S, i, as, nx, nz, 0.4, false) == MWB_HIT_NONE;
+    if (ok && carrying >= 0) {
+      CarryPos cp = carry_pos(S, i, nx, nz, c, s, carrying);
+      const mwb_proto& pr = S.protos[S.ent_proto[carrying * N + i]];
+      ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.radius_is_f32 != 0) == MWB_HIT_NONE;
+      if (ok) {
+        S.ent_px[carrying * N + i] = cp.x;
+        S.ent_py[carrying * N + i] = cp.y;
+        S.ent_pz[carrying * N + i] = cp.z;
+      }
+    }
+    if (ok) {
+      px = nx;
+      pz = nz;
+      S.ent_px[as * N + i] = px;
+      S.ent_pz[as * N + i] = pz;
+    }
+  } else if (action == 0 || action == 1) {   // turn_left / turn_right
+    double ang = d_mul(action == 0 ? turn_step : -turn_step, 0.017453292519943295 /* math.pi / 180 */);
+    double ndir = d_add(dir, ang);
+    bool ok = true;
+    if (carrying >= 0) {
+      double c = mwb_libm::cos_glibc(ndir), s = mwb_libm::sin_glibc(ndir);
+      CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying);
+      const mwb_proto& pr = S.protos[S.ent_proto[carrying * N + i]];
+      // the agent's dir is already updated when the reference tests this; intersect() does not read it
+      ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.radius_is_f32 != 0) == MWB_HIT_NONE;
+      if (ok) {
+        S.ent_px[carrying * N + i] = cp.x;
+        S.ent_py[carrying * N + i] = cp.y;
+        S.ent_pz[carrying * N + i] = cp.z;
+        S.ent_dir[carrying * N + i] = ndir;
+      }
+    }
+    if (ok) {
+      dir = ndir;
+      S.ent_dir[as * N + i] = dir;
+    }
+  } else if (action == 4) {   // pickup
+    double c = mwb_libm::cos_glibc(dir), s = mwb_libm::sin_glibc(dir);
+    double tx = d_add(px, d_mul(d_mul(c, 1.5), 0.4));
+    double tz = d_add(pz, d_mul(d_mul(-s, 1.5), 0.4));
+    int hit = world_intersect(S, i, as, tx, tz, d_mul(1.2, 0.4), false);
+    if (carrying < 0 && hit >= 0 && !S.protos[S.ent_proto[hit * N + i]].is_static) carrying = hit;
+  } else if (action == 5) {   // drop
+    if (carrying >= 0) {
+      S.ent_py[carrying * N + i] = 0.0;
+      carrying = -1;
+    }
+  }
+
+  if (carrying >= 0) {   // carried object follows the agent
+    double c = mwb_libm::cos_glibc(dir), s = mwb_libm::sin_glibc(dir);
+    CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying);
+    S.ent_px[carrying * N + i] = cp.x;
+    S.ent_py[carrying * N + i] = cp.y;
+    S.ent_pz[carrying * N + i] = cp.z;
+    S.ent_dir[carrying * N + i] = dir;
+  }
+
+  StepOut o;
+  o.reward = 0.0;
+  o.terminated = 0;
+  o.truncated = sc >= S.max_episode_steps ? 1 : 0;
+
+  if (S.rule_kind == MWB_RULE_GOAL) {
+    // near(box): np.linalg.norm(box.pos - agent.pos) < r_box + r_agent + 1.1 * max_forward_step
+    int b = S.rule_arg;
+    int bp = S.ent_proto[b * N + i];
+    if (bp >= 0) {
+      double dx = d_sub(S.ent_px[b * N + i], px);
+      double dy = d_sub(S.ent_py[b * N + i], S.ent_py[as * N + i]);
+      double dz = d_sub(S.ent_pz[b * N + i], pz);
+      double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
+      const mwb_proto& pr = S.protos[bp];
+      double thr = d_add(sum_radii(pr.radius, pr.radius_is_f32 != 0, 0.4, false), S.near_extra);
+      if (d < thr) {
+        o.reward = d_add(o.reward, d_sub(1.0, d_mul(0.2, d_div((double)sc, (double)S.max_episode_steps))));
+        o.terminated = 1;
+      }
+    }
+  } else if (S.rule_kind == MWB_RULE_PICKUP) {
+    if (carrying >= 0) {
+      // the observation of this step still shows the object at its carry position
+      S.ghost_slot[i] = carrying;
+      S.ghost_proto[i] = S.ent_proto[carrying * N + i];
+      S.ghost_pose[0 * N + i] = S.ent_px[carrying * N + i];
+      S.ghost_pose[1 * N + i] = S.ent_py[carrying * N + i];
+      S.ghost_pose[2 * N + i] = S.ent_pz[carrying * N + i];
+      S.ghost_pose[3 * N + i] = S.ent_dir[carrying * N + i];
+      for (int k = 0; k < 3; ++k) S.ghost_col[k * N + i] = S.ent_col[((size_t)carrying * 3 + k) * N + i];
+      S.ent_proto[carrying * N + i] = -1;
+      carrying = -1;
+      int np_ = S.num_picked[i] + 1;
+      S.num_picked[i] = np_;
+      o.reward = 1.0;
+      if (np_ == S.rule_arg) o.terminated = 1;
+    }
+  }
+  S.carrying[i] = carrying;
+  return o;
+}

@@ -1,0 +1,545 @@
+// raster_core.cuh -- K2 arithmetic: camera, vertex pipeline, triangle setup, coverage,
+// depth, shading.  The kernel that drives these functions is in raster.cuh.
+//
+// What is restated here (reference = Farama-Foundation/Miniworld @ c660156, the GL state it
+// programs, and the OpenGL 2.1 fixed-function rules those calls select):
+//   MiniWorldEnv.render_obs      miniworld.py:1177-1221  clear to sky_color / depth 1,
+//                                gluPerspective(fov_y, W/H, 0.04, 100), gluLookAt(cam_pos,
+//                                cam_pos + cam_dir, +Y)
+//   Agent.cam_pos / cam_dir      entity.py:476-503
+//   _render_static/_render_world miniworld.py:1019-1086  LIGHT0 positional at light_pos,
+//                                COLOR_MATERIAL(AMBIENT_AND_DIFFUSE), SMOOTH shading,
+//                                rooms -> entities in list order, DEPTH_TEST LESS, CULL_FACE
+//   Room._render                 miniworld.py:401-434    floor / ceiling polygons, wall quads
+//   Box.render + drawBox         entity.py:409-432, opengl.py:460-503
+//   Texture.load                 opengl.py:147-184       RGB8, mipmaps, trilinear, REPEAT
+//   FrameBuffer                  opengl.py:197-435       N-sample MSAA, DEPTH_COMPONENT16,
+//                                box-filter resolve to unorm8, depth -> metres (:400-435)
+//
+// Arithmetic contract (DESIGN.md "pixel spec"): everything that decides WHICH surface a
+// sample sees -- vertex transform, homogeneous edge functions, the z plane, the 16-bit
+// depth code -- is float32 with one rounding per operation in a fixed order (f*_rn
+// helpers; never contracted), so the CPU oracle (oracle/softgl.c) reproduces coverage and
+// depth bit for bit.  Colour (lighting, perspective-correct interpolation, trilinear
+// filtering, resolve) is ordinary float32 where FMA contraction is allowed; it is
+// continuous in its inputs and is held to <= 1 LSB against the oracle.
+#pragma once
+#include "libm_sincos.cuh"
+#include "state.h"
+
+#define MWB_NEAR 0.04
+#define MWB_FAR 100.0
+#define MWB_MAX_LEVELS 12
+#define MWB_SKY_KEY 0xFFFF0000u
+
+struct TexDev {
+  int32_t w, h, nlev, pad;
+  int32_t lw[MWB_MAX_LEVELS], lh[MWB_MAX_LEVELS];
+  int32_t off[MWB_MAX_LEVELS];   // texel offset of each level in the pool
+};
+
+struct MeshDev {
+  int32_t first, count;          // triangle range in the mesh pool
+};
+
+struct RenderAssets {
+  const TexDev* tex;
+  const uint32_t* texels;        // RGBA8 pool, row 0 = bottom of the image
+  int32_t num_tex;
+  const MeshDev* meshes;
+  const float* mesh_pos;         // [T][3][3]
+  const float* mesh_nrm;
+  const float* mesh_uv;          // [T][3][2]
+  const float* mesh_rgb;
+  int32_t num_meshes;
+};
+
+// D3D standard sample patterns, offsets from the pixel's top-left corner, image space
+// (x right, y down).  All are multiples of 1/16: sample coordinates are exact in float32.
+MWB_DEVCONST float mwb_sample_x[13] = {0.5f, 0.375f, 0.875f, 0.125f, 0.625f,
+                                       0.5625f, 0.4375f, 0.8125f, 0.3125f, 0.1875f, 0.0625f, 0.6875f, 0.9375f};
+MWB_DEVCONST float mwb_sample_y[13] = {0.5f, 0.125f, 0.375f, 0.625f, 0.875f,
+                                       0.3125f, 0.6875f, 0.5625f, 0.1875f, 0.8125f, 0.4375f, 0.9375f, 0.0625f};
+MWB_DEV int sample_base(int msaa) { return msaa == 1 ? 0 : (msaa == 4 ? 1 : 5); }
+
+struct Camera {
+  float ex, ey, ez;              // eye
+  float sx, sy, sz;              // right   (gluLookAt's s)
+  float ux, uy, uz;              // up      (u = s x f)
+  float fx, fy, fz;              // forward (f)
+  float px, py;                  // projection scales cot/aspect, cot
+  float za, zb;                  // z_clip = za * w_clip - zb
+  float halfw, halfh;
+  float light[3], lamb[3], ldif[3], sky[3];
+};
+
+// Camera of env i.  Angles go through the glibc-exact sin / cos so that the oracle, fed the
+// same (pos, dir, cam_*) doubles on the host, derives the identical float32 basis.
+MWB_DEV Camera make_camera(const DevState& S, int i) {
+  const size_t N = S.N;
+  const int as = S.agent_slot[i];
+  double px = S.ent_px[as * N + i], py = S.ent_py[as * N + i], pz = S.ent_pz[as * N + i];
+  double dir = S.ent_dir[as * N + i];
+  double h = S.cam[0 * N + i], fd = S.cam[1 * N + i], pitch = S.cam[2 * N + i], fov = S.cam[3 * N + i];
+  double ct = mwb_libm::cos_glibc(dir), st = mwb_libm::sin_glibc(dir);
+  double phi = d_div(d_mul(pitch, 3.141592653589793), 180.0);
+  double cp = mwb_libm::cos_glibc(phi), sp = mwb_libm::sin_glibc(phi);
+  Camera c;
+  c.ex = (float)d_add(px, d_mul(fd, ct));
+  c.ey = (float)d_add(py, h);
+  c.ez = (float)d_sub(pz, d_mul(fd, st));
+  c.sx = (float)st;
+  c.sy = 0.0f;
+  c.sz = (float)ct;
+  c.ux = (float)(-d_mul(ct, sp));
+  c.uy = (float)cp;
+  c.uz = (float)d_mul(st, sp);
+  c.fx = (float)d_mul(cp, ct);
+  c.fy = (float)sp;
+  c.fz = (float)(-d_mul(cp, st));
+  double half = d_div(d_mul(fov, 3.141592653589793), 360.0);
+  double cot = d_div(mwb_libm::cos_glibc(half), mwb_libm::sin_glibc(half));
+  c.py = (float)cot;
+  c.px = (float)d_div(cot, d_div((double)S.obs_w, (double)S.obs_h));
+  c.za = (float)((MWB_FAR + MWB_NEAR) / (MWB_FAR - MWB_NEAR));
+  c.zb = (float)(2.0 * MWB_FAR * MWB_NEAR / (MWB_FAR - MWB_NEAR));
+  c.halfw = 0.5f * (float)S.obs_w;
+  c.halfh = 0.5f * (float)S.obs_h;
+  for (int k = 0; k < 3; ++k) {
+    c.sky[k] = (float)S.envp[(0 + k) * N + i];
+    c.light[k] = (float)S.envp[(3 + k) * N + i];
+    c.ldif[k] = (float)S.envp[(6 + k) * N + i];
+    c.lamb[k] = (float)S.envp[(9 + k) * N + i];
+  }
+  return c;
+}
+
+// vertex after the exact part of the pipeline: window-homogeneous position + z numerator
+struct HVert {
+  float X, Y, w, zeta;           // X/w = column, Y/w = row (y down), zeta/w = window z in [0,1]
+  float xc, yc, zc;              // clip x, y, z (frustum tests)
+};
+
+MWB_DEV float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+  return f_add(f_add(f_mul(ax, bx), f_mul(ay, by)), f_mul(az, bz));
+}
+
+MWB_DEV HVert transform_vertex(const Camera& c, float x, float y, float z) {
+  float rx = f_sub(x, c.ex), ry = f_sub(y, c.ey), rz = f_sub(z, c.ez);
+  float xe = dot3_rn(c.sx, c.sy, c.sz, rx, ry, rz);
+  float ye = dot3_rn(c.ux, c.uy, c.uz, rx, ry, rz);
+  float w = dot3_rn(c.fx, c.fy, c.fz, rx, ry, rz);   // distance along the view axis
+  HVert v;
+  v.w = w;
+  v.xc = f_mul(c.px, xe);
+  v.yc = f_mul(c.py, ye);
+  v.zc = f_sub(f_mul(c.za, w), c.zb);
+  v.X = f_mul(f_add(v.xc, w), c.halfw);
+  v.Y = f_mul(f_sub(w, v.yc), c.halfh);
+  v.zeta = f_mul(0.5f, f_add(v.zc, w));
+  return v;
+}
+
+// Fixed-function vertex lighting (one positional light, no attenuation, no specular):
+// clamp01(m * (0.2 + L_amb + L_diff * max(N . norm(P_light - P), 0))); N is NOT renormalised
+// (neither GL_NORMALIZE nor GL_RESCALE_NORMAL is enabled by the reference).
+MWB_DEV void light_vertex(const Camera& c, float x, float y, float z, float nx, float ny, float nz,
+                          const float m[3], float out[3]) {
+  float lx = c.light[0] - x, ly = c.light[1] - y, lz = c.light[2] - z;
+  float inv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+  float ndl = (nx * lx + ny * ly + nz * lz) * inv;
+  ndl = ndl > 0.0f ? ndl : 0.0f;
+  for (int k = 0; k < 3; ++k) {
+    float v = m[k] * (0.2f + c.lamb[k] + c.ldif[k] * ndl);
+    out[k] = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+  }
+}
+
+// One set-up triangle, 36 words.  Edge k is opposite vertex k, so E_k / sum(E) is the
+// perspective-correct weight of vertex k's attributes.
+struct TriRec {
+  float A[3], B[3], C[3];        // homogeneous edge functions E_k(x, y) = A x + B y + C  (exact)
+  float R[3];                    // conservative half-extent of E_k over a pixel (+ rounding margin)
+  float Za, Zb, Zc;              // window z plane (exact)
+  float u[3], v[3];              // texcoords per vertex
+  float r[3], g[3], b[3];        // lit colour per vertex
+  int32_t tex;                   // texture id or -1
+  int32_t bx, by;                // bbox: lo | hi << 16, pixel units, clamped to the frame
+};
+
+struct VertAttr {
+  float u, v, r, g, b;
+};
+
+MWB_DEV bool frustum_reject(const HVert& a, const HVert& b, const HVert& c) {
+  if (a.xc < -a.w && b.xc < -b.w && c.xc < -c.w) return true;
+  if (a.xc > a.w && b.xc > b.w && c.xc > c.w) return true;
+  if (a.yc < -a.w && b.yc < -b.w && c.yc < -c.w) return true;
+  if (a.yc > a.w && b.yc > b.w && c.yc > c.w) return true;
+  if (a.zc < -a.w && b.zc < -b.w && c.zc < -c.w) return true;
+  if (a.zc > a.w && b.zc > b.w && c.zc > c.w) return true;
+  return false;
+}
+
+MWB_DEV void edge_rn(const HVert& a, const HVert& b, float& A, float& B, float& C) {
+  A = f_sub(f_mul(a.Y, b.w), f_mul(a.w, b.Y));
+  B = f_sub(f_mul(a.w, b.X), f_mul(a.X, b.w));
+  C = f_sub(f_mul(a.X, b.Y), f_mul(a.Y, b.X));
+}
+
+// GL triangle (v0, v1, v2), counter-clockwise = front in GL's y-up window.  In image space
+// (y down) front faces have negative signed area, so edges are built on (v0, v2, v1): then
+// det > 0 <=> front-facing and the interior is E_k >= 0.  Returns false if culled.
+MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, const VertAttr& a0,
+                            const VertAttr& a1, const VertAttr& a2, int tex, int W, int H, TriRec& t) {
+  if (frustum_reject(g0, g1, g2)) return false;
+  const HVert& v0 = g0;
+  const HVert& v1 = g2;
+  const HVert& v2 = g1;
+  edge_rn(v1, v2, t.A[0], t.B[0], t.C[0]);
+  edge_rn(v2, v0, t.A[1], t.B[1], t.C[1]);
+  edge_rn(v0, v1, t.A[2], t.B[2], t.C[2]);
+  float det = f_add(f_add(f_mul(v0.X, t.A[0]), f_mul(v0.Y, t.B[0])), f_mul(v0.w, t.C[0]));
+  if (!(det > 0.0f)) return false;   // back-facing or degenerate (GL_CULL_FACE, GL_BACK)
+  t.Za = f_div(f_add(f_add(f_mul(v0.zeta, t.A[0]), f_mul(v1.zeta, t.A[1])), f_mul(v2.zeta, t.A[2])), det);
+  t.Zb = f_div(f_add(f_add(f_mul(v0.zeta, t.B[0]), f_mul(v1.zeta, t.B[1])), f_mul(v2.zeta, t.B[2])), det);
+  t.Zc = f_div(f_add(f_add(f_mul(v0.zeta, t.C[0]), f_mul(v1.zeta, t.C[1])), f_mul(v2.zeta, t.C[2])), det);
+  for (int k = 0; k < 3; ++k) {
+    float aa = fabsf(t.A[k]), ab = fabsf(t.B[k]);
+    // |E(sample) - E(centre)| <= 0.4375 (|A| + |B|); plus a bound on evaluation rounding
+    t.R[k] = 0.4375f * (aa + ab) + 4e-6f * (aa * (float)W + ab * (float)H + fabsf(t.C[k])) + 1e-30f;
+  }
+  const VertAttr& b0 = a0;
+  const VertAttr& b1 = a2;
+  const VertAttr& b2 = a1;
+  t.u[0] = b0.u; t.u[1] = b1.u; t.u[2] = b2.u;
+  t.v[0] = b0.v; t.v[1] = b1.v; t.v[2] = b2.v;
+  t.r[0] = b0.r; t.r[1] = b1.r; t.r[2] = b2.r;
+  t.g[0] = b0.g; t.g[1] = b1.g; t.g[2] = b2.g;
+  t.b[0] = b0.b; t.b[1] = b1.b; t.b[2] = b2.b;
+  t.tex = tex;
+  // screen bbox (conservative); any vertex at or behind the eye plane -> whole frame
+  int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
+  const float weps = 1e-3f;
+  if (v0.w > weps && v1.w > weps && v2.w > weps) {
+    float xa = v0.X / v0.w, xb = v1.X / v1.w, xc = v2.X / v2.w;
+    float ya = v0.Y / v0.w, yb = v1.Y / v1.w, yc = v2.Y / v2.w;
+    float fx0 = fminf(xa, fminf(xb, xc)) - 1.0f, fx1 = fmaxf(xa, fmaxf(xb, xc)) + 1.0f;
+    float fy0 = fminf(ya, fminf(yb, yc)) - 1.0f, fy1 = fmaxf(ya, fmaxf(yb, yc)) + 1.0f;
+    if (fx1 < 0.0f || fy1 < 0.0f || fx0 > (float)W || fy0 > (float)H) return false;
+    x0 = fx0 > 0.0f ? (int)fx0 : 0;
+    y0 = fy0 > 0.0f ? (int)fy0 : 0;
+    x1 = fx1 < (float)(W - 1) ? (int)fx1 : W - 1;
+    y1 = fy1 < (float)(H - 1) ? (int)fy1 : H - 1;
+  }
+  t.bx = x0 | (x1 << 16);
+  t.by = y0 | (y1 << 16);
+  return true;
+}
+
+// Exact edge value at a sample and the tie rule that makes shared edges watertight: the
+// neighbouring triangle sees the exactly negated (A, B, C), so exactly one side owns E == 0.
+MWB_DEV bool edge_inside(float A, float B, float C, float xs, float ys) {
+  float e = f_add(f_add(f_mul(A, xs), f_mul(B, ys)), C);
+  if (e > 0.0f) return true;
+  if (e < 0.0f) return false;
+  return A > 0.0f || (A == 0.0f && B > 0.0f);
+}
+
+// Depth-tested visibility of triangle `slot` over the `msaa` samples of pixel (px, py).
+// keys[s] = depth16 << 16 | slot of the nearest surface so far (GL_LESS on 16-bit codes;
+// slots ascend in draw order, so on equal codes the earlier draw keeps the sample).
+MWB_DEV void raster_pixel(const TriRec& t, int slot, int px, int py, int msaa, uint32_t* keys) {
+  float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
+  float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
+  float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
+  float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
+  if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) return;   // certainly outside
+  bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;    // certainly inside
+  const int sb = sample_base(msaa);
+  for (int s = 0; s < msaa; ++s) {
+    float xs = (float)px + mwb_sample_x[sb + s], ys = (float)py + mwb_sample_y[sb + s];
+    if (!full) {
+      if (!edge_inside(t.A[0], t.B[0], t.C[0], xs, ys)) continue;
+      if (!edge_inside(t.A[1], t.B[1], t.C[1], xs, ys)) continue;
+      if (!edge_inside(t.A[2], t.B[2], t.C[2], xs, ys)) continue;
+    }
+    float z = f_add(f_add(f_mul(t.Za, xs), f_mul(t.Zb, ys)), t.Zc);
+    if (!(z >= 0.0f && z <= 1.0f)) continue;   // near / far clip (also drops NaN)
+    uint32_t code = (uint32_t)f_add(f_mul(z, 65535.0f), 0.5f);
+    uint32_t key = (code << 16) | (uint32_t)slot;
+    if (key < keys[s]) keys[s] = key;
+  }
+}
+
+// ---------------------------------------------------------------------------- shading
+
+MWB_DEV int wrap_repeat(int i, int n) {
+  int m = i % n;
+  return m < 0 ? m + n : m;
+}
+
+MWB_DEV void bilinear(const RenderAssets& A, const TexDev& T, int level, float u, float v, float out[3]) {
+  int w = T.lw[level], h = T.lh[level];
+  const uint32_t* base = A.texels + T.off[level];
+  float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+  float xf = floorf(x), yf = floorf(y);
+  float fx = x - xf, fy = y - yf;
+  int x0 = wrap_repeat((int)xf, w), y0 = wrap_repeat((int)yf, h);
+  int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
+  uint32_t t00 = base[y0 * w + x0], t10 = base[y0 * w + x1], t01 = base[y1 * w + x0], t11 = base[y1 * w + x1];
+  for (int k = 0; k < 3; ++k) {
+    float c00 = (float)((t00 >> (8 * k)) & 255u), c10 = (float)((t10 >> (8 * k)) & 255u);
+    float c01 = (float)((t01 >> (8 * k)) & 255u), c11 = (float)((t11 >> (8 * k)) & 255u);
+    float top = c00 + fx * (c10 - c00), bot = c01 + fx * (c11 - c01);
+    out[k] = (top + fy * (bot - top)) * (1.0f / 255.0f);
+  }
+}
+
+// Colour of triangle t at the centre of pixel (px, py): Gouraud colour x trilinear texture
+// (GL_MODULATE), both interpolated perspective-correctly.  LOD from analytic derivatives.
+MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py, float out[3]) {
+  float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
+  float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
+  float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
+  float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
+  float inv = 1.0f / (e0 + e1 + e2);
+  float b0 = e0 * inv, b1 = e1 * inv, b2 = e2 * inv;
+  float r = b0 * t.r[0] + b1 * t.r[1] + b2 * t.r[2];
+  float g = b0 * t.g[0] + b1 * t.g[1] + b2 * t.g[2];
+  float b = b0 * t.b[0] + b1 * t.b[1] + b2 * t.b[2];
+  if (t.tex >= 0) {
+    const TexDev& T = A.tex[t.tex];
+    float u = b0 * t.u[0] + b1 * t.u[1] + b2 * t.u[2];
+    float v = b0 * t.v[0] + b1 * t.v[1] + b2 * t.v[2];
+    float sa = t.A[0] + t.A[1] + t.A[2], sb = t.B[0] + t.B[1] + t.B[2];
+    float dudx = (t.u[0] * t.A[0] + t.u[1] * t.A[1] + t.u[2] * t.A[2] - u * sa) * inv * (float)T.w;
+    float dvdx = (t.v[0] * t.A[0] + t.v[1] * t.A[1] + t.v[2] * t.A[2] - v * sa) * inv * (float)T.h;
+    float dudy = (t.u[0] * t.B[0] + t.u[1] * t.B[1] + t.u[2] * t.B[2] - u * sb) * inv * (float)T.w;
+    float dvdy = (t.v[0] * t.B[0] + t.v[1] * t.B[1] + t.v[2] * t.B[2] - v * sb) * inv * (float)T.h;
+    float rho2 = fmaxf(dudx * dudx + dvdx * dvdx, dudy * dudy + dvdy * dvdy);
+    float lambda = 0.5f * log2f(fmaxf(rho2, 1e-20f));
+    float tc[3];
+    if (lambda <= 0.0f) {
+      bilinear(A, T, 0, u, v, tc);               // magnification: GL_LINEAR on level 0
+    } else {
+      float lmax = (float)(T.nlev - 1);
+      if (lambda >= lmax) {
+        bilinear(A, T, T.nlev - 1, u, v, tc);
+      } else {
+        int l0 = (int)lambda;
+        float f = lambda - (float)l0;
+        float ta[3], tb[3];
+        bilinear(A, T, l0, u, v, ta);
+        bilinear(A, T, l0 + 1, u, v, tb);
+        for (int k = 0; k < 3; ++k) tc[k] = ta[k] + f * (tb[k] - ta[k]);
+      }
+    }
+    r *= tc[0];
+    g *= tc[1];
+    b *= tc[2];
+  }
+  out[0] = r;
+  out[1] = g;
+  out[2] = b;
+}
+
+MWB_DEV uint8_t to_unorm8(float c) {
+  c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+  return (uint8_t)(int)(c * 255.0f + 0.5f);
+}
+
+// depth16 code -> metres, the float32 arithmetic of FrameBuffer.get_depth_map
+// (opengl.py:427-431): d = code / 65535; clip = (d - 0.5) * 2; z = -2 f n / (clip (f - n) - (f + n))
+MWB_DEV float depth_code_to_metres(uint32_t code) {
+  float d = f_div((float)code, 65535.0f);
+  float clip = f_mul(f_sub(d, 0.5f), 2.0f);
+  const float c0 = (float)(-2.0 * MWB_FAR * MWB_NEAR), c1 = (float)(MWB_FAR - MWB_NEAR), c2 = (float)(MWB_FAR + MWB_NEAR);
+  return f_div(c0, f_sub(f_mul(clip, c1), c2));
+}
+
+// ------------------------------------------------------------------ scene -> triangles
+// A frame's draw list is a sequence of "items": the static quads of the room template in
+// order, then each entity slot in list order (Box = 6 faces).  Every item yields <= 2
+// triangles (a quad is split as the fan (0,1,2), (0,2,3)).
+
+struct Item {
+  float pos[4][3];
+  float nrm[3];
+  float uv[4][2];
+  float mat[3];
+  int32_t tex;
+  int32_t nverts;
+};
+
+// static quad q of env i -> Item (texture choice and texel density applied here)
+MWB_DEV void room_item(const DevState& S, const RenderAssets& A, int i, int q, Item& it) {
+  const int g = geom_index(S, i);
+  const mwb_quad& Q = S.quads[(size_t)g * S.Q + q];
+  const int tex = S.room_tex[((size_t)i * S.R + Q.room) * 3 + Q.surf];
+  const TexDev& T = A.tex[tex];
+  // gen_texcs_wall / gen_texcs_floor: float64 multiply by TEX_DENSITY / size, then float32
+  const double xc = 512.0 / (double)T.w, yc = 512.0 / (double)T.h;
+  for (int k = 0; k < 4; ++k) {
+    it.pos[k][0] = Q.pos[k][0];
+    it.pos[k][1] = Q.pos[k][1];
+    it.pos[k][2] = Q.pos[k][2];
+    it.uv[k][0] = (float)d_mul(Q.uvm[k][0], xc);
+    it.uv[k][1] = (float)d_mul(Q.uvm[k][1], yc);
+  }
+  it.nrm[0] = Q.nrm[0];
+  it.nrm[1] = Q.nrm[1];
+  it.nrm[2] = Q.nrm[2];
+  it.mat[0] = it.mat[1] = it.mat[2] = 1.0f;   // glColor3f(1, 1, 1)
+  it.tex = tex;
+  it.nverts = Q.num_verts;
+}
+
+// face f (0..5, drawBox order: +z, -z, -x, +x, +y, -y) of a Box -> Item
+MWB_DEV void box_item(const mwb_proto& pr, double px, double py, double pz, double dir, const double col[3],
+                      int f, Item& it) {
+  const float hx = (float)(pr.size[0] / 2), sy = (float)pr.size[1], hz = (float)(pr.size[2] / 2);
+  const float x0 = -hx, x1 = hx, y0 = 0.0f, y1 = sy, z0 = -hz, z1 = hz;
+  float v[4][3];
+  float n[3] = {0, 0, 0};
+  switch (f) {
+    case 0: n[2] = 1;  { float q[4][3] = {{x1, y1, z1}, {x0, y1, z1}, {x0, y0, z1}, {x1, y0, z1}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+    case 1: n[2] = -1; { float q[4][3] = {{x0, y1, z0}, {x1, y1, z0}, {x1, y0, z0}, {x0, y0, z0}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+    case 2: n[0] = -1; { float q[4][3] = {{x0, y1, z1}, {x0, y1, z0}, {x0, y0, z0}, {x0, y0, z1}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+    case 3: n[0] = 1;  { float q[4][3] = {{x1, y1, z0}, {x1, y1, z1}, {x1, y0, z1}, {x1, y0, z0}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+    case 4: n[1] = 1;  { float q[4][3] = {{x1, y1, z1}, {x1, y1, z0}, {x0, y1, z0}, {x0, y1, z1}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+    default: n[1] = -1; { float q[4][3] = {{x1, y0, z0}, {x1, y0, z1}, {x0, y0, z1}, {x0, y0, z0}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+  }
+  // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = -x s + z c
+  const float c = (float)mwb_libm::cos_glibc(dir), s = (float)mwb_libm::sin_glibc(dir);
+  const float tx = (float)px, ty = (float)py, tz = (float)pz;
+  for (int k = 0; k < 4; ++k) {
+    it.pos[k][0] = f_add(f_add(f_mul(v[k][0], c), f_mul(v[k][2], s)), tx);
+    it.pos[k][1] = f_add(v[k][1], ty);
+    it.pos[k][2] = f_add(f_sub(f_mul(v[k][2], c), f_mul(v[k][0], s)), tz);
+    it.uv[k][0] = it.uv[k][1] = 0.0f;
+  }
+  it.nrm[0] = f_add(f_mul(n[0], c), f_mul(n[2], s));
+  it.nrm[1] = n[1];
+  it.nrm[2] = f_sub(f_mul(n[2], c), f_mul(n[0], s));
+  for (int k = 0; k < 3; ++k) it.mat[k] = (float)col[k];
+  it.tex = -1;
+  it.nverts = 4;
+}
+
+// Item -> up to two set-up triangles; returns how many survived culling
+MWB_DEV int item_triangles(const Camera& cam, const Item& it, int W, int H, TriRec out[2]) {
+  HVert hv[4];
+  VertAttr at[4];
+  for (int k = 0; k < it.nverts; ++k) {
+    hv[k] = transform_vertex(cam, it.pos[k][0], it.pos[k][1], it.pos[k][2]);
+    float col[3];
+    light_vertex(cam, it.pos[k][0], it.pos[k][1], it.pos[k][2], it.nrm[0], it.nrm[1], it.nrm[2], it.mat, col);
+    at[k].u = it.uv[k][0];
+    at[k].v = it.uv[k][1];
+    at[k].r = col[0];
+    at[k].g = col[1];
+    at[k].b = col[2];
+  }
+  int n = 0;
+  if (setup_triangle(hv[0], hv[1], hv[2], at[0], at[1], at[2], it.tex, W, H, out[n])) ++n;
+  if (it.nverts == 4 && setup_triangle(hv[0], hv[2], hv[3], at[0], at[2], at[3], it.tex, W, H, out[n])) ++n;
+  return n;
+}
+
+// Number of draw items of env i and the decoding of item index -> (room quad | entity face).
+struct ItemMap {
+  int n_quads;
+  int n_items;
+  int ent_first[9];              // first item index of each drawn entity (<= 8) + end
+  int ent_slot[8];
+  int n_ents;
+};
+
+MWB_DEV ItemMap build_item_map(const DevState& S, int i) {
+  ItemMap m;
+  const size_t N = S.N;
+  const int g = geom_index(S, i);
+  m.n_quads = S.num_quads[g];
+  int n = m.n_quads;
+  m.n_ents = 0;
+  const int slots = S.num_slots[i];
+  const int ghost = S.ghost_slot[i];
+  // reference draw order: display list (rooms, static entities), then non-static entities;
+  // two passes over the list reproduce it
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int e = 0; e < slots && m.n_ents < 8; ++e) {
+      int p = e == ghost ? S.ghost_proto[i] : S.ent_proto[e * N + i];
+      if (p < 0) continue;
+      const mwb_proto& pr = S.protos[p];
+      if (pr.kind != MWB_KIND_BOX) continue;     // agent is never drawn; meshes: raster_mesh
+      if ((pr.is_static != 0) != (pass == 0)) continue;
+      m.ent_first[m.n_ents] = n;
+      m.ent_slot[m.n_ents] = e;
+      ++m.n_ents;
+      n += 6;
+    }
+  }
+  m.ent_first[m.n_ents] = n;
+  m.n_items = n;
+  return m;
+}
+
+MWB_DEV void fetch_item(const DevState& S, const RenderAssets& A, int i, const ItemMap& m, int idx, Item& it) {
+  if (idx < m.n_quads) {
+    room_item(S, A, i, idx, it);
+    return;
+  }
+  const size_t N = S.N;
+  int k = 0;
+  while (k + 1 < m.n_ents && idx >= m.ent_first[k + 1]) ++k;
+  const int e = m.ent_slot[k];
+  const int face = idx - m.ent_first[k];
+  double col[3];
+  if (e == S.ghost_slot[i]) {
+    for (int c = 0; c < 3; ++c) col[c] = S.ghost_col[c * N + i];
+    box_item(S.protos[S.ghost_proto[i]], S.ghost_pose[0 * N + i], S.ghost_pose[1 * N + i], S.ghost_pose[2 * N + i],
+             S.ghost_pose[3 * N + i], col, face, it);
+  } else {
+    for (int c = 0; c < 3; ++c) col[c] = S.ent_col[((size_t)e * 3 + c) * N + i];
+    box_item(S.protos[S.ent_proto[e * N + i]], S.ent_px[e * N + i], S.ent_py[e * N + i], S.ent_pz[e * N + i],
+             S.ent_dir[e * N + i], col, face, it);
+  }
+}
+
+// Resolve one pixel: average the colour of the surface seen by each sample (box filter of
+// the MSAA resolve blit), shading each distinct triangle once at the pixel centre.
+template <typename TriFetch>
+MWB_DEV void resolve_pixel(const RenderAssets& A, const Camera& cam, const TriFetch& tris, const uint32_t* keys,
+                           int msaa, int px, int py, uint8_t rgb[3]) {
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  uint32_t done = 0;
+  const float wgt = 1.0f / (float)msaa;
+  for (int s = 0; s < msaa; ++s) {
+    if (done & (1u << s)) continue;
+    const uint32_t id = keys[s] >= MWB_SKY_KEY ? 0xFFFFu : (keys[s] & 0xFFFFu);
+    int cnt = 0;
+    for (int q = s; q < msaa; ++q) {
+      const uint32_t idq = keys[q] >= MWB_SKY_KEY ? 0xFFFFu : (keys[q] & 0xFFFFu);
+      if (idq == id) {
+        done |= 1u << q;
+        ++cnt;
+      }
+    }
+    float c[3];
+    if (id == 0xFFFFu) {
+      c[0] = cam.sky[0];
+      c[1] = cam.sky[1];
+      c[2] = cam.sky[2];
+    } else {
+      shade_pixel(A, tris(id), px, py, c);
+    }
+    const float f = (float)cnt * wgt;
+    acc[0] += f * c[0];
+    acc[1] += f * c[1];
+    acc[2] += f * c[2];
+  }
+  rgb[0] = to_unorm8(acc[0]);
+  rgb[1] = to_unorm8(acc[1]);
+  rgb[2] = to_unorm8(acc[2]);
+}

@@ -1,0 +1,134 @@
+// reset.cuh -- device-side MiniWorldEnv.reset(): runs a lowered _gen_world() per env.
+//
+// Restates reference miniworld/miniworld.py:544-604 (reset), :839-909 (place_entity),
+// :272-284 (Room.point_inside), :987-1003 (_gen_static_data's texture draws via
+// opengl.py:113-145) and entity.py:405-407 / :505-516 (randomize), consuming the env's
+// numpy PCG64 stream in exactly the reference's call order, so that an episode reset on the
+// GPU lands on the same poses, colours and camera parameters as `env.reset()` in Python.
+// The level's `_gen_world()` is lowered on the host into a short program of
+// CHOICE / UNIFORM / PLACE ops (miniworld_b200/program.py); room layout comes from the
+// shared static template.  Levels whose topology is random per episode (Maze) reset on the
+// host and arrive through mwb_set_world instead.
+#pragma once
+#include "physics.cuh"
+
+// Room.point_inside: all(sum(edge_norms * (p - outline), axis=1) > 0)
+MWB_DEV bool room_contains(const mwb_room& r, double px, double pz) {
+  for (int e = 0; e < r.num_edges; ++e) {
+    double d = d_add(d_mul(r.edge_nx[e], d_sub(px, r.edge_px[e])), d_mul(r.edge_nz[e], d_sub(pz, r.edge_pz[e])));
+    if (!(d > 0.0)) return false;
+  }
+  return true;
+}
+
+MWB_DEV void device_reset(const DevState& S, int i) {
+  const size_t N = S.N;
+  NpRng rng = load_rng(S, i);
+  const mwb_params& P = S.params;
+  const int g = geom_index(S, i);
+  const mwb_room* rooms = S.rooms + (size_t)g * S.R;
+  const int n_rooms = S.num_rooms[g];
+
+  S.step_count[i] = 0;
+  S.carrying[i] = -1;
+  S.num_picked[i] = 0;
+  S.ghost_slot[i] = -1;
+  S.num_slots[i] = 0;
+  for (int e = 0; e < S.E; ++e) S.ent_proto[e * N + i] = -1;
+  // Agent() defaults (entity.py:459-474)
+  S.cam[0 * N + i] = P.cam_height;
+  S.cam[1 * N + i] = P.cam_fwd_disp;
+  S.cam[2 * N + i] = P.cam_pitch;
+  S.cam[3 * N + i] = P.cam_fov_y;
+
+  int ireg[8];
+  double freg[8];
+  bool static_done = false;
+  int slots = 0;
+
+  for (int pc = 0; pc < S.num_ops; ++pc) {
+    const mwb_op& op = S.ops[pc];
+    if (op.op == MWB_OP_END) break;
+    if (op.op == MWB_OP_CHOICE) {
+      ireg[op.a & 7] = (int)rng_integers(rng, (uint32_t)op.b);
+    } else if (op.op == MWB_OP_UNIFORM) {
+      freg[op.a & 7] = rng_uniform(rng, op.f[0], d_sub(op.f[1], op.f[0]));
+    } else if (op.op == MWB_OP_PLACE) {
+      if (!static_done) {
+        // first place_entity triggers _gen_static_data: per room Texture.get(wall/floor/ceil)
+        for (int r = 0; r < n_rooms; ++r)
+          for (int k = 0; k < 3; ++k) {
+            int v = 0;
+            if (S.domain_rand) v = (int)rng_integers(rng, (uint32_t)rooms[r].tex_count[k]);
+            S.room_tex[((size_t)i * S.R + r) * 3 + k] = rooms[r].tex_first[k] + v;
+          }
+        static_done = true;
+      }
+      int proto = op.a;
+      if (op.ireg_a >= 0) proto += ireg[op.ireg_a & 7] * op.stride_a;
+      if (op.ireg_b >= 0) proto += ireg[op.ireg_b & 7] * op.stride_b;
+      const mwb_proto& pr = S.protos[proto];
+      const double rad = pr.radius;
+      double x, z, dir;
+      for (;;) {
+        int r = op.room;
+        if (r < 0) {   // Generator.choice(n, p=room_probs): searchsorted(cdf, random(), 'right')
+          double u = rng_random(rng);
+          r = 0;
+          while (r < n_rooms - 1 && rooms[r].cdf <= u) ++r;
+        }
+        const mwb_room& rm = rooms[r];
+        double lx = isnan(op.f[0]) ? rm.min_x : op.f[0];
+        double hx = isnan(op.f[1]) ? rm.max_x : op.f[1];
+        double lz = isnan(op.f[2]) ? rm.min_z : op.f[2];
+        double hz = isnan(op.f[3]) ? rm.max_z : op.f[3];
+        double lox = d_sub(lx, rad), loz = d_sub(lz, rad);
+        x = rng_uniform(rng, lox, d_sub(d_add(hx, rad), lox));
+        (void)rng_random(rng);   // the y component: uniform(0, 0) still consumes a draw
+        z = rng_uniform(rng, loz, d_sub(d_add(hz, rad), loz));
+        if (!room_contains(rm, x, z)) continue;
+        S.num_slots[i] = slots;   // entities placed so far
+        if (world_intersect(S, i, -1, x, z, rad, pr.radius_is_f32 != 0) != MWB_HIT_NONE) continue;
+        dir = op.dir_freg >= 0 ? freg[op.dir_freg & 7]
+                               : rng_uniform(rng, -3.141592653589793, d_sub(3.141592653589793, -3.141592653589793));
+        break;
+      }
+      int e = slots++;
+      S.ent_proto[e * N + i] = proto;
+      S.ent_px[e * N + i] = x;
+      S.ent_py[e * N + i] = 0.0;
+      S.ent_pz[e * N + i] = z;
+      S.ent_dir[e * N + i] = dir;
+      for (int k = 0; k < 3; ++k) S.ent_col[((size_t)e * 3 + k) * N + i] = pr.color[k];
+      if (op.is_agent) S.agent_slot[i] = e;
+      S.num_slots[i] = slots;
+    }
+  }
+
+  // params.sample_many(rand, self, [sky_color, light_pos, light_color, light_ambient])
+  const double* defs[4] = {P.sky_color, P.light_pos, P.light_color, P.light_ambient};
+  const double* los[4] = {P.sky_color_lo, P.light_pos_lo, P.light_color_lo, P.light_ambient_lo};
+  const double* rngs[4] = {P.sky_color_rng, P.light_pos_rng, P.light_color_rng, P.light_ambient_rng};
+  for (int q = 0; q < 4; ++q)
+    for (int k = 0; k < 3; ++k)
+      S.envp[(size_t)(q * 3 + k) * N + i] = S.domain_rand ? rng_uniform(rng, los[q][k], rngs[q][k]) : defs[q][k];
+
+  // for ent in self.entities: ent.randomize(params, rand)
+  if (S.domain_rand) {
+    for (int e = 0; e < slots; ++e) {
+      const mwb_proto& pr = S.protos[S.ent_proto[e * N + i]];
+      if (pr.kind == MWB_KIND_BOX) {
+        for (int k = 0; k < 3; ++k) {
+          double c = d_add(pr.color[k], rng_uniform(rng, P.obj_color_bias_lo[k], P.obj_color_bias_rng[k]));
+          S.ent_col[((size_t)e * 3 + k) * N + i] = c < 0.0 ? 0.0 : (c > 1.0 ? 1.0 : c);
+        }
+      } else if (pr.kind == MWB_KIND_AGENT) {
+        S.cam[0 * N + i] = rng_uniform(rng, P.cam_height_lo, P.cam_height_rng);
+        S.cam[1 * N + i] = rng_uniform(rng, P.cam_fwd_disp_lo, P.cam_fwd_disp_rng);
+        S.cam[2 * N + i] = rng_uniform(rng, P.cam_pitch_lo, P.cam_pitch_rng);
+        S.cam[3 * N + i] = rng_uniform(rng, P.cam_fov_y_lo, P.cam_fov_y_rng);
+      }
+    }
+  }
+  store_rng(S, i, rng);
+}

@@ -1,0 +1,102 @@
+"""Builder for the device-side reset program (include/mwb.h: mwb_op).
+
+A level's `device_program(prog)` re-states its `_gen_world()` placement calls against this
+builder; the result is the short CHOICE / UNIFORM / PLACE program csrc/reset.cuh interprets
+per environment on the GPU, drawing from that env's numpy-exact PCG64 stream in the same
+order as the Python `_gen_world()` does (reference miniworld.py:839-909).
+`tests/test_reset_program.py` checks every level's program against its `_gen_world()`.
+"""
+import math
+
+import numpy as np
+
+from .engine import OP_CHOICE, OP_DTYPE, OP_PLACE, OP_UNIFORM, PROTO_DTYPE
+from .entity import Agent
+from .pack import proto_record
+
+
+class _Reg:
+    def __init__(self, index):
+        self.index = index
+
+
+class ProtoTable:
+    def __init__(self, base, strides):
+        self.base, self.strides = base, strides
+
+
+class ResetProgram:
+    def __init__(self):
+        self.ops = []
+        self.protos = []
+        self._ireg = 0
+        self._freg = 0
+        self.agent_proto = self.proto(Agent())
+        self.num_placed = 0
+
+    # ---- prototypes
+    def proto(self, ent):
+        self.protos.append(proto_record(ent))
+        return len(self.protos) - 1
+
+    def proto_table(self, nested):
+        """2-D table of entities indexed by two CHOICE results."""
+        base = len(self.protos)
+        rows, cols = len(nested), len(nested[0])
+        for row in nested:
+            assert len(row) == cols
+            for ent in row:
+                self.proto(ent)
+        return ProtoTable(base, (cols, 1))
+
+    # ---- random draws
+    def choice(self, n):
+        op = np.zeros((), OP_DTYPE)
+        op["op"], op["a"], op["b"] = OP_CHOICE, self._ireg, int(n)
+        self.ops.append(op)
+        self._ireg += 1
+        assert self._ireg <= 8
+        return _Reg(self._ireg - 1)
+
+    def uniform(self, lo, hi):
+        op = np.zeros((), OP_DTYPE)
+        op["op"], op["a"] = OP_UNIFORM, self._freg
+        op["f"][:2] = (float(lo), float(hi))
+        self.ops.append(op)
+        self._freg += 1
+        assert self._freg <= 8
+        return _Reg(self._freg - 1)
+
+    # ---- placement
+    def place(self, proto, index=None, room=None, dir=None, min_x=None, max_x=None, min_z=None, max_z=None,
+              _agent=False):
+        op = np.zeros((), OP_DTYPE)
+        op["op"] = OP_PLACE
+        op["ireg_a"] = op["ireg_b"] = -1
+        if isinstance(proto, ProtoTable):
+            op["a"] = proto.base
+            ia, ib = index
+            op["ireg_a"], op["stride_a"] = ia.index, proto.strides[0]
+            op["ireg_b"], op["stride_b"] = ib.index, proto.strides[1]
+        else:
+            op["a"] = int(proto)
+        op["room"] = -1 if room is None else int(room)
+        op["dir_freg"] = -1 if dir is None else dir.index
+        op["is_agent"] = int(_agent)
+        op["f"] = [math.nan if v is None else float(v) for v in (min_x, max_x, min_z, max_z)]
+        self.ops.append(op)
+        # reset registers are per-program-run, but CHOICE results feeding a PLACE are dead after it
+        if isinstance(proto, ProtoTable):
+            self._ireg = 0
+        self.num_placed += 1
+        return self.num_placed - 1
+
+    def place_agent(self, **kw):
+        return self.place(self.agent_proto, _agent=True, **kw)
+
+    # ---- output
+    def op_array(self):
+        return np.array(self.ops, OP_DTYPE)
+
+    def proto_array(self):
+        return np.array(self.protos, PROTO_DTYPE)

@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE (pixel oracle harness).  Not imported by the product.
+
+Builds the draw list of one observation from a host-side world object -- either the
+UNMODIFIED reference env (oracle/ref_stub.py) or the package's host mirror -- exactly as the
+reference submits it to OpenGL (Room._render miniworld.py:401-434, Box.render
+entity.py:409-432 + drawBox opengl.py:460-503, MeshEnt.render entity.py:150-161), and hands
+it to oracle/softgl.c.  Float conventions: whatever the reference passes through
+glVertex3f / glTexCoord2f / glNormal3f / glColor3f is rounded to float32 here; model
+transforms (glTranslatef / glRotatef / glScalef) are applied in float32, one rounding per
+operation, in the order documented in DESIGN.md.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libsoftgl.so")
+f32 = np.float32
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "_build/libsoftgl.so"])
+    return LIB
+
+
+class _Scene(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("dir", C.c_double), ("cam_height", C.c_double),
+                ("cam_fwd_disp", C.c_double), ("cam_pitch", C.c_double), ("cam_fov_y", C.c_double),
+                ("sky", C.c_double * 3), ("light_pos", C.c_double * 3), ("light_color", C.c_double * 3),
+                ("light_ambient", C.c_double * 3), ("width", C.c_int), ("height", C.c_int), ("samples", C.c_int),
+                ("num_tris", C.c_int), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("tri_uv", C.c_void_p),
+                ("tri_rgb", C.c_void_p), ("tri_tex", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.softgl_textures_create.restype = C.c_void_p
+        _lib.softgl_textures_create.argtypes = [C.c_int]
+        _lib.softgl_textures_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.softgl_textures_destroy.argtypes = [C.c_void_p]
+        _lib.softgl_render.argtypes = [C.POINTER(_Scene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+class TextureSet:
+    """name/variant -> oracle texture index; texels come from PNG-order RGB8 arrays."""
+
+    def __init__(self, textures):
+        """textures: list of uint8[H, W, 3] arrays (top row first), index = oracle texture id."""
+        self.n = len(textures)
+        self.h = lib().softgl_textures_create(self.n)
+        for i, t in enumerate(textures):
+            t = np.ascontiguousarray(t[..., :3], np.uint8)
+            lib().softgl_textures_set(self.h, i, t.shape[1], t.shape[0], t.ctypes.data)
+
+    def close(self):
+        if self.h:
+            lib().softgl_textures_destroy(self.h)
+            self.h = None
+
+
+def _fan(n):
+    return [(0, k, k + 1) for k in range(1, n - 1)]
+
+
+_BOX_FACES = None
+
+
+def _box_faces(sx, sy, sz):
+    """drawBox(x_min=-sx/2, x_max=+sx/2, y_min=0, y_max=sy, ...) vertex order (opengl.py:460-503)."""
+    x0, x1, y0, y1, z0, z1 = f32(-sx / 2), f32(sx / 2), f32(0), f32(sy), f32(-sz / 2), f32(sz / 2)
+    return [
+        ((0, 0, 1), [(x1, y1, z1), (x0, y1, z1), (x0, y0, z1), (x1, y0, z1)]),
+        ((0, 0, -1), [(x0, y1, z0), (x1, y1, z0), (x1, y0, z0), (x0, y0, z0)]),
+        ((-1, 0, 0), [(x0, y1, z1), (x0, y1, z0), (x0, y0, z0), (x0, y0, z1)]),
+        ((1, 0, 0), [(x1, y1, z0), (x1, y1, z1), (x1, y0, z1), (x1, y0, z0)]),
+        ((0, 1, 0), [(x1, y1, z1), (x1, y1, z0), (x0, y1, z0), (x0, y1, z1)]),
+        ((0, -1, 0), [(x1, y0, z0), (x1, y0, z1), (x0, y0, z1), (x0, y0, z0)]),
+    ]
+
+
+def _rot_y(v, c, s):
+    """glRotatef(theta, 0, 1, 0) on a float32 vector, one rounding per op: x' = x c + z s,
+    z' = z c - x s."""
+    x, y, z = (f32(a) for a in v)
+    return (f32(f32(x * c) + f32(z * s)), y, f32(f32(z * c) - f32(x * s)))
+
+
+def draw_list(env, tex_index):
+    """Triangles of one frame in submission order.  tex_index(texture_object) -> oracle id."""
+    P, Nn, UV, RGB, TX = [], [], [], [], []
+
+    def emit(verts, normals, uvs, color, tex):
+        for a, b, c in _fan(len(verts)):
+            P.append([verts[a], verts[b], verts[c]])
+            Nn.append([normals[a], normals[b], normals[c]])
+            UV.append([uvs[a], uvs[b], uvs[c]])
+            RGB.append([color, color, color])
+            TX.append(tex)
+
+    white = (1.0, 1.0, 1.0)
+    for r in env.rooms:
+        n = len(r.floor_verts)
+        emit([tuple(v) for v in r.floor_verts], [(0, 1, 0)] * n, [tuple(t) for t in r.floor_texcs], white,
+             tex_index(r.floor_tex))
+        if not r.no_ceiling:
+            emit([tuple(v) for v in r.ceil_verts], [(0, -1, 0)] * n, [tuple(t) for t in r.ceil_texcs], white,
+                 tex_index(r.ceil_tex))
+        for q in range(len(r.wall_verts) // 4):
+            sl = slice(4 * q, 4 * q + 4)
+            emit([tuple(v) for v in r.wall_verts[sl]], [tuple(v) for v in r.wall_norms[sl]],
+                 [tuple(t) for t in r.wall_texcs[sl]], white, tex_index(r.wall_tex))
+
+    def draw_entity(ent):
+        kind = type(ent).__name__
+        if kind == "Box":
+            c, s = f32(math.cos(ent.dir)), f32(math.sin(ent.dir))
+            t = [f32(v) for v in ent.pos]
+            sx, sy, sz = ent.size
+            col = tuple(float(v) for v in ent.color_vec)
+            for nrm, quad in _box_faces(sx, sy, sz):
+                vs = []
+                for v in quad:
+                    rx, ry, rz = _rot_y(v, c, s)
+                    vs.append((f32(rx + t[0]), f32(ry + t[1]), f32(rz + t[2])))
+                nn = _rot_y(nrm, c, s)
+                emit(vs, [nn] * 4, [(0.0, 0.0)] * 4, col, -1)
+        elif hasattr(ent, "mesh"):
+            raise NotImplementedError("mesh entities: see draw_list_mesh")
+
+    # display list first (static entities), then the dynamic ones, both in list order
+    for ent in env.entities:
+        if ent.is_static and ent is not env.agent:
+            draw_entity(ent)
+    for ent in env.entities:
+        if not ent.is_static and ent is not env.agent:
+            draw_entity(ent)
+    T = len(P)
+    return (np.asarray(P, np.float32).reshape(T, 3, 3), np.asarray(Nn, np.float32).reshape(T, 3, 3),
+            np.asarray(UV, np.float32).reshape(T, 3, 2), np.asarray(RGB, np.float32).reshape(T, 3, 3),
+            np.asarray(TX, np.int32))
+
+
+def render(env, texset, tex_index, width=80, height=60, samples=8, want_codes=False):
+    """Oracle observation of `env` (reference env or host mirror): (rgb u8[H,W,3], depth f32[H,W,1])."""
+    pos, nrm, uv, rgb, tx = draw_list(env, tex_index)
+    sc = _Scene()
+    a = env.agent
+    for k in range(3):
+        sc.pos[k] = float(a.pos[k])
+        sc.sky[k] = float(env.sky_color[k])
+        sc.light_pos[k] = float(env.light_pos[k])
+        sc.light_color[k] = float(env.light_color[k])
+        sc.light_ambient[k] = float(env.light_ambient[k])
+    sc.dir = float(a.dir)
+    sc.cam_height, sc.cam_fwd_disp = float(a.cam_height), float(getattr(a, "cam_fwd_disp", 0.0))
+    sc.cam_pitch, sc.cam_fov_y = float(a.cam_pitch), float(a.cam_fov_y)
+    sc.width, sc.height, sc.samples = width, height, samples
+    sc.num_tris = len(tx)
+    sc.tri_pos, sc.tri_nrm, sc.tri_uv = pos.ctypes.data, nrm.ctypes.data, uv.ctypes.data
+    sc.tri_rgb, sc.tri_tex = rgb.ctypes.data, tx.ctypes.data
+    out = np.zeros((height, width, 3), np.uint8)
+    depth = np.zeros((height, width, 1), np.float32)
+    codes = np.zeros((height, width), np.uint16)
+    rc = lib().softgl_render(C.byref(sc), texset.h, out.ctypes.data, depth.ctypes.data, codes.ctypes.data)
+    assert rc == 0
+    return (out, depth, codes) if want_codes else (out, depth)
