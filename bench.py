@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched MiniWorld step path on B200 (and the CPU arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json): MiniWorld-FourRooms-v0, N_envs = 4096 per GPU, 80x60 RGB + depth,
+uniformly random actions, next-step auto-reset, env i seeded 1000 + i.  One "step" = one
+mwb_step call: K1 (physics / reward / device resets) + K2 (render RGB + depth) for every env.
+
+  value  : whole-job env-steps/s with actions and outputs resident in HBM (torch CUDA tensors),
+           timed with CUDA events over exactly K steps, barrier + synchronize on both sides,
+           max over ranks.  Multi-GPU: envs shard 4096 per rank (weak scaling); every step the
+           uint8 observations are gathered to rank 0 with NCCL (inside the timed region).
+  e2e    : the same K steps through the public host API (BatchedMiniWorld.step_host): actions
+           from pinned host memory, observations / rewards / flags back to pinned host memory,
+           copies inside the timed region.
+  roofline: K2's algorithmic bytes (framebuffer written once) / its CUDA-event time inside the
+           timed region, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline: the oracle port (oracle/physics_port.py + oracle/softgl.c) on host cores.
+
+--impl reference: the reference's own Pyglet/OpenGL path cannot run here (no pyglet, GL or
+gymnasium in the image; /root/reference is absent on the GPU box), so this arm times the CPU
+oracle port of the same workload on all host cores, one process per core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LEVEL = "MiniWorld-FourRooms-v0"
+N_ENVS = 4096
+W, H = 80, 60
+BYTES_RGB = W * H * 3
+BYTES_DEPTH = W * H * 4
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+
+def _port_worker(args):
+    """One process: the oracle port of the workload on one core; `warm_s` untimed seconds, then
+    `budget_s` timed seconds.  Returns (env-steps, seconds) of the timed part."""
+    rank, warm_s, budget_s, seed0 = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.envs import LEVELS
+    from oracle import softgl
+    from oracle.physics_port import PortEnv
+    port = PortEnv(LEVELS[LEVEL](device=None))
+    port.reset(seed=seed0 + rank)
+    ts = softgl.TextureSet([t.texels for t in Texture.registry])
+    rng = np.random.default_rng(12345 + rank)
+    tex_index = lambda tex: tex.tex_id
+    n, done = 0, False
+    t_start = time.perf_counter()
+    t0 = None
+    while True:
+        now = time.perf_counter()
+        if t0 is None and now - t_start >= warm_s:
+            t0, n = now, 0
+        if t0 is not None and now - t0 >= budget_s:
+            break
+        if done:
+            port.reset()
+            done = False
+        else:
+            _, te, tr, _ = port.step(int(rng.integers(0, 3)))
+            done = te or tr
+        softgl.render(port.env, ts, tex_index, W, H, 8)     # RGB + depth in one pass
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_port_throughput(cores, warm_s, budget_s):
+    if cores == 1:
+        n, dt = _port_worker((0, warm_s, budget_s, 1000))
+        return n / dt, n
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_port_worker, [(r, warm_s, budget_s, 1000) for r in range(cores)])
+    return sum(n / dt for n, dt in res), sum(n for n, _ in res)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import softgl
+    softgl.build()
+    cores = os.cpu_count() or 1
+    # the K "steps" are K equal slices of one continuous run (each slice a bounded sample of
+    # the workload); W warm-up slices are discarded.  Whole arm <= ~2 minutes.
+    slice_s = min(1.0, 100.0 / max(1, args.steps + args.warmup))
+    warm_s, budget = slice_s * args.warmup, slice_s * args.steps
+    value, vals = cpu_port_throughput(cores, warm_s, budget)
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
+        "config": {"workload": "%s 80x60 RGB+depth, random actions, auto-reset" % LEVEL, "n_envs": cores,
+                   "note": "reference Pyglet/GL path cannot run on this box (no pyglet/GL/gymnasium); "
+                           "CPU oracle port timed instead, one env process per host core"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d env-steps total in %.0f s on %d processes (one env each)" % (vals, budget, cores)},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from miniworld_b200.batched import BatchedMiniWorld
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    N = args.envs
+    env = BatchedMiniWorld(LEVEL, N, obs_width=W, obs_height=H, want_depth=True, device=local)
+    env.reset(seed=1000 + rank * N)
+    total = Wm + K
+    gen = np.random.default_rng(12345 + rank)
+    acts_np = gen.integers(0, env.action_space.n, size=(total, N), dtype=np.int32)
+    acts = torch.as_tensor(acts_np, device=dev)
+    gather_list = None
+    if world > 1 and rank == 0:
+        gather_list = [torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(world)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(t):
+        obs, rew, te, tr, info = env.step(acts[t])
+        if world > 1:
+            dist.gather(obs, gather_list, dst=0)
+        return obs, rew, te, tr
+
+    # ---- device-resident arm
+    for t in range(Wm):
+        one_step(t)
+    barrier()
+    env.engine.profile(True)
+    env.engine.profile_read()
+    launches0 = env.engine.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    done_steps = torch.zeros((), dtype=torch.int64, device=dev)
+    e0.record()
+    for t in range(Wm, total):
+        obs, rew, te, tr = one_step(t)
+        done_steps += (te | tr).sum()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    k1_ms, k2_ms, n1, n2 = env.engine.profile_read()
+    env.engine.profile(False)
+    launches = env.engine.launch_count() - launches0
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * N * K / (ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    out = dict(obs=pin((N, H, W, 3), torch.uint8), depth=pin((N, H, W, 1), torch.float32),
+               reward=pin((N,), torch.float64), terminated=pin((N,), torch.uint8), truncated=pin((N,), torch.uint8))
+    acts_pin = torch.as_tensor(acts_np).pin_memory().numpy()
+    for t in range(min(Wm, 3)):
+        env.step_host(acts_pin[t], out)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(Wm, total):
+        env.step_host(acts_pin[t], out)      # synchronous: returns when the host buffers are filled
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_value = world * N * K / e2e_s
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_kind = measured_hbm()
+        bytes_per_launch = N * (BYTES_RGB + BYTES_DEPTH)
+        k2_avg_ms = k2_ms / max(1, n2)
+        achieved = bytes_per_launch / (k2_avg_ms * 1e-3) / 1e9 if n2 else None
+        cpu = {"value": None, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": "skipped"}
+        if world == 1 and not args.no_cpu:
+            from oracle import softgl
+            softgl.build()
+            v, n = cpu_port_throughput(1, 1.0, 12.0)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                   "sample": "%d env-steps of 1 env in 12 s (oracle/physics_port.py + oracle/softgl.c)" % n}
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64+f32", "data": "synthetic",
+            "config": {"workload": "%s N_envs=%d per GPU, 80x60 RGB+depth, 8x MSAA, random actions, next-step "
+                                   "auto-reset on device" % (LEVEL, N),
+                       "global_envs": world * N, "obs_gather": "NCCL gather of uint8 obs to rank 0" if world > 1 else "none",
+                       "l2": "per-step outputs %.1f MB > 126 MB L2; no explicit flush" % (bytes_per_launch / 1e6),
+                       "episodes_finished_in_timed_region": int(done_steps.item())},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "traffic": None,
+                         "kernel": "render_kernel<8>", "kernel_avg_ms": k2_avg_ms, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "k1_avg_ms": k1_ms / max(1, n1), "kernel_share_of_step": k2_ms / ms if ms else None},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
+                    "d2h_bytes_per_step": N * (BYTES_RGB + BYTES_DEPTH + 8 + 1 + 1), "ms_per_step": e2e_s * 1e3 / K},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default 4096)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -275,6 +275,12 @@ int mwb_get_state(mwb_handle* h, const mwb_state_view* out);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mwb_launch_count(mwb_handle* h);
 
+/* Device-side timing of the two kernels: when enabled, every K1 / K2 launch is bracketed by
+ * CUDA events on the launching stream; mwb_profile_read synchronises, returns the summed
+ * milliseconds and launch counts since the last read, and clears them (bench.py roofline). */
+int mwb_profile(mwb_handle* h, int enable);
+int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int64_t* k1_launches, int64_t* k2_launches);
+
 /* sizeof() of every ABI struct, in declaration order (config, params, tex_desc, mesh_desc,
  * room, quad, seg, proto, entity, op, geometry, world, rng_state, state_view): lets a
  * binding verify its mirror of this header.  Returns the number of entries written. */

@@ -103,6 +103,10 @@ struct mwb_handle {
   WorldUpload* d_upload;
   int tri_cap;
   bool have_params, have_protos, have_template;
+  bool profiling;
+#ifndef MWB_HOSTSIM
+  std::vector<cudaEvent_t> ev_k1, ev_k2;   // start/stop pairs
+#endif
   // asset storage
   void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops;
 };
@@ -309,6 +313,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   mwb_handle* h = new mwb_handle();
   h->cfg = *cfg;
   h->launches = 0;
+  h->profiling = false;
   h->have_params = h->have_protos = h->have_template = false;
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
   h->protos = h->ops = nullptr;
@@ -667,16 +672,65 @@ extern "C" int mwb_set_world(mwb_handle* h, const int32_t* env_ids, int n, const
   return launch_upload(h, up, false);
 }
 
+// ------------------------------------------------------------------ profiling
+#ifndef MWB_HOSTSIM
+static void prof_mark(mwb_handle* h, std::vector<cudaEvent_t>& v, stream_t s) {
+  if (!h->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  v.push_back(e);
+}
+static double prof_drain(std::vector<cudaEvent_t>& v, int64_t* count) {
+  double ms = 0.0;
+  *count = 0;
+  for (size_t k = 0; k + 1 < v.size(); k += 2) {
+    float t = 0.0f;
+    cudaEventSynchronize(v[k + 1]);
+    if (cudaEventElapsedTime(&t, v[k], v[k + 1]) == cudaSuccess) {
+      ms += t;
+      ++*count;
+    }
+  }
+  for (cudaEvent_t e : v) cudaEventDestroy(e);
+  v.clear();
+  return ms;
+}
+#endif
+
+extern "C" int mwb_profile(mwb_handle* h, int enable) {
+  if (!h) return fail(MWB_EINVAL, "null handle");
+  h->profiling = enable != 0;
+  return MWB_OK;
+}
+
+extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int64_t* k1_launches, int64_t* k2_launches) {
+  if (!h) return fail(MWB_EINVAL, "null handle");
+  double a = 0.0, b = 0.0;
+  int64_t na = 0, nb = 0;
+#ifndef MWB_HOSTSIM
+  a = prof_drain(h->ev_k1, &na);
+  b = prof_drain(h->ev_k2, &nb);
+#endif
+  if (k1_ms) *k1_ms = a;
+  if (k2_ms) *k2_ms = b;
+  if (k1_launches) *k1_launches = na;
+  if (k2_launches) *k2_launches = nb;
+  return MWB_OK;
+}
+
 // ------------------------------------------------------------------ ABI: the hot path
 static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s) {
   if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * (int)sizeof(TriRec);
+  prof_mark(h, h->ev_k2, s);
   switch (h->S.msaa) {
     case 1: render_kernel<1><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
     case 4: render_kernel<4><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
     default: render_kernel<8><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
   }
+  prof_mark(h, h->ev_k2, s);
   h->launches++;
   CK(cudaGetLastError());
 #else
@@ -726,7 +780,9 @@ extern "C" int mwb_step(mwb_handle* h, const int32_t* actions, const double* ste
   uint8_t* d_te = terminated && is_device_ptr(terminated) ? terminated : h->d_term;
   uint8_t* d_tr = truncated && is_device_ptr(truncated) ? truncated : h->d_trunc;
 #ifndef MWB_HOSTSIM
+  prof_mark(h, h->ev_k1, s);
   step_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(h->S, d_act, d_sp, d_rew, d_te, d_tr);
+  prof_mark(h, h->ev_k1, s);
   h->launches++;
   CK(cudaGetLastError());
 #else

@@ -111,7 +111,7 @@ EXPORTS = (
     "mwb_create", "mwb_destroy", "mwb_last_error", "mwb_upload_textures", "mwb_upload_meshes",
     "mwb_set_params", "mwb_set_protos", "mwb_set_template", "mwb_set_program", "mwb_seed",
     "mwb_reset", "mwb_set_world", "mwb_step", "mwb_render_obs", "mwb_get_state",
-    "mwb_launch_count", "mwb_abi_sizes",
+    "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read",
 )
 
 _libs = {}
@@ -145,6 +145,9 @@ def load_library(lib_path=None):
     lib.mwb_launch_count.argtypes = [vp]
     lib.mwb_launch_count.restype = C.c_int64
     lib.mwb_abi_sizes.argtypes = [i32p, C.c_int]
+    lib.mwb_profile.argtypes = [vp, C.c_int]
+    lib.mwb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64)]
     for name in EXPORTS:
         if name not in ("mwb_last_error", "mwb_launch_count"):
             getattr(lib, name).restype = C.c_int
@@ -348,6 +351,15 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.mwb_launch_count(self.h))
+
+    def profile(self, enable=True):
+        self._check(self.lib.mwb_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """(k1_ms, k2_ms, k1_launches, k2_launches) since the last read, CUDA-event timed."""
+        a, b, na, nb = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+        self._check(self.lib.mwb_profile_read(self.h, C.byref(a), C.byref(b), C.byref(na), C.byref(nb)))
+        return a.value, b.value, na.value, nb.value
 
     # ---- state
     def get_state(self, rng=False, room_tex=False):

@@ -250,8 +250,24 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
     float ZC = ((v[0]->Z * EC[0] + v[1]->Z * EC[1]) + v[2]->Z * EC[2]) / det;
     const Tex* tex = sc->tri_tex[ti] >= 0 ? &ts->tex[sc->tri_tex[ti]] : NULL;
 
-    for (int py = 0; py < H; ++py)
-      for (int px = 0; px < W; ++px) {
+    /* loop bounds only: when the whole triangle is in front of the eye its samples lie
+     * inside the bounding box of its projected vertices (padded by one pixel) */
+    int bx0 = 0, bx1 = W - 1, by0 = 0, by1 = H - 1;
+    if (g[0].W > 1e-3f && g[1].W > 1e-3f && g[2].W > 1e-3f) {
+      float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+      for (int k = 0; k < 3; ++k) {
+        float sx = g[k].X / g[k].W, sy = g[k].Y / g[k].W;
+        xmin = sx < xmin ? sx : xmin; xmax = sx > xmax ? sx : xmax;
+        ymin = sy < ymin ? sy : ymin; ymax = sy > ymax ? sy : ymax;
+      }
+      if (xmax < -1.0f || ymax < -1.0f || xmin > (float)W + 1.0f || ymin > (float)H + 1.0f) continue;
+      if (xmin - 1.0f > 0.0f) bx0 = (int)(xmin - 1.0f);
+      if (ymin - 1.0f > 0.0f) by0 = (int)(ymin - 1.0f);
+      if (xmax + 1.0f < (float)(W - 1)) bx1 = (int)(xmax + 1.0f);
+      if (ymax + 1.0f < (float)(H - 1)) by1 = (int)(ymax + 1.0f);
+    }
+    for (int py = by0; py <= by1; ++py)
+      for (int px = bx0; px <= bx1; ++px) {
         unsigned pass = 0;
         uint16_t codes[8];
         for (int s = 0; s < NS; ++s) {

@@ -1,0 +1,45 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session")
+def libmwb_path():
+    """In-tree libmwb.so (built by __graft_entry__.build())."""
+    path = os.path.join(ROOT, "miniworld_b200", "libmwb.so")
+    nvcc = os.path.exists("/usr/local/cuda/bin/nvcc")
+    if nvcc:     # `make` is a no-op when the library is newer than its sources
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "miniworld_b200", "csrc")],
+                              stdout=subprocess.DEVNULL)
+    return path
+
+
+@pytest.fixture(scope="session")
+def hostsim_path():
+    """Test-only CPU build of the kernels' inner functions (tests/hostsim/build.sh)."""
+    out = subprocess.check_output([os.path.join(ROOT, "tests", "hostsim", "build.sh")]).decode().strip().splitlines()[-1]
+    return out
+
+
+@pytest.fixture(scope="session")
+def softgl_lib():
+    from oracle import softgl
+    softgl.build()
+    return softgl
+
+
+def golden(name):
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))

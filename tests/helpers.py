@@ -1,0 +1,90 @@
+"""Shared comparison code for the CPU (host-sim) and GPU parity tests."""
+import numpy as np
+
+from miniworld_b200.batched import BatchedMiniWorld
+from miniworld_b200.engine import RNG_DTYPE, rng_state_of
+
+CASES = {
+    # golden name: (level id, domain_rand)
+    "hallway": ("MiniWorld-Hallway-v0", False),
+    "oneroom": ("MiniWorld-OneRoom-v0", False),
+    "fourrooms": ("MiniWorld-FourRooms-v0", False),
+    "fourrooms_dr": ("MiniWorld-FourRooms-v0", True),
+    "pickup": ("MiniWorld-PickupObjects-v0", False),
+    "pickup_dr": ("MiniWorld-PickupObjects-v0", True),
+    "maze_dr": ("MiniWorld-MazeS8-v0", True),
+    "mazes3": ("MiniWorld-MazeS3-v0", False),
+}
+
+
+def make_env(name, g, lib_path=None, n=None, **kw):
+    level, dr = CASES[name]
+    N = g["actions"].shape[1] if n is None else n
+    env = BatchedMiniWorld(level, N, domain_rand=dr, autoreset=True, lib_path=lib_path, **kw)
+    seeds = [1000 + i for i in range(N)]
+    if env.device_reset:
+        env.engine.seed(np.arange(N), np.array([rng_state_of(s) for s in seeds], RNG_DTYPE))
+        env.engine.reset()
+    else:
+        env._host_reset(np.arange(N, dtype=np.int32), seeds)
+    env._seeded = True
+    return env
+
+
+def state_mismatches(env, g, t, N, out=None):
+    """List of human-readable differences between the engine state and golden row t."""
+    st = env.get_state()
+    bad = []
+
+    def cmp(label, a, b):
+        if not np.array_equal(a, b):
+            rows = np.nonzero(~np.all((np.asarray(a) == np.asarray(b)).reshape(len(a), -1), axis=1))[0]
+            bad.append("%s: envs %s e.g. got %r want %r" % (label, rows[:4], np.asarray(a)[rows[0]], np.asarray(b)[rows[0]]))
+
+    cmp("agent.pos", st["agent_pos"], g["pos"][t, :N])
+    cmp("agent.dir", st["agent_dir"], g["dir"][t, :N])
+    cmp("step_count", st["step_count"], g["step_count"][t, :N])
+    cmp("cam", st["cam"], g["cam"][t, :N])
+    cmp("sky_color", st["env_params"][:, 0:3], g["sky_color"][t, :N])
+    cmp("light_pos", st["env_params"][:, 3:6], g["light_pos"][t, :N])
+    cmp("light_color", st["env_params"][:, 6:9], g["light_color"][t, :N])
+    cmp("light_ambient", st["env_params"][:, 9:12], g["light_ambient"][t, :N])
+    ents = st["ents"]
+    live = ents["proto"] >= 0
+    if not np.array_equal(live.sum(1), g["n_ents"][t, :N]):
+        bad.append("entity count: got %r want %r" % (live.sum(1)[:8], g["n_ents"][t, :8]))
+    else:
+        for i in range(N):
+            idx = np.nonzero(live[i])[0]
+            if not (np.array_equal(ents[i, idx]["pos"], g["ent_pos"][t, i, :len(idx)]) and
+                    np.array_equal(ents[i, idx]["dir"], g["ent_dir"][t, i, :len(idx)])):
+                bad.append("entity poses of env %d" % i)
+                break
+            boxes = g["ent_kind"][t, i, :len(idx)] == 1
+            if not np.array_equal(ents[i, idx]["color"][boxes], g["ent_color"][t, i, :len(idx)][boxes]):
+                bad.append("box colours of env %d" % i)
+                break
+    if out is not None:
+        cmp("reward", out["reward"], g["reward"][t, :N])
+        cmp("terminated", out["terminated"].astype(bool), g["terminated"][t, :N])
+        cmp("truncated", out["truncated"].astype(bool), g["truncated"][t, :N])
+    return bad
+
+
+def run_trajectory(name, g, lib_path=None, steps=None, n=None, check_every=1):
+    """Replay the golden action stream and compare every state bit-for-bit."""
+    env = make_env(name, g, lib_path, n)
+    N = env.num_envs
+    T = g["actions"].shape[0] if steps is None else min(steps, g["actions"].shape[0])
+    bad = state_mismatches(env, g, 0, N)
+    assert not bad, "after reset: " + "; ".join(bad)
+    out = None
+    for t in range(T):
+        out = env.step_host(g["actions"][t, :N], out, render=False)
+        if (t + 1) % check_every == 0 or t == T - 1:
+            bad = state_mismatches(env, g, t + 1, N, out)
+            assert not bad, "step %d: %s" % (t + 1, "; ".join(bad))
+        else:
+            assert np.array_equal(out["reward"], g["reward"][t + 1, :N]), "reward at step %d" % (t + 1)
+    env.close()
+    return T, N

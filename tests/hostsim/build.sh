@@ -7,5 +7,5 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 OUT="$HERE/../_hostsim"
 mkdir -p "$OUT"
 g++ -x c++ -std=c++17 -O2 -ffp-contract=off -mfma -fPIC -shared -DMWB_HOSTSIM \
-    -Wno-unused-function -o "$OUT/libmwb_hostsim.so" "$HERE/../../miniworld_b200/csrc/mwb.cu" -lm
+    -Wno-unused-function -o "$OUT/libmwb_hostsim.so" "$HERE/../../miniworld_b200/csrc/mwb.cu" "$HERE/extra.cpp" -lm
 echo "$OUT/libmwb_hostsim.so"

@@ -1,0 +1,96 @@
+"""Size-independent properties at BASELINE.json's full sizes, and the drop-in single-env API
+(the reference's own tests/test_miniworld.py invariants re-run on this engine)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fourrooms_4096_properties(libmwb_path):
+    import torch
+    from miniworld_b200.batched import BatchedMiniWorld
+    N, T = 4096, 300
+    acts = np.random.default_rng(12345).integers(0, 3, size=(T, N), dtype=np.int32)
+    runs = []
+    for rep in range(2):
+        env = BatchedMiniWorld("MiniWorld-FourRooms-v0", N, want_depth=True)
+        env.reset(seed=1000)
+        a = torch.as_tensor(acts, device="cuda")
+        tot_r = torch.zeros(N, dtype=torch.float64, device="cuda")
+        n_done = 0
+        for t in range(T):
+            obs, r, te, tr, info = env.step(a[t])
+            tot_r += r
+            n_done += int((te | tr).sum())
+            assert bool(((r == 0) | ((r > 0.8) & (r <= 1.0))).all())      # 1 - 0.2 * frac
+            assert not bool((te & (r == 0)).any())
+        st = env.get_state()
+        # agents stay inside the floorplan minus their radius (test_collision_detection's invariant)
+        assert (np.abs(st["agent_pos"][:, [0, 2]]) <= 7 - 0.4 + 1e-9).all()
+        assert (st["step_count"] <= 250).all() and (st["step_count"] >= 0).all()
+        d = info["depth"]
+        assert bool((d > 0.04 - 1e-6).all()) and bool((d <= 100.0).all())
+        assert 0 < float(obs.float().mean()) < 255
+        runs.append((obs.cpu().numpy().copy(), tot_r.cpu().numpy().copy(), st["agent_pos"].copy(), n_done))
+        env.close()
+    # same seeds + same actions => identical pixels, rewards and poses (check_env's determinism)
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][2], runs[1][2]) and runs[0][3] == runs[1][3] and runs[0][3] > 4096
+
+
+def test_single_env_api_collision_invariant(libmwb_path):
+    """reference tests/test_miniworld.py:82-95 on the drop-in class."""
+    from miniworld_b200.envs import OneRoom
+    env = OneRoom()
+    for _ in range(6):
+        env.reset()
+        room = env.rooms[0]
+        for _ in range(30):
+            obs, r, te, tr, _ = env.step(env.actions.move_forward)
+            x, _, z = env.agent.pos
+            assert room.min_x <= x <= room.max_x and room.min_z <= z <= room.max_z
+            assert obs.shape == env.observation_space.shape and obs.dtype == np.uint8
+    env.close()
+
+
+def test_single_env_matches_golden_and_batched(libmwb_path):
+    """MiniWorldEnv (N = 1 view, host RNG, Python level rule) walks the reference trajectory."""
+    from conftest import golden
+    from miniworld_b200.envs import FourRooms, PickupObjects
+    for name, cls in (("fourrooms", FourRooms), ("pickup", PickupObjects)):
+        g = golden(name)
+        env = cls()
+        env.reset(seed=1000)
+        assert np.array_equal(env.agent.pos, g["pos"][0, 0])
+        done = False
+        for t in range(120):
+            if done:
+                env.reset()
+                r, te, tr = 0.0, False, False
+            else:
+                obs, r, te, tr, _ = env.step(int(g["actions"][t, 0]))
+            done = te or tr
+            assert np.array_equal(env.agent.pos, g["pos"][t + 1, 0]) and env.agent.dir == g["dir"][t + 1, 0]
+            assert r == g["reward"][t + 1, 0] and te == g["terminated"][t + 1, 0] and tr == g["truncated"][t + 1, 0]
+        assert 0 < obs.mean() < 255
+        d = env.render_depth()
+        assert d.shape == (60, 80, 1) and d.dtype == np.float32
+        env.close()
+
+
+def test_all_levels_no_intersection_after_reset(libmwb_path):
+    """reference tests/test_miniworld.py:98-120 (domain_rand on; agent never spawns inside anything)."""
+    from miniworld_b200.envs import LEVELS
+    for eid, cls in LEVELS.items():
+        if "Maze-v0" in eid or "MazeS8" in eid:
+            continue      # 8x8 maze: covered by the golden-trajectory test
+        env = cls(domain_rand=True)
+        rng = np.random.default_rng(0)
+        for _ in range(3):
+            env.reset()
+            assert not env.intersect(env.agent, env.agent.pos, env.agent.radius)
+            for _ in range(20):
+                _, _, te, tr, _ = env.step(int(rng.integers(0, env.action_space.n)))
+                if te or tr:
+                    env.reset()
+        env.close()

@@ -1,0 +1,36 @@
+"""Kernel logic on the CPU: the MWB_DEV functions of csrc/ compiled by g++ (tests/hostsim)
+replay reference trajectories and render frames.  This checks the kernels' arithmetic where
+no GPU exists; the `-m gpu` tests run the real kernels through libmwb.so."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from helpers import CASES, make_env, run_trajectory
+
+
+@pytest.mark.parametrize("name,steps,n", [("hallway", 60, 16), ("oneroom", 60, 16), ("fourrooms", 80, 16),
+                                          ("fourrooms_dr", 60, 8), ("pickup", 120, 8), ("pickup_dr", 60, 8),
+                                          ("mazes3", 40, 4)])
+def test_physics_and_reset_bit_exact(hostsim_path, name, steps, n):
+    run_trajectory(name, golden(name), hostsim_path, steps=steps, n=n, check_every=10)
+
+
+def test_render_matches_oracle(hostsim_path, softgl_lib):
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.envs import LEVELS
+    g = golden("fourrooms")
+    env = make_env("fourrooms", g, hostsim_path, n=3, want_depth=True)
+    N = env.num_envs
+    obs = np.zeros((N, 60, 80, 3), np.uint8)
+    depth = np.zeros((N, 60, 80, 1), np.float32)
+    env.engine.render(obs=obs, depth=depth)
+    ts = softgl_lib.TextureSet([t.texels for t in Texture.registry])
+    for i in range(N):
+        ref = LEVELS["MiniWorld-FourRooms-v0"](device=None)
+        ref.reset(seed=1000 + i)
+        rgb, d = softgl_lib.render(ref, ts, lambda tex: tex.tex_id)
+        assert np.abs(rgb.astype(int) - obs[i].astype(int)).max() <= 1
+        assert np.array_equal(d, depth[i])
+        assert 0 < rgb.mean() < 255
+    ts.close()
+    env.close()
