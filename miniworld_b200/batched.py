@@ -132,7 +132,12 @@ class BatchedMiniWorld:
         return self.render(), {}
 
     def _host_reset(self, ids, seeds, hold=False):
+        """Host-side reset of the listed envs (levels without a device program).  The env's numpy
+        stream is shared with the device: per-step domain-rand draws happen in K1, so the
+        stream position is pulled from the device before `_gen_world()` runs on the host and
+        pushed back afterwards."""
         worlds = []
+        dev_rng = self.engine.get_state(rng=True)["rng"] if (self.domain_rand and self._seeded) else None
         for k, i in enumerate(ids):
             w = self._workers[i]
             if w is None:
@@ -140,6 +145,8 @@ class BatchedMiniWorld:
                 w.__dict__.update({k2: v for k2, v in self.proto_env.__dict__.items()
                                    if k2 not in ("_np_random", "agent", "entities", "rooms", "wall_segs")})
                 w._np_random = None
+            elif dev_rng is not None and (seeds is None):
+                w._np_random = generator_from_state(dev_rng[i])
             w.reset(seed=None if seeds is None else seeds[k])
             worlds.append(pack.pack_world(w))
             worlds[-1]["hold"] = int(hold)
@@ -147,6 +154,8 @@ class BatchedMiniWorld:
         self.engine.sync_assets()
         self.engine.set_protos(worlds[0]["protos"])
         self.engine.set_world(ids, worlds)
+        if self.domain_rand:
+            self.engine.seed(ids, np.array([rng_state_of(self._workers[i].np_random) for i in ids], RNG_DTYPE))
 
     # ------------------------------------------------------------------ step / render
     def step(self, actions):

@@ -101,7 +101,15 @@ def _install_pyglet():
     image.ImageData = _Noop
     pyglet.image = image
     graphics = types.ModuleType("pyglet.graphics")
-    graphics.vertex_list = lambda *a, **k: _Noop("vlist")
+    def _vertex_list(count, *attrs):
+        """Capture what the reference hands to pyglet (objmesh.py:198-204) so the oracle
+        harness can read the mesh arrays back: .attrs['v3f'] etc. are flat float arrays."""
+        vl = _Noop("vlist")
+        vl.count = count
+        vl.attrs = {fmt: data for fmt, data in attrs}
+        return vl
+
+    graphics.vertex_list = _vertex_list
     pyglet.graphics = graphics
     window = types.ModuleType("pyglet.window")
     window.Window = lambda *a, **k: _Noop("window")

@@ -136,7 +136,32 @@ def draw_list(env, tex_index):
                 nn = _rot_y(nrm, c, s)
                 emit(vs, [nn] * 4, [(0.0, 0.0)] * 4, col, -1)
         elif hasattr(ent, "mesh"):
-            raise NotImplementedError("mesh entities: see draw_list_mesh")
+            # glTranslatef(pos) glScalef(s, s, s) glRotatef(dir): v' = pos + s * (R v); the normal
+            # goes through the inverse transpose, R n / s, and is NOT renormalised
+            m = ent.mesh
+            c, s = f32(math.cos(ent.dir)), f32(math.sin(ent.dir))
+            t = np.asarray(ent.pos, dtype=np.float32)
+            sc = f32(ent.scale)
+            inv = f32(f32(1.0) / sc)
+            if hasattr(m, "vlists"):      # the reference's ObjMesh (arrays captured by ref_stub)
+                cat = lambda key, k: np.concatenate([np.asarray(v.attrs[key], np.float32).reshape(-1, 3, k)
+                                                     for v in m.vlists])
+                V, Nm, Tm, Cm = cat("v3f", 3), cat("n3f", 3), cat("t2f", 2), cat("c3f", 3)
+            else:                         # the package's host mirror (assets.ObjMesh)
+                V, Nm, Tm, Cm = m.verts, m.norms, m.texcs, m.colors
+            x, y, z = V[..., 0], V[..., 1], V[..., 2]
+            wx = (x * c + z * s) * sc + t[0]
+            wy = y * sc + t[1]
+            wz = (z * c - x * s) * sc + t[2]
+            nx = (Nm[..., 0] * c + Nm[..., 2] * s) * inv
+            ny = Nm[..., 1] * inv
+            nz = (Nm[..., 2] * c - Nm[..., 0] * s) * inv
+            F = V.shape[0]
+            P.extend(np.stack([wx, wy, wz], axis=-1).astype(np.float32))
+            Nn.extend(np.stack([nx, ny, nz], axis=-1).astype(np.float32))
+            UV.extend(np.asarray(Tm, np.float32))
+            RGB.extend(np.asarray(Cm, np.float32))
+            TX.extend([-1] * F)
 
     # display list first (static entities), then the dynamic ones, both in list order
     for ent in env.entities:

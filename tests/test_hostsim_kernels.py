@@ -10,7 +10,7 @@ from helpers import CASES, make_env, run_trajectory
 
 @pytest.mark.parametrize("name,steps,n", [("hallway", 60, 16), ("oneroom", 60, 16), ("fourrooms", 80, 16),
                                           ("fourrooms_dr", 60, 8), ("pickup", 120, 8), ("pickup_dr", 60, 8),
-                                          ("mazes3", 40, 4)])
+                                          ("mazes3", 40, 4), ("maze_dr", 12, 3)])
 def test_physics_and_reset_bit_exact(hostsim_path, name, steps, n):
     run_trajectory(name, golden(name), hostsim_path, steps=steps, n=n, check_every=10)
 
