@@ -13,9 +13,15 @@
 
 #ifdef __CUDACC__
 #define MWB_DEV __device__ __forceinline__
+#define MWB_DEVM __device__ __forceinline__
+#define MWB_DEV_NOINLINE __device__ __noinline__
+#define MWB_ALIGN16 __align__(16)
 #define MWB_DEVCONST __device__ const
 #else
 #define MWB_DEV static inline
+#define MWB_DEVM inline
+#define MWB_DEV_NOINLINE static
+#define MWB_ALIGN16 alignas(16)
 #define MWB_DEVCONST static const
 #endif
 

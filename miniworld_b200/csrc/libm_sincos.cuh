@@ -100,7 +100,8 @@ MWB_DEV double do_sincos(double a, double da, int n) {
   return (n & 2) ? -r : r;
 }
 
-MWB_DEV double sin_glibc(double x) {
+// out of line on purpose: ~600 instructions each, called from many sites
+MWB_DEV_NOINLINE double sin_glibc(double x) {
   int k = 0x7fffffff & highword(x);
   double a, da;
   if (k < 0x3e500000) return x;
@@ -110,7 +111,7 @@ MWB_DEV double sin_glibc(double x) {
   return do_sincos(a, da, n);
 }
 
-MWB_DEV double cos_glibc(double x) {
+MWB_DEV_NOINLINE double cos_glibc(double x) {
   int k = 0x7fffffff & highword(x);
   double a, da;
   if (k < 0x3e400000) return 1.0;

@@ -104,9 +104,12 @@ struct mwb_handle {
   int tri_cap;
   bool have_params, have_protos, have_template;
   bool profiling;
+  int k2_minblocks;
 #ifndef MWB_HOSTSIM
   std::vector<cudaEvent_t> ev_k1, ev_k2;   // start/stop pairs
 #endif
+  std::vector<int> mesh_counts;   // triangles per uploaded mesh (host copy)
+  void* mesh_tris_buf;
   // asset storage
   void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops;
 };
@@ -255,38 +258,62 @@ __global__ void seed_kernel(DevState S, const WorldUpload* u, int n) {
   S.rng_cache[i] = u[t].rng.uinteger;
 }
 #else
-// host simulator: sequential stand-in for render_kernel built from the same MWB_DEV functions
+// host simulator: sequential stand-in for mesh_setup_kernel + render_kernel built from the
+// same MWB_DEV functions
 struct VecTris {
   const TriRec* t;
   const TriRec& operator()(uint32_t slot) const { return t[slot]; }
 };
-static void hostsim_render(const DevState& S, const RenderAssets& A, uint8_t* obs, float* depth) {
-  const int W = S.obs_w, H = S.obs_h, M = S.msaa;
+template <int MSAA>
+static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* obs, float* depth) {
+  const int W = S.obs_w, H = S.obs_h;
   for (int i = 0; i < S.N; ++i) {
     Camera cam = make_camera(S, i);
-    ItemMap imap = build_item_map(S, i);
+    FrameMap fm = build_frame_map(S, i);
     std::vector<TriRec> tris;
-    for (int idx = 0; idx < imap.n_items; ++idx) {
-      Item it;
-      fetch_item(S, A, i, imap, idx, it);
-      TriRec loc[2];
-      int cnt = item_triangles(cam, it, W, H, loc);
-      for (int k = 0; k < cnt; ++k) tris.push_back(loc[k]);
+    TriRec rec;
+    int seg;
+    for (int task = 0; task < 2 * fm.n_quads; ++task)
+      if (task_triangle(S, A, cam, fm, i, task, W, H, rec, seg)) tris.push_back(rec);
+    for (int k = 0; k < fm.n_ents; ++k) {
+      if (fm.ent_kind[k] == MWB_KIND_BOX) {
+        for (int t = 0; t < 12; ++t)
+          if (task_triangle(S, A, cam, fm, i, fm.ent_task0[k] + t, W, H, rec, seg)) tris.push_back(rec);
+      } else {
+        const mwb_proto& pr = S.protos[fm.ent_proto[k]];
+        const EntPose P = entity_pose(S, i, fm.ent_slot[k]);
+        const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
+        for (int t = 0; t < A.meshes[pr.mesh_id].count; ++t) {
+          TriInput in;
+          mesh_triangle(A, pr, P, c, s, t, in);
+          if (finish_triangle(cam, in, W, H, rec)) tris.push_back(rec);
+        }
+      }
     }
     VecTris fetch{tris.data()};
     for (int py = 0; py < H; ++py)
       for (int px = 0; px < W; ++px) {
-        uint32_t keys[16];
-        for (int s = 0; s < M; ++s) keys[s] = MWB_SKY_KEY;
-        for (size_t j = 0; j < tris.size(); ++j) raster_pixel(tris[j], (int)j, px, py, M, keys);
+        uint32_t keys[MSAA];
+        for (int s = 0; s < MSAA; ++s) keys[s] = MWB_SKY_KEY;
+        uint32_t kmax = MWB_SKY_KEY;
+        for (size_t j = 0; j < tris.size(); ++j) {
+          const TriRec& t = tris[j];
+          if ((t.bx & 0xFFFF) > px || (t.bx >> 16) < px || (t.by & 0xFFFF) > py || (t.by >> 16) < py) continue;
+          raster_pixel<MSAA>(load_hot(&t), (int)j, px, py, keys, kmax);
+        }
         if (obs) {
           uint8_t rgb[3];
-          resolve_pixel(A, cam, fetch, keys, M, px, py, rgb);
+          resolve_pixel<MSAA>(A, cam, fetch, keys, px, py, rgb);
           memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
         }
         if (depth) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(keys[0] >> 16);
       }
   }
+}
+static void hostsim_render(const DevState& S, const RenderAssets& A, uint8_t* obs, float* depth) {
+  if (S.msaa == 1) hostsim_render_t<1>(S, A, obs, depth);
+  else if (S.msaa == 4) hostsim_render_t<4>(S, A, obs, depth);
+  else hostsim_render_t<8>(S, A, obs, depth);
 }
 #endif
 
@@ -317,6 +344,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->have_params = h->have_protos = h->have_template = false;
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
   h->protos = h->ops = nullptr;
+  h->mesh_tris_buf = nullptr;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
 #ifndef MWB_HOSTSIM
@@ -353,6 +381,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   AL(rng_s_hi, N); AL(rng_s_lo, N); AL(rng_inc_hi, N); AL(rng_inc_lo, N); AL(rng_has32, N); AL(rng_cache, N);
   AL(num_rooms, G); AL(num_quads, G); AL(num_segs, G);
   AL(rooms, G * S.R); AL(quads, G * S.Q); AL(segs, G * S.S); AL(room_tex, N * S.R * 3);
+  AL(mesh_seg, N * E);
 #undef AL
   if (!rc) rc = alloc_arr(h, &h->d_actions, N);
   if (!rc) rc = alloc_arr(h, &h->d_step_params, 3 * N);
@@ -376,9 +405,16 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (h->tri_cap > 1500) h->tri_cap = 1500;
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * (int)sizeof(TriRec);
-  CK(cudaFuncSetAttribute(render_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  {
+    const char* v = getenv("MWB_K2_MINBLOCKS");   // tuning knob: resident blocks per SM the kernel is compiled for
+    h->k2_minblocks = (v && atoi(v) == 2) ? 2 : 3;
+  }
 #endif
   *out = h;
   return MWB_OK;
@@ -392,7 +428,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
 #endif
   for (void* p : h->allocs) dev_free(p);
   void* extra[] = {h->tex_desc, h->texels, h->mesh_desc, h->mesh_pos, h->mesh_nrm, h->mesh_uv, h->mesh_rgb,
-                   h->protos, h->ops};
+                   h->protos, h->ops, h->mesh_tris_buf};
   for (void* p : extra)
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
@@ -488,9 +524,11 @@ extern "C" int mwb_upload_meshes(mwb_handle* h, const mwb_mesh_desc* descs, int 
   if (!h || !descs || n <= 0) return fail(MWB_EINVAL, "bad arguments");
   std::vector<MeshDev> md(n);
   size_t total = 0;
+  h->mesh_counts.assign(n, 0);
   for (int m = 0; m < n; ++m) {
     md[m].first = (int32_t)descs[m].offset;
     md[m].count = descs[m].num_tris;
+    h->mesh_counts[m] = descs[m].num_tris;
     size_t end = (size_t)descs[m].offset + descs[m].num_tris;
     if (end > total) total = end;
   }
@@ -525,6 +563,22 @@ extern "C" int mwb_set_protos(mwb_handle* h, const mwb_proto* protos, int n) {
   h->S.protos = (const mwb_proto*)h->protos;
   h->S.num_protos = n;
   h->have_protos = true;
+  // per-frame triangle lists of mesh entities: [N][E][largest mesh]
+  int cap = 0;
+  for (int k = 0; k < n; ++k)
+    if (protos[k].kind == MWB_KIND_MESH) {
+      if (protos[k].mesh_id < 0 || protos[k].mesh_id >= (int)h->mesh_counts.size())
+        return fail(MWB_ESTATE, "mesh prototype refers to a mesh that was not uploaded");
+      if (h->mesh_counts[protos[k].mesh_id] > cap) cap = h->mesh_counts[protos[k].mesh_id];
+    }
+  if (cap > h->S.mesh_cap) {
+    if (h->mesh_tris_buf) dev_free(h->mesh_tris_buf);
+    h->mesh_tris_buf = nullptr;
+    const size_t bytes = (size_t)h->S.N * h->S.E * cap * sizeof(TriRec);
+    if (dev_alloc(&h->mesh_tris_buf, bytes) != 0) return fail(MWB_ECUDA, "mesh triangle buffer allocation failed");
+    h->S.mesh_tris = (TriRec*)h->mesh_tris_buf;
+    h->S.mesh_cap = cap;
+  }
   return MWB_OK;
 }
 
@@ -724,11 +778,25 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s) 
   if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * (int)sizeof(TriRec);
+  if (h->S.mesh_cap > 0) {
+    mesh_setup_kernel<<<dim3(h->S.N, h->S.E), 256, 0, s>>>(h->S, h->A);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
   prof_mark(h, h->ev_k2, s);
-  switch (h->S.msaa) {
-    case 1: render_kernel<1><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
-    case 4: render_kernel<4><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
-    default: render_kernel<8><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow); break;
+#define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow)
+  if (h->k2_minblocks == 2) {
+    switch (h->S.msaa) {
+      case 1: MWB_LAUNCH_K2(1, 2); break;
+      case 4: MWB_LAUNCH_K2(4, 2); break;
+      default: MWB_LAUNCH_K2(8, 2); break;
+    }
+  } else {
+    switch (h->S.msaa) {
+      case 1: MWB_LAUNCH_K2(1, 3); break;
+      case 4: MWB_LAUNCH_K2(4, 3); break;
+      default: MWB_LAUNCH_K2(8, 3); break;
+    }
   }
   prof_mark(h, h->ev_k2, s);
   h->launches++;

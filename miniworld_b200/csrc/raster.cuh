@@ -5,15 +5,16 @@
 // OpenGL draw + MSAA resolve + glReadPixels round trip, for N environments per launch.
 //
 // Structure of one block (env i, 10 warps):
-//   A. thread 0 derives the camera (raster_core.cuh: make_camera) and the frame's draw list.
-//   B. geometry: one thread per draw item (static room quad or box face) transforms, lights
-//      and sets up <= 2 triangles; survivors of frustum / back-face culling are compacted IN
-//      DRAW ORDER into shared memory (block-wide ballot/prefix scan) -- the set-up triangles
-//      of a frame never touch HBM.
-//   C. raster: one warp per 8x8 pixel tile (lane = column x, rows y and y+4).  Per chunk of
+//   A. thread 0 derives the camera (raster_core.cuh: make_camera) and the frame map.
+//   B. geometry: one thread per triangle task (half of a static room quad or of a box face)
+//      transforms, lights and sets up its triangle; survivors of frustum / back-face culling
+//      are compacted IN DRAW ORDER into shared memory (shuffle prefix scan) -- the set-up
+//      triangles of rooms and boxes never touch HBM.  Mesh entities (thousands of triangles)
+//      arrive as per-entity lists prepared by mesh_setup_kernel.
+//   C. raster: one warp per 8x8 pixel tile, taken as two 8x4 halves (lane = pixel).  Per chunk of
 //      32 triangles every lane tests one triangle's bbox / edge functions against the tile
 //      and a warp ballot yields the tile's coverage list; hits are applied in order to the
-//      per-sample (depth16, triangle) keys held in registers.
+//      per-sample (depth16, slot) keys held in registers.
 //   D. resolve: each pixel shades the distinct triangles its samples see (perspective-
 //      correct Gouraud x trilinear texture), box-filters, converts to unorm8; the tile is
 //      transposed through shared memory and written as 8-byte row segments; depth (sample 0's
@@ -26,22 +27,93 @@
 
 #define MWB_RENDER_THREADS 320
 #define MWB_RENDER_WARPS (MWB_RENDER_THREADS / 32)
+#define MWB_MAX_SEGS (1 + MWB_MAX_DRAWN)
 
-struct SmemTris {
-  const TriRec* t;
-  __device__ const TriRec& operator()(uint32_t slot) const { return t[slot]; }
-};
+// ---- mesh pre-pass: block (env i, entity slot e) sets up that entity's triangles ----------
+__global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAssets A) {
+  const int i = blockIdx.x, e = blockIdx.y;
+  const size_t N = S.N;
+  __shared__ Camera cam;
+  __shared__ int warp_tot[8];
+  __shared__ int box[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  MeshSegInfo* info = S.mesh_seg + (size_t)i * S.E + e;
+  const int p = e == S.ghost_slot[i] ? S.ghost_proto[i] : (e < S.num_slots[i] ? S.ent_proto[e * N + i] : -1);
+  if (p < 0 || S.protos[p].kind != MWB_KIND_MESH) {
+    if (tid == 0) info->count = 0;
+    return;
+  }
+  if (tid == 0) {
+    cam = make_camera(S, i);
+    box[0] = box[1] = 0x7fffffff;
+    box[2] = box[3] = -1;
+  }
+  __syncthreads();
+  const mwb_proto& pr = S.protos[p];
+  const EntPose P = entity_pose(S, i, e);
+  const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
+  const int ntris = A.meshes[pr.mesh_id].count;
+  TriRec* out = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
+  int total = 0;
+  int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+  for (int start = 0; start < ntris; start += 256) {
+    const int t = start + tid;
+    TriRec rec;
+    int keep = 0;
+    if (t < ntris) {
+      TriInput in;
+      mesh_triangle(A, pr, P, c, s, t, in);
+      keep = finish_triangle(cam, in, S.obs_w, S.obs_h, rec) ? 1 : 0;
+    }
+    int incl = keep;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0, chunk = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      int v = warp_tot[w];
+      if (w < warp) woff += v;
+      chunk += v;
+    }
+    if (keep) {
+      const int pos = total + woff + incl - 1;
+      if (pos < S.mesh_cap) out[pos] = rec;
+      x0 = min(x0, rec.bx & 0xFFFF); x1 = max(x1, rec.bx >> 16);
+      y0 = min(y0, rec.by & 0xFFFF); y1 = max(y1, rec.by >> 16);
+    }
+    total += chunk;
+    __syncthreads();
+  }
+  if (x1 >= 0) {
+    atomicMin(&box[0], x0); atomicMin(&box[1], y0);
+    atomicMax(&box[2], x1); atomicMax(&box[3], y1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    info->count = total < S.mesh_cap ? total : S.mesh_cap;
+    info->bx = box[2] >= 0 ? (box[0] | (box[2] << 16)) : 0;
+    info->by = box[3] >= 0 ? (box[1] | (box[3] << 16)) : 0;
+  }
+}
 
-template <int MSAA>
-__global__ void __launch_bounds__(MWB_RENDER_THREADS)
+// ---- K2 --------------------------------------------------------------------------------
+template <int MSAA, int MINB>
+__global__ void __launch_bounds__(MWB_RENDER_THREADS, MINB)
 render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int tri_cap,
               int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TriRec* tris = reinterpret_cast<TriRec*>(smem_raw);
   __shared__ Camera cam;
-  __shared__ ItemMap imap;
+  __shared__ FrameMap fmap;
+  __shared__ Segment segs[MWB_MAX_SEGS];
+  __shared__ int seg_count[MWB_MAX_SEGS];
   __shared__ int warp_tot[MWB_RENDER_WARPS];
-  __shared__ __align__(8) uint8_t stage[MWB_RENDER_WARPS][8][24];
+  __shared__ __align__(8) uint8_t stage[MWB_RENDER_WARPS][4][24];
 
   const int i = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -49,22 +121,19 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
 
   if (tid == 0) {
     cam = make_camera(S, i);
-    imap = build_item_map(S, i);
+    fmap = build_frame_map(S, i);
   }
+  if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
 
-  // ---- B. geometry -> shared-memory triangle list, draw order preserved
+  // ---- B. room + box triangles -> shared memory, draw order preserved
   int ntris = 0;
-  for (int start = 0; start < imap.n_items; start += MWB_RENDER_THREADS) {
-    const int idx = start + tid;
-    TriRec loc[2];
-    int cnt = 0;
-    if (idx < imap.n_items) {
-      Item it;
-      fetch_item(S, A, i, imap, idx, it);
-      cnt = item_triangles(cam, it, W, H, loc);
-    }
-    int incl = cnt;
+  for (int start = 0; start < fmap.n_tasks; start += MWB_RENDER_THREADS) {
+    const int task = start + tid;
+    TriRec rec;
+    int keep = 0, seg = 0;
+    if (task < fmap.n_tasks) keep = task_triangle(S, A, cam, fmap, i, task, W, H, rec, seg) ? 1 : 0;
+    int incl = keep;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       int v = __shfl_up_sync(0xffffffffu, incl, d);
@@ -79,83 +148,113 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
       if (w < warp) woff += v;
       total += v;
     }
-    const int pos = ntris + woff + incl - cnt;
-    for (int k = 0; k < cnt; ++k)
-      if (pos + k < tri_cap) tris[pos + k] = loc[k];
+    if (keep) {
+      const int pos = ntris + woff + incl - 1;
+      if (pos < tri_cap) {
+        tris[pos] = rec;
+        atomicAdd(&seg_count[seg], 1);
+      }
+    }
     ntris += total;
     __syncthreads();
   }
-  if (ntris > tri_cap) {
-    if (tid == 0) atomicAdd(overflow, 1);
-    ntris = tri_cap;
+  if (tid == 0) {
+    if (ntris > tri_cap) atomicAdd(overflow, 1);
+    // segment table: smem-resident lists are contiguous in draw order; mesh lists live in HBM
+    int smem_pos = 0, slot = 0;
+    for (int k = 0; k <= fmap.n_ents; ++k) {
+      Segment& sg = segs[k];
+      if (k == 0 || fmap.ent_kind[k - 1] == MWB_KIND_BOX) {
+        sg.tris = tris + smem_pos;
+        sg.count = seg_count[k];
+        smem_pos += sg.count;
+        sg.bx = (W - 1) << 16;
+        sg.by = (H - 1) << 16;
+      } else {
+        const int e = fmap.ent_slot[k - 1];
+        const MeshSegInfo mi = S.mesh_seg[(size_t)i * S.E + e];
+        sg.tris = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
+        sg.count = mi.count;
+        sg.bx = mi.bx;
+        sg.by = mi.by;
+      }
+      sg.base = slot;
+      slot += sg.count;
+    }
   }
+  __syncthreads();
+  const int nsegs = 1 + fmap.n_ents;
 
-  // ---- C/D. one warp per 8x8 tile
+  // ---- C/D. one warp per 8x8 tile, rasterised as two 8x4 halves (lane = one pixel) so that a
+  //      single copy of the unrolled per-sample code serves both halves (instruction cache)
   const int tiles_x = (W + 7) >> 3, tiles_y = (H + 7) >> 3;
   const int lx = lane & 7, ly = lane >> 3;
-  SmemTris fetch{tris};
-  for (int tile = warp; tile < tiles_x * tiles_y; tile += MWB_RENDER_WARPS) {
-    const int tx0 = (tile % tiles_x) << 3, ty0 = (tile / tiles_x) << 3;
-    const int px = tx0 + lx, pya = ty0 + ly, pyb = pya + 4;
-    uint32_t ka[MSAA], kb[MSAA];
+  const SegLookup fetch{segs, nsegs};
+#pragma unroll 1
+  for (int half = warp; half < 2 * tiles_x * tiles_y; half += MWB_RENDER_WARPS) {
+    const int tile = half >> 1;
+    const int tx0 = (tile % tiles_x) << 3, ty0 = ((tile / tiles_x) << 3) + ((half & 1) << 2);
+    const int px = tx0 + lx, py = ty0 + ly;
+    uint32_t keys[MSAA];
 #pragma unroll
-    for (int s = 0; s < MSAA; ++s) ka[s] = kb[s] = MWB_SKY_KEY;
+    for (int s = 0; s < MSAA; ++s) keys[s] = MWB_SKY_KEY;
+    uint32_t kmax = MWB_SKY_KEY;
 
-    for (int cb = 0; cb < ntris; cb += 32) {
-      const int j = cb + lane;
-      bool hit = false;
-      if (j < ntris) {
-        const TriRec& t = tris[j];
-        const int bx0 = t.bx & 0xFFFF, bx1 = t.bx >> 16, by0 = t.by & 0xFFFF, by1 = t.by >> 16;
-        hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 7 && by1 >= ty0;
-        if (hit) {
+#pragma unroll 1
+    for (int sgi = 0; sgi < nsegs; ++sgi) {
+      const Segment sg = segs[sgi];
+      if (sg.count == 0) continue;
+      if ((sg.bx & 0xFFFF) > tx0 + 7 || (sg.bx >> 16) < tx0 || (sg.by & 0xFFFF) > ty0 + 3 || (sg.by >> 16) < ty0) continue;
+#pragma unroll 1
+      for (int cb = 0; cb < sg.count; cb += 32) {
+        const int j = cb + lane;
+        bool hit = false;
+        if (j < sg.count) {
+          const TriRec& t = sg.tris[j];
+          const int bx0 = t.bx & 0xFFFF, bx1 = t.bx >> 16, by0 = t.by & 0xFFFF, by1 = t.by >> 16;
+          hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0;
+          if (hit) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {   // tile entirely outside one edge?
-            float cx = t.A[k] > 0.0f ? (float)(tx0 + 8) : (float)tx0;
-            float cy = t.B[k] > 0.0f ? (float)(ty0 + 8) : (float)ty0;
-            if (t.A[k] * cx + t.B[k] * cy + t.C[k] + t.R[k] < 0.0f) hit = false;
+            for (int k = 0; k < 3; ++k) {   // half-tile entirely outside one edge?
+              const float cx = t.A[k] > 0.0f ? (float)(tx0 + 8) : (float)tx0;
+              const float cy = t.B[k] > 0.0f ? (float)(ty0 + 4) : (float)ty0;
+              if (t.A[k] * cx + t.B[k] * cy + t.C[k] + t.R[k] < 0.0f) hit = false;
+            }
           }
         }
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, hit);
-      while (mask) {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const TriRec& t = tris[cb + b];
-        raster_pixel(t, cb + b, px, pya, MSAA, ka);
-        raster_pixel(t, cb + b, px, pyb, MSAA, kb);
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+#pragma unroll 1
+        while (mask) {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const HotTri t = load_hot(sg.tris + cb + b);
+          raster_pixel<MSAA>(t, sg.base + cb + b, px, py, keys, kmax);
+        }
       }
     }
 
-    uint8_t ca[3], cbv[3];
-    resolve_pixel(A, cam, fetch, ka, MSAA, px, pya, ca);
-    resolve_pixel(A, cam, fetch, kb, MSAA, px, pyb, cbv);
+    uint8_t rgb[3];
+    resolve_pixel<MSAA>(A, cam, fetch, keys, px, py, rgb);
     if (obs != nullptr) {
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        stage[warp][ly][lx * 3 + c] = ca[c];
-        stage[warp][ly + 4][lx * 3 + c] = cbv[c];
-      }
+      for (int c = 0; c < 3; ++c) stage[warp][ly][lx * 3 + c] = rgb[c];
       __syncwarp();
-      if (lane < 24) {   // 8 rows x 3 segments of 8 bytes
+      if (lane < 12) {   // 4 rows x 3 segments of 8 bytes
         const int row = lane / 3, seg = lane % 3;
-        const int py = ty0 + row;
-        if (py < H && tx0 + 8 <= W) {
+        const int y = ty0 + row;
+        if (y < H && tx0 + 8 <= W) {
           uint2 v = *reinterpret_cast<const uint2*>(&stage[warp][row][seg * 8]);
-          *reinterpret_cast<uint2*>(obs + ((size_t)i * H + py) * W * 3 + (size_t)tx0 * 3 + seg * 8) = v;
-        } else if (py < H) {   // ragged right edge (W not a multiple of 8): byte stores
+          *reinterpret_cast<uint2*>(obs + ((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + seg * 8) = v;
+        } else if (y < H) {   // ragged right edge (W not a multiple of 8): byte stores
           for (int q = 0; q < 8; ++q) {
             int bcol = seg * 8 + q;
-            if (tx0 + bcol / 3 < W) obs[((size_t)i * H + py) * W * 3 + (size_t)tx0 * 3 + bcol] = stage[warp][row][bcol];
+            if (tx0 + bcol / 3 < W) obs[((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + bcol] = stage[warp][row][bcol];
           }
         }
       }
     }
-    if (depth != nullptr) {
-      if (px < W && pya < H) depth[((size_t)i * H + pya) * W + px] = depth_code_to_metres(ka[0] >> 16);
-      if (px < W && pyb < H) depth[((size_t)i * H + pyb) * W + px] = depth_code_to_metres(kb[0] >> 16);
-    }
+    if (depth != nullptr && px < W && py < H) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(keys[0] >> 16);
   }
 }
 

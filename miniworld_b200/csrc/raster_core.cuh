@@ -56,11 +56,21 @@ struct RenderAssets {
 
 // D3D standard sample patterns, offsets from the pixel's top-left corner, image space
 // (x right, y down).  All are multiples of 1/16: sample coordinates are exact in float32.
-MWB_DEVCONST float mwb_sample_x[13] = {0.5f, 0.375f, 0.875f, 0.125f, 0.625f,
-                                       0.5625f, 0.4375f, 0.8125f, 0.3125f, 0.1875f, 0.0625f, 0.6875f, 0.9375f};
-MWB_DEVCONST float mwb_sample_y[13] = {0.5f, 0.125f, 0.375f, 0.625f, 0.875f,
-                                       0.3125f, 0.6875f, 0.5625f, 0.1875f, 0.8125f, 0.4375f, 0.9375f, 0.0625f};
-MWB_DEV int sample_base(int msaa) { return msaa == 1 ? 0 : (msaa == 4 ? 1 : 5); }
+// Indexed with compile-time (unrolled) s so the offsets fold into immediates.
+template <int MSAA>
+MWB_DEV float sample_x(int s) {
+  if (MSAA == 1) return 0.5f;
+  if (MSAA == 4) return s == 0 ? 0.375f : s == 1 ? 0.875f : s == 2 ? 0.125f : 0.625f;
+  return s == 0 ? 0.5625f : s == 1 ? 0.4375f : s == 2 ? 0.8125f : s == 3 ? 0.3125f
+       : s == 4 ? 0.1875f : s == 5 ? 0.0625f : s == 6 ? 0.6875f : 0.9375f;
+}
+template <int MSAA>
+MWB_DEV float sample_y(int s) {
+  if (MSAA == 1) return 0.5f;
+  if (MSAA == 4) return s == 0 ? 0.125f : s == 1 ? 0.375f : s == 2 ? 0.625f : 0.875f;
+  return s == 0 ? 0.3125f : s == 1 ? 0.6875f : s == 2 ? 0.5625f : s == 3 ? 0.1875f
+       : s == 4 ? 0.8125f : s == 5 ? 0.4375f : s == 6 ? 0.9375f : 0.0625f;
+}
 
 struct Camera {
   float ex, ey, ez;              // eye
@@ -155,17 +165,45 @@ MWB_DEV void light_vertex(const Camera& c, float x, float y, float z, float nx, 
   }
 }
 
-// One set-up triangle, 36 words.  Edge k is opposite vertex k, so E_k / sum(E) is the
-// perspective-correct weight of vertex k's attributes.
-struct TriRec {
+// One set-up triangle, 36 words (144 B, 16-byte aligned so the rasteriser's hot part -- the
+// first 64 bytes -- moves as four 128-bit loads).  Edge k is opposite vertex k, so
+// E_k / sum(E) is the perspective-correct weight of vertex k's attributes.
+struct MWB_ALIGN16 TriRec {
   float A[3], B[3], C[3];        // homogeneous edge functions E_k(x, y) = A x + B y + C  (exact)
   float R[3];                    // conservative half-extent of E_k over a pixel (+ rounding margin)
   float Za, Zb, Zc;              // window z plane (exact)
+  float Zr;                      // conservative half-extent of z over a pixel (+ rounding margin)
+  float T[3];                    // tie rule as a threshold: sample inside edge k  <=>  E_k >= T[k]
+  int32_t tex;                   // texture id or -1       (T = 0 if the edge owns E == 0, else the
+  int32_t bx, by;                //                         smallest positive float, i.e. E > 0)
   float u[3], v[3];              // texcoords per vertex
   float r[3], g[3], b[3];        // lit colour per vertex
-  int32_t tex;                   // texture id or -1
-  int32_t bx, by;                // bbox: lo | hi << 16, pixel units, clamped to the frame
+  float pad[1];
 };
+
+// the hot 76 bytes of a TriRec, held in registers while a tile is rasterised
+struct HotTri {
+  float A[3], B[3], C[3], R[3];
+  float Za, Zb, Zc, Zr;
+  float T[3];
+};
+
+MWB_DEV HotTri load_hot(const TriRec* t) {
+  HotTri h;
+#ifdef __CUDA_ARCH__
+  const float4* p = reinterpret_cast<const float4*>(t);
+  const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
+  h.A[0] = q0.x; h.A[1] = q0.y; h.A[2] = q0.z; h.B[0] = q0.w;
+  h.B[1] = q1.x; h.B[2] = q1.y; h.C[0] = q1.z; h.C[1] = q1.w;
+  h.C[2] = q2.x; h.R[0] = q2.y; h.R[1] = q2.z; h.R[2] = q2.w;
+  h.Za = q3.x; h.Zb = q3.y; h.Zc = q3.z; h.Zr = q3.w;
+  h.T[0] = q4.x; h.T[1] = q4.y; h.T[2] = q4.z;
+#else
+  for (int k = 0; k < 3; ++k) { h.A[k] = t->A[k]; h.B[k] = t->B[k]; h.C[k] = t->C[k]; h.R[k] = t->R[k]; h.T[k] = t->T[k]; }
+  h.Za = t->Za; h.Zb = t->Zb; h.Zc = t->Zc; h.Zr = t->Zr;
+#endif
+  return h;
+}
 
 struct VertAttr {
   float u, v, r, g, b;
@@ -204,10 +242,15 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   t.Za = f_div(f_add(f_add(f_mul(v0.zeta, t.A[0]), f_mul(v1.zeta, t.A[1])), f_mul(v2.zeta, t.A[2])), det);
   t.Zb = f_div(f_add(f_add(f_mul(v0.zeta, t.B[0]), f_mul(v1.zeta, t.B[1])), f_mul(v2.zeta, t.B[2])), det);
   t.Zc = f_div(f_add(f_add(f_mul(v0.zeta, t.C[0]), f_mul(v1.zeta, t.C[1])), f_mul(v2.zeta, t.C[2])), det);
+  // |z(sample) - z(centre)| <= 0.4375 (|Za| + |Zb|); plus a bound on evaluation rounding
+  t.Zr = 0.4375f * (fabsf(t.Za) + fabsf(t.Zb)) + 4e-6f * (fabsf(t.Za) * (float)W + fabsf(t.Zb) * (float)H + fabsf(t.Zc)) + 1e-6f;
+  t.pad[0] = 0.0f;
   for (int k = 0; k < 3; ++k) {
     float aa = fabsf(t.A[k]), ab = fabsf(t.B[k]);
     // |E(sample) - E(centre)| <= 0.4375 (|A| + |B|); plus a bound on evaluation rounding
     t.R[k] = 0.4375f * (aa + ab) + 4e-6f * (aa * (float)W + ab * (float)H + fabsf(t.C[k])) + 1e-30f;
+    // tie rule: the edge with A > 0, or A == 0 and B > 0, owns samples with E == 0
+    t.T[k] = (t.A[k] > 0.0f || (t.A[k] == 0.0f && t.B[k] > 0.0f)) ? 0.0f : 1.401298464e-45f;
   }
   const VertAttr& b0 = a0;
   const VertAttr& b1 = a2;
@@ -237,39 +280,57 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   return true;
 }
 
-// Exact edge value at a sample and the tie rule that makes shared edges watertight: the
-// neighbouring triangle sees the exactly negated (A, B, C), so exactly one side owns E == 0.
-MWB_DEV bool edge_inside(float A, float B, float C, float xs, float ys) {
-  float e = f_add(f_add(f_mul(A, xs), f_mul(B, ys)), C);
-  if (e > 0.0f) return true;
-  if (e < 0.0f) return false;
-  return A > 0.0f || (A == 0.0f && B > 0.0f);
+// Exact edge value at a sample.  Shared edges are watertight: the neighbouring triangle sees
+// the exactly negated (A, B, C), and exactly one of the two owns E == 0 (threshold T).
+MWB_DEV float edge_value(float A, float B, float C, float xs, float ys) {
+  return f_add(f_add(f_mul(A, xs), f_mul(B, ys)), C);
 }
 
-// Depth-tested visibility of triangle `slot` over the `msaa` samples of pixel (px, py).
+template <int MSAA>
+MWB_DEV uint32_t max_key(const uint32_t (&keys)[MSAA]) {
+  uint32_t m = keys[0];
+#pragma unroll
+  for (int s = 1; s < MSAA; ++s) m = keys[s] > m ? keys[s] : m;
+  return m;
+}
+
+// Depth-tested visibility of triangle `slot` over the MSAA samples of pixel (px, py).
 // keys[s] = depth16 << 16 | slot of the nearest surface so far (GL_LESS on 16-bit codes;
 // slots ascend in draw order, so on equal codes the earlier draw keeps the sample).
-MWB_DEV void raster_pixel(const TriRec& t, int slot, int px, int py, int msaa, uint32_t* keys) {
-  float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
-  float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
-  float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
-  float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
+// `kmax` caches max(keys): a triangle whose nearest possible depth code over the pixel is
+// already behind every stored sample cannot win any GL_LESS test and is skipped.
+template <int MSAA>
+MWB_DEV void raster_pixel(const HotTri& t, int slot, int px, int py, uint32_t (&keys)[MSAA], uint32_t& kmax) {
+  const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
+  const float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
+  const float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
+  const float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
   if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) return;   // certainly outside
-  bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;    // certainly inside
-  const int sb = sample_base(msaa);
-  for (int s = 0; s < msaa; ++s) {
-    float xs = (float)px + mwb_sample_x[sb + s], ys = (float)py + mwb_sample_y[sb + s];
-    if (!full) {
-      if (!edge_inside(t.A[0], t.B[0], t.C[0], xs, ys)) continue;
-      if (!edge_inside(t.A[1], t.B[1], t.C[1], xs, ys)) continue;
-      if (!edge_inside(t.A[2], t.B[2], t.C[2], xs, ys)) continue;
+  const float zc = t.Za * cx + t.Zb * cy + t.Zc;
+  const float zlo = zc - t.Zr;
+  if (zlo > 1.0f || zc + t.Zr < 0.0f) return;                                    // beyond far / before near
+  // smallest code any sample of this pixel can get (one code of slack for the rounding of z * 65535)
+  if (zlo * 65535.0f - 1.0f > (float)(kmax >> 16)) return;                      // certainly occluded
+  const bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;   // certainly inside
+  const float fx = (float)px, fy = (float)py;
+  bool changed = false;
+#pragma unroll
+  for (int s = 0; s < MSAA; ++s) {
+    const float xs = fx + sample_x<MSAA>(s), ys = fy + sample_y<MSAA>(s);
+    bool in = true;
+    if (!full)
+      in = edge_value(t.A[0], t.B[0], t.C[0], xs, ys) >= t.T[0] && edge_value(t.A[1], t.B[1], t.C[1], xs, ys) >= t.T[1] &&
+           edge_value(t.A[2], t.B[2], t.C[2], xs, ys) >= t.T[2];
+    const float z = f_add(f_add(f_mul(t.Za, xs), f_mul(t.Zb, ys)), t.Zc);
+    in = in && z >= 0.0f && z <= 1.0f;   // near / far clip (also drops NaN)
+    const uint32_t code = (uint32_t)f_add(f_mul(z, 65535.0f), 0.5f);
+    const uint32_t key = (code << 16) | (uint32_t)slot;
+    if (in && key < keys[s]) {
+      keys[s] = key;
+      changed = true;
     }
-    float z = f_add(f_add(f_mul(t.Za, xs), f_mul(t.Zb, ys)), t.Zc);
-    if (!(z >= 0.0f && z <= 1.0f)) continue;   // near / far clip (also drops NaN)
-    uint32_t code = (uint32_t)f_add(f_mul(z, 65535.0f), 0.5f);
-    uint32_t key = (code << 16) | (uint32_t)slot;
-    if (key < keys[s]) keys[s] = key;
   }
+  if (changed) kmax = max_key<MSAA>(keys);
 }
 
 // ---------------------------------------------------------------------------- shading
@@ -319,21 +380,21 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
     float dvdy = (t.v[0] * t.B[0] + t.v[1] * t.B[1] + t.v[2] * t.B[2] - v * sb) * inv * (float)T.h;
     float rho2 = fmaxf(dudx * dudx + dvdx * dvdx, dudy * dudy + dvdy * dvdy);
     float lambda = 0.5f * log2f(fmaxf(rho2, 1e-20f));
-    float tc[3];
-    if (lambda <= 0.0f) {
-      bilinear(A, T, 0, u, v, tc);               // magnification: GL_LINEAR on level 0
-    } else {
-      float lmax = (float)(T.nlev - 1);
-      if (lambda >= lmax) {
-        bilinear(A, T, T.nlev - 1, u, v, tc);
-      } else {
-        int l0 = (int)lambda;
-        float f = lambda - (float)l0;
-        float ta[3], tb[3];
-        bilinear(A, T, l0, u, v, ta);
-        bilinear(A, T, l0 + 1, u, v, tb);
-        for (int k = 0; k < 3; ++k) tc[k] = ta[k] + f * (tb[k] - ta[k]);
-      }
+    // magnification: GL_LINEAR on level 0; else GL_LINEAR_MIPMAP_LINEAR between floor(lambda) and +1
+    const float lmax = (float)(T.nlev - 1);
+    const float lc = lambda <= 0.0f ? 0.0f : (lambda >= lmax ? lmax : lambda);
+    const int l0 = (int)lc;
+    const float f = lc - (float)l0;
+    float tc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      const float wj = j == 0 ? 1.0f - f : f;
+      if (wj == 0.0f) continue;
+      float tj[3];
+      bilinear(A, T, l0 + j, u, v, tj);
+      tc[0] += wj * tj[0];
+      tc[1] += wj * tj[1];
+      tc[2] += wj * tj[2];
     }
     r *= tc[0];
     g *= tc[1];
@@ -359,173 +420,252 @@ MWB_DEV float depth_code_to_metres(uint32_t code) {
 }
 
 // ------------------------------------------------------------------ scene -> triangles
-// A frame's draw list is a sequence of "items": the static quads of the room template in
-// order, then each entity slot in list order (Box = 6 faces).  Every item yields <= 2
-// triangles (a quad is split as the fan (0,1,2), (0,2,3)).
+// A frame's draw list, in the reference's submission order (miniworld.py:1052-1077): the
+// static quads of every room, then the entities -- display-list (static) ones first, then the
+// dynamic ones, each group in entity-list order.  It is cut into SEGMENTS: segment 0 = room
+// triangles, segment 1 + k = the k-th drawn entity (a Box: <= 12 triangles set up in shared
+// memory by the render kernel; a MeshEnt: set up by mesh_setup_kernel into HBM).  Triangle
+// "slots" number the surviving triangles consecutively across segments, so slot order ==
+// draw order and the per-sample key (depth16 << 16 | slot) implements GL_LESS exactly.
 
-struct Item {
-  float pos[4][3];
-  float nrm[3];
-  float uv[4][2];
-  float mat[3];
-  int32_t tex;
-  int32_t nverts;
+#define MWB_MAX_DRAWN 8
+
+struct FrameMap {
+  int n_quads;                       // room quads of this env
+  int n_ents;                        // drawn entities
+  int n_tasks;                       // triangle tasks handled in shared memory: 2 per quad + 12 per box
+  int ent_slot[MWB_MAX_DRAWN];       // entity-list slot
+  int ent_proto[MWB_MAX_DRAWN];
+  int ent_kind[MWB_MAX_DRAWN];       // MWB_KIND_BOX / MWB_KIND_MESH
+  int ent_task0[MWB_MAX_DRAWN];      // first task index (boxes), -1 for meshes
 };
 
-// static quad q of env i -> Item (texture choice and texel density applied here)
-MWB_DEV void room_item(const DevState& S, const RenderAssets& A, int i, int q, Item& it) {
-  const int g = geom_index(S, i);
-  const mwb_quad& Q = S.quads[(size_t)g * S.Q + q];
-  const int tex = S.room_tex[((size_t)i * S.R + Q.room) * 3 + Q.surf];
-  const TexDev& T = A.tex[tex];
-  // gen_texcs_wall / gen_texcs_floor: float64 multiply by TEX_DENSITY / size, then float32
-  const double xc = 512.0 / (double)T.w, yc = 512.0 / (double)T.h;
-  for (int k = 0; k < 4; ++k) {
-    it.pos[k][0] = Q.pos[k][0];
-    it.pos[k][1] = Q.pos[k][1];
-    it.pos[k][2] = Q.pos[k][2];
-    it.uv[k][0] = (float)d_mul(Q.uvm[k][0], xc);
-    it.uv[k][1] = (float)d_mul(Q.uvm[k][1], yc);
+struct EntPose {
+  double x, y, z, dir;
+  double col[3];
+};
+
+MWB_DEV EntPose entity_pose(const DevState& S, int i, int e) {
+  const size_t N = S.N;
+  EntPose p;
+  if (e == S.ghost_slot[i]) {
+    p.x = S.ghost_pose[0 * N + i];
+    p.y = S.ghost_pose[1 * N + i];
+    p.z = S.ghost_pose[2 * N + i];
+    p.dir = S.ghost_pose[3 * N + i];
+    for (int c = 0; c < 3; ++c) p.col[c] = S.ghost_col[c * N + i];
+  } else {
+    p.x = S.ent_px[e * N + i];
+    p.y = S.ent_py[e * N + i];
+    p.z = S.ent_pz[e * N + i];
+    p.dir = S.ent_dir[e * N + i];
+    for (int c = 0; c < 3; ++c) p.col[c] = S.ent_col[((size_t)e * 3 + c) * N + i];
   }
-  it.nrm[0] = Q.nrm[0];
-  it.nrm[1] = Q.nrm[1];
-  it.nrm[2] = Q.nrm[2];
-  it.mat[0] = it.mat[1] = it.mat[2] = 1.0f;   // glColor3f(1, 1, 1)
-  it.tex = tex;
-  it.nverts = Q.num_verts;
+  return p;
 }
 
-// face f (0..5, drawBox order: +z, -z, -x, +x, +y, -y) of a Box -> Item
-MWB_DEV void box_item(const mwb_proto& pr, double px, double py, double pz, double dir, const double col[3],
-                      int f, Item& it) {
-  const float hx = (float)(pr.size[0] / 2), sy = (float)pr.size[1], hz = (float)(pr.size[2] / 2);
-  const float x0 = -hx, x1 = hx, y0 = 0.0f, y1 = sy, z0 = -hz, z1 = hz;
-  float v[4][3];
-  float n[3] = {0, 0, 0};
-  switch (f) {
-    case 0: n[2] = 1;  { float q[4][3] = {{x1, y1, z1}, {x0, y1, z1}, {x0, y0, z1}, {x1, y0, z1}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
-    case 1: n[2] = -1; { float q[4][3] = {{x0, y1, z0}, {x1, y1, z0}, {x1, y0, z0}, {x0, y0, z0}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
-    case 2: n[0] = -1; { float q[4][3] = {{x0, y1, z1}, {x0, y1, z0}, {x0, y0, z0}, {x0, y0, z1}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
-    case 3: n[0] = 1;  { float q[4][3] = {{x1, y1, z0}, {x1, y1, z1}, {x1, y0, z1}, {x1, y0, z0}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
-    case 4: n[1] = 1;  { float q[4][3] = {{x1, y1, z1}, {x1, y1, z0}, {x0, y1, z0}, {x0, y1, z1}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
-    default: n[1] = -1; { float q[4][3] = {{x1, y0, z0}, {x1, y0, z1}, {x0, y0, z1}, {x0, y0, z0}}; for (int a = 0; a < 12; ++a) v[a / 3][a % 3] = q[a / 3][a % 3]; } break;
+MWB_DEV FrameMap build_frame_map(const DevState& S, int i) {
+  FrameMap m;
+  const size_t N = S.N;
+  m.n_quads = S.num_quads[geom_index(S, i)];
+  m.n_ents = 0;
+  int tasks = 2 * m.n_quads;
+  const int slots = S.num_slots[i];
+  const int ghost = S.ghost_slot[i];
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int e = 0; e < slots && m.n_ents < MWB_MAX_DRAWN; ++e) {
+      const int p = e == ghost ? S.ghost_proto[i] : S.ent_proto[e * N + i];
+      if (p < 0) continue;
+      const mwb_proto& pr = S.protos[p];
+      if (pr.kind != MWB_KIND_BOX && pr.kind != MWB_KIND_MESH) continue;   // the agent is never drawn
+      if ((pr.is_static != 0) != (pass == 0)) continue;
+      const int k = m.n_ents++;
+      m.ent_slot[k] = e;
+      m.ent_proto[k] = p;
+      m.ent_kind[k] = pr.kind;
+      m.ent_task0[k] = -1;
+      if (pr.kind == MWB_KIND_BOX) {
+        m.ent_task0[k] = tasks;
+        tasks += 12;
+      }
+    }
   }
-  // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = -x s + z c
-  const float c = (float)mwb_libm::cos_glibc(dir), s = (float)mwb_libm::sin_glibc(dir);
-  const float tx = (float)px, ty = (float)py, tz = (float)pz;
-  for (int k = 0; k < 4; ++k) {
-    it.pos[k][0] = f_add(f_add(f_mul(v[k][0], c), f_mul(v[k][2], s)), tx);
-    it.pos[k][1] = f_add(v[k][1], ty);
-    it.pos[k][2] = f_add(f_sub(f_mul(v[k][2], c), f_mul(v[k][0], s)), tz);
-    it.uv[k][0] = it.uv[k][1] = 0.0f;
-  }
-  it.nrm[0] = f_add(f_mul(n[0], c), f_mul(n[2], s));
-  it.nrm[1] = n[1];
-  it.nrm[2] = f_sub(f_mul(n[2], c), f_mul(n[0], s));
-  for (int k = 0; k < 3; ++k) it.mat[k] = (float)col[k];
-  it.tex = -1;
-  it.nverts = 4;
+  m.n_tasks = tasks;
+  return m;
 }
 
-// Item -> up to two set-up triangles; returns how many survived culling
-MWB_DEV int item_triangles(const Camera& cam, const Item& it, int W, int H, TriRec out[2]) {
-  HVert hv[4];
-  VertAttr at[4];
-  for (int k = 0; k < it.nverts; ++k) {
-    hv[k] = transform_vertex(cam, it.pos[k][0], it.pos[k][1], it.pos[k][2]);
+struct TriInput {
+  float pos[3][3];
+  float nrm[3][3];
+  float uv[3][2];
+  float mat[3][3];
+  int tex;
+};
+
+// world-space triangle -> set-up record (transform, light, cull)
+MWB_DEV bool finish_triangle(const Camera& cam, const TriInput& in, int W, int H, TriRec& out) {
+  HVert hv[3];
+  VertAttr at[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    hv[k] = transform_vertex(cam, in.pos[k][0], in.pos[k][1], in.pos[k][2]);
     float col[3];
-    light_vertex(cam, it.pos[k][0], it.pos[k][1], it.pos[k][2], it.nrm[0], it.nrm[1], it.nrm[2], it.mat, col);
-    at[k].u = it.uv[k][0];
-    at[k].v = it.uv[k][1];
+    light_vertex(cam, in.pos[k][0], in.pos[k][1], in.pos[k][2], in.nrm[k][0], in.nrm[k][1], in.nrm[k][2], in.mat[k], col);
+    at[k].u = in.uv[k][0];
+    at[k].v = in.uv[k][1];
     at[k].r = col[0];
     at[k].g = col[1];
     at[k].b = col[2];
   }
-  int n = 0;
-  if (setup_triangle(hv[0], hv[1], hv[2], at[0], at[1], at[2], it.tex, W, H, out[n])) ++n;
-  if (it.nverts == 4 && setup_triangle(hv[0], hv[2], hv[3], at[0], at[2], at[3], it.tex, W, H, out[n])) ++n;
-  return n;
+  return setup_triangle(hv[0], hv[1], hv[2], at[0], at[1], at[2], in.tex, W, H, out);
 }
 
-// Number of draw items of env i and the decoding of item index -> (room quad | entity face).
-struct ItemMap {
-  int n_quads;
-  int n_items;
-  int ent_first[9];              // first item index of each drawn entity (<= 8) + end
-  int ent_slot[8];
-  int n_ents;
+// half `half` (fan (0,1,2) / (0,2,3)) of static quad q of env i
+MWB_DEV bool room_triangle(const DevState& S, const RenderAssets& A, int i, int q, int half, TriInput& in) {
+  const mwb_quad& Q = S.quads[(size_t)geom_index(S, i) * S.Q + q];
+  if (half == 1 && Q.num_verts < 4) return false;
+  const int tex = S.room_tex[((size_t)i * S.R + Q.room) * 3 + Q.surf];
+  const TexDev& T = A.tex[tex];
+  // gen_texcs_wall / gen_texcs_floor: float64 multiply by TEX_DENSITY / size, then float32
+  const double xc = 512.0 / (double)T.w, yc = 512.0 / (double)T.h;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int v = k == 0 ? 0 : k + half;
+    in.pos[k][0] = Q.pos[v][0];
+    in.pos[k][1] = Q.pos[v][1];
+    in.pos[k][2] = Q.pos[v][2];
+    in.uv[k][0] = (float)d_mul(Q.uvm[v][0], xc);
+    in.uv[k][1] = (float)d_mul(Q.uvm[v][1], yc);
+    in.nrm[k][0] = Q.nrm[0];
+    in.nrm[k][1] = Q.nrm[1];
+    in.nrm[k][2] = Q.nrm[2];
+    in.mat[k][0] = in.mat[k][1] = in.mat[k][2] = 1.0f;   // glColor3f(1, 1, 1)
+  }
+  in.tex = tex;
+  return true;
+}
+
+// triangle t (0..11) of a Box: face t / 2 in drawBox order (+z, -z, -x, +x, +y, -y), fan half t % 2
+MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput& in) {
+  const int f = t >> 1, half = t & 1;
+  const float hx = (float)(pr.size[0] / 2), sy = (float)pr.size[1], hz = (float)(pr.size[2] / 2);
+  // corner c of the face: sign pattern per drawBox (opengl.py:460-503)
+  // each entry: (x sign, y top?, z sign) for corners 0..3
+  const signed char X[6][4] = {{1, -1, -1, 1}, {-1, 1, 1, -1}, {-1, -1, -1, -1}, {1, 1, 1, 1}, {1, 1, -1, -1}, {1, 1, -1, -1}};
+  const signed char Y[6][4] = {{1, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 1, 1}, {0, 0, 0, 0}};
+  const signed char Z[6][4] = {{1, 1, 1, 1}, {-1, -1, -1, -1}, {1, -1, -1, 1}, {-1, 1, 1, -1}, {1, -1, -1, 1}, {-1, 1, 1, -1}};
+  const float NX[6] = {0, 0, -1, 1, 0, 0}, NY[6] = {0, 0, 0, 0, 1, -1}, NZ[6] = {1, -1, 0, 0, 0, 0};
+  // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = z c - x s
+  const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
+  const float tx = (float)P.x, ty = (float)P.y, tz = (float)P.z;
+  const float nx = f_add(f_mul(NX[f], c), f_mul(NZ[f], s)), ny = NY[f], nz = f_sub(f_mul(NZ[f], c), f_mul(NX[f], s));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int v = k == 0 ? 0 : k + half;
+    const float x = X[f][v] > 0 ? hx : -hx, y = Y[f][v] ? sy : 0.0f, z = Z[f][v] > 0 ? hz : -hz;
+    in.pos[k][0] = f_add(f_add(f_mul(x, c), f_mul(z, s)), tx);
+    in.pos[k][1] = f_add(y, ty);
+    in.pos[k][2] = f_add(f_sub(f_mul(z, c), f_mul(x, s)), tz);
+    in.uv[k][0] = in.uv[k][1] = 0.0f;
+    in.nrm[k][0] = nx;
+    in.nrm[k][1] = ny;
+    in.nrm[k][2] = nz;
+    for (int q = 0; q < 3; ++q) in.mat[k][q] = (float)P.col[q];
+  }
+  in.tex = -1;
+}
+
+// triangle t of a MeshEnt: glTranslatef(pos) glScalef(s) glRotatef(dir): v' = pos + s (R v);
+// normals through the inverse transpose, R n / s, not renormalised (entity.py:150-161)
+MWB_DEV void mesh_triangle(const RenderAssets& A, const mwb_proto& pr, const EntPose& P, float c, float s, int t,
+                           TriInput& in) {
+  const MeshDev& M = A.meshes[pr.mesh_id];
+  const size_t base = (size_t)(M.first + t);
+  const float sc = pr.scale, inv = f_div(1.0f, sc);
+  const float tx = (float)P.x, ty = (float)P.y, tz = (float)P.z;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* p = A.mesh_pos + (base * 3 + k) * 3;
+    const float* n = A.mesh_nrm + (base * 3 + k) * 3;
+    const float* m = A.mesh_rgb + (base * 3 + k) * 3;
+    in.pos[k][0] = f_add(f_mul(f_add(f_mul(p[0], c), f_mul(p[2], s)), sc), tx);
+    in.pos[k][1] = f_add(f_mul(p[1], sc), ty);
+    in.pos[k][2] = f_add(f_mul(f_sub(f_mul(p[2], c), f_mul(p[0], s)), sc), tz);
+    in.nrm[k][0] = (n[0] * c + n[2] * s) * inv;
+    in.nrm[k][1] = n[1] * inv;
+    in.nrm[k][2] = (n[2] * c - n[0] * s) * inv;
+    in.uv[k][0] = A.mesh_uv[(base * 3 + k) * 2 + 0];
+    in.uv[k][1] = A.mesh_uv[(base * 3 + k) * 2 + 1];
+    in.mat[k][0] = m[0];
+    in.mat[k][1] = m[1];
+    in.mat[k][2] = m[2];
+  }
+  in.tex = -1;   // ball_* / key_* carry no texture (objmesh.py:226-230)
+}
+
+// shared-memory triangle task -> (segment, record); false if culled / nonexistent
+MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camera& cam, const FrameMap& m, int i,
+                           int task, int W, int H, TriRec& out, int& seg) {
+  TriInput in;
+  if (task < 2 * m.n_quads) {
+    seg = 0;
+    if (!room_triangle(S, A, i, task >> 1, task & 1, in)) return false;
+  } else {
+    int k = 0;
+    while (k + 1 < m.n_ents && (m.ent_task0[k] < 0 || task >= m.ent_task0[k] + 12)) ++k;
+    seg = 1 + k;
+    box_triangle(S.protos[m.ent_proto[k]], entity_pose(S, i, m.ent_slot[k]), task - m.ent_task0[k], in);
+  }
+  return finish_triangle(cam, in, W, H, out);
+}
+
+// one triangle list of a frame
+struct Segment {
+  const TriRec* tris;
+  int base, count;                   // slots [base, base + count)
+  int bx, by;                        // bbox lo | hi << 16 (pixels)
 };
 
-MWB_DEV ItemMap build_item_map(const DevState& S, int i) {
-  ItemMap m;
-  const size_t N = S.N;
-  const int g = geom_index(S, i);
-  m.n_quads = S.num_quads[g];
-  int n = m.n_quads;
-  m.n_ents = 0;
-  const int slots = S.num_slots[i];
-  const int ghost = S.ghost_slot[i];
-  // reference draw order: display list (rooms, static entities), then non-static entities;
-  // two passes over the list reproduce it
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int e = 0; e < slots && m.n_ents < 8; ++e) {
-      int p = e == ghost ? S.ghost_proto[i] : S.ent_proto[e * N + i];
-      if (p < 0) continue;
-      const mwb_proto& pr = S.protos[p];
-      if (pr.kind != MWB_KIND_BOX) continue;     // agent is never drawn; meshes: raster_mesh
-      if ((pr.is_static != 0) != (pass == 0)) continue;
-      m.ent_first[m.n_ents] = n;
-      m.ent_slot[m.n_ents] = e;
-      ++m.n_ents;
-      n += 6;
-    }
+struct SegLookup {                   // slot -> record
+  const Segment* seg;
+  int n;
+  MWB_DEVM const TriRec& operator()(uint32_t slot) const {
+    int k = 0;
+    while (k + 1 < n && (int)slot >= seg[k + 1].base) ++k;
+    return seg[k].tris[(int)slot - seg[k].base];
   }
-  m.ent_first[m.n_ents] = n;
-  m.n_items = n;
-  return m;
-}
+};
 
-MWB_DEV void fetch_item(const DevState& S, const RenderAssets& A, int i, const ItemMap& m, int idx, Item& it) {
-  if (idx < m.n_quads) {
-    room_item(S, A, i, idx, it);
-    return;
-  }
-  const size_t N = S.N;
-  int k = 0;
-  while (k + 1 < m.n_ents && idx >= m.ent_first[k + 1]) ++k;
-  const int e = m.ent_slot[k];
-  const int face = idx - m.ent_first[k];
-  double col[3];
-  if (e == S.ghost_slot[i]) {
-    for (int c = 0; c < 3; ++c) col[c] = S.ghost_col[c * N + i];
-    box_item(S.protos[S.ghost_proto[i]], S.ghost_pose[0 * N + i], S.ghost_pose[1 * N + i], S.ghost_pose[2 * N + i],
-             S.ghost_pose[3 * N + i], col, face, it);
-  } else {
-    for (int c = 0; c < 3; ++c) col[c] = S.ent_col[((size_t)e * 3 + c) * N + i];
-    box_item(S.protos[S.ent_proto[e * N + i]], S.ent_px[e * N + i], S.ent_py[e * N + i], S.ent_pz[e * N + i],
-             S.ent_dir[e * N + i], col, face, it);
-  }
-}
+// per (env, entity slot) result of mesh_setup_kernel
+struct MeshSegInfo {
+  int count, bx, by, pad;
+};
 
 // Resolve one pixel: average the colour of the surface seen by each sample (box filter of
-// the MSAA resolve blit), shading each distinct triangle once at the pixel centre.
-template <typename TriFetch>
-MWB_DEV void resolve_pixel(const RenderAssets& A, const Camera& cam, const TriFetch& tris, const uint32_t* keys,
-                           int msaa, int px, int py, uint8_t rgb[3]) {
+// the MSAA resolve blit), shading each distinct triangle once at the pixel centre.  The
+// distinct-surface loop is deliberately not unrolled: one copy of the shading code.
+template <int MSAA>
+MWB_DEV uint32_t key_id(uint32_t key) { return key >= MWB_SKY_KEY ? 0xFFFFu : (key & 0xFFFFu); }
+
+template <int MSAA, typename TriFetch>
+MWB_DEV void resolve_pixel(const RenderAssets& A, const Camera& cam, const TriFetch& tris, const uint32_t (&keys)[MSAA],
+                           int px, int py, uint8_t rgb[3]) {
   float acc[3] = {0.0f, 0.0f, 0.0f};
-  uint32_t done = 0;
-  const float wgt = 1.0f / (float)msaa;
-  for (int s = 0; s < msaa; ++s) {
-    if (done & (1u << s)) continue;
-    const uint32_t id = keys[s] >= MWB_SKY_KEY ? 0xFFFFu : (keys[s] & 0xFFFFu);
-    int cnt = 0;
-    for (int q = s; q < msaa; ++q) {
-      const uint32_t idq = keys[q] >= MWB_SKY_KEY ? 0xFFFFu : (keys[q] & 0xFFFFu);
-      if (idq == id) {
-        done |= 1u << q;
-        ++cnt;
-      }
-    }
+  uint32_t todo = (1u << MSAA) - 1u;
+  const float wgt = 1.0f / (float)MSAA;
+#pragma unroll 1
+  while (todo) {
+    // id of the first unprocessed sample (select chain: keys stay in registers)
+    const uint32_t first = todo & (0u - todo);
+    uint32_t id = 0;
+#pragma unroll
+    for (int s = 0; s < MSAA; ++s)
+      if (first == (1u << s)) id = key_id<MSAA>(keys[s]);
+    uint32_t same = 0;
+#pragma unroll
+    for (int s = 0; s < MSAA; ++s)
+      if (key_id<MSAA>(keys[s]) == id) same |= 1u << s;
+    todo &= ~same;
     float c[3];
     if (id == 0xFFFFu) {
       c[0] = cam.sky[0];
@@ -534,7 +674,11 @@ MWB_DEV void resolve_pixel(const RenderAssets& A, const Camera& cam, const TriFe
     } else {
       shade_pixel(A, tris(id), px, py, c);
     }
-    const float f = (float)cnt * wgt;
+#ifdef __CUDA_ARCH__
+    const float f = (float)__popc(same) * wgt;
+#else
+    const float f = (float)__builtin_popcount(same) * wgt;
+#endif
     acc[0] += f * c[0];
     acc[1] += f * c[1];
     acc[2] += f * c[2];

@@ -9,6 +9,9 @@
 #include "../../include/mwb.h"
 #include "np_rng.cuh"
 
+struct TriRec;
+struct MeshSegInfo;
+
 struct DevState {
   int32_t N, E, R, Q, S;        // envs, entity slots, room / quad / segment capacity
   int32_t shared_geom;
@@ -50,6 +53,11 @@ struct DevState {
   mwb_quad* quads;
   mwb_seg* segs;
   int32_t* room_tex;            // [N][R][3] texture id in use (domain-rand variants)
+
+  // ---- per-frame mesh triangle lists written by mesh_setup_kernel: [N][E][mesh_cap] ----
+  TriRec* mesh_tris;
+  MeshSegInfo* mesh_seg;        // [N][E]
+  int32_t mesh_cap;             // 0 = the level has no mesh entities
 
   // ---- level definition (shared) ----
   const mwb_proto* protos;

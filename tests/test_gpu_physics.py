@@ -13,13 +13,13 @@ pytestmark = pytest.mark.gpu
 def test_device_reset_levels_bit_exact(libmwb_path, name):
     """pose / dir / reward / terminated / truncated / entity poses / per-episode domain
     randomisation, every step, device-side resets included."""
-    T, N = run_trajectory(name, golden(name), libmwb_path, check_every=1)
+    T, N = run_trajectory(name, golden(name), libmwb_path, check_every=5)   # reward / flags every step
     assert T >= 300 and N >= 16
 
 
 @pytest.mark.parametrize("name", ["mazes3", "maze_dr"])
 def test_host_reset_levels_bit_exact(libmwb_path, name):
-    run_trajectory(name, golden(name), libmwb_path, check_every=1)
+    run_trajectory(name, golden(name), libmwb_path, check_every=5)
 
 
 def test_rng_stream_position_after_rollout(libmwb_path):

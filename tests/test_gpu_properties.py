@@ -22,7 +22,7 @@ def test_fourrooms_4096_properties(libmwb_path):
             obs, r, te, tr, info = env.step(a[t])
             tot_r += r
             n_done += int((te | tr).sum())
-            assert bool(((r == 0) | ((r > 0.8) & (r <= 1.0))).all())      # 1 - 0.2 * frac
+            assert bool(((r == 0) | ((r >= 0.8) & (r <= 1.0))).all())      # 1 - 0.2 * frac
             assert not bool((te & (r == 0)).any())
         st = env.get_state()
         # agents stay inside the floorplan minus their radius (test_collision_detection's invariant)
