@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MWB_ABI_VERSION 3
+#define MWB_ABI_VERSION 4
 
 /* error codes */
 #define MWB_OK 0
@@ -226,6 +226,7 @@ typedef struct mwb_state_view {
   mwb_rng_state* rng;        /* [N]                                                              */
   int32_t* room_tex;         /* [N][max_rooms][3] texture id in use per room surface             */
   int32_t* num_picked_up;    /* [N]                                                              */
+  int64_t* episodes_done;    /* [1] steps that ended an episode (terminated|truncated) so far    */
 } mwb_state_view;
 
 /* ---- lifetime ------------------------------------------------------------------------

@@ -107,6 +107,10 @@ class BatchedMiniWorld:
                 truncated=torch.zeros(N, dtype=torch.uint8, device=dev),
                 actions=torch.zeros(N, dtype=torch.int32, device=dev),
             )
+            # bool views of the uint8 flag buffers the kernel writes (no per-step conversion kernels)
+            self._bufs["term_view"] = self._bufs["terminated"].view(torch.bool)
+            self._bufs["trunc_view"] = self._bufs["truncated"].view(torch.bool)
+            self._info = {"depth": self._bufs["depth"]} if self.want_depth else {}
         return self._torch
 
     # ------------------------------------------------------------------ reset
@@ -163,20 +167,23 @@ class BatchedMiniWorld:
         as torch CUDA tensors; obs is uint8 [N, H, W, 3] (and info['depth'] when want_depth)."""
         torch = self._ensure_torch()
         b = self._bufs
-        if isinstance(actions, torch.Tensor):
+        if isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.int32 and actions.is_contiguous():
+            acts = actions                      # consumed in place by K1, no copy
+        elif isinstance(actions, torch.Tensor):
             b["actions"].copy_(actions.to(torch.int32), non_blocking=True)
+            acts = b["actions"]
         else:
             b["actions"].copy_(torch.as_tensor(np.asarray(actions, np.int32)), non_blocking=True)
+            acts = b["actions"]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if not self.device_reset and self.autoreset and self._host_done.any():
             self._host_reset(np.nonzero(self._host_done)[0].astype(np.int32), None, hold=True)
             self._host_done[:] = False
-        self.engine.step(b["actions"], obs=b["obs"], depth=b["depth"], reward=b["reward"],
+        self.engine.step(acts, obs=b["obs"], depth=b["depth"], reward=b["reward"],
                          terminated=b["terminated"], truncated=b["truncated"], stream=stream)
         if not self.device_reset and self.autoreset:
             self._host_done = (b["terminated"] | b["truncated"]).bool().cpu().numpy()
-        info = {"depth": b["depth"]} if self.want_depth else {}
-        return b["obs"], b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
+        return b["obs"], b["reward"], b["term_view"], b["trunc_view"], self._info
 
     def step_host(self, actions, out=None, render=True):
         """Same step with HOST buffers end to end (numpy in, numpy out): actions are copied

@@ -25,6 +25,7 @@
 #endif
 
 #define MWB_MAX_ENTS_CAP 16
+#define MWB_STAGE_QUAD_BYTES_HOST 16384
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -102,9 +103,15 @@ struct mwb_handle {
   int* d_overflow;
   WorldUpload* d_upload;
   int tri_cap;
+  int stage_bytes;
   bool have_params, have_protos, have_template;
   bool profiling;
+  bool frames_copied;
   int k2_minblocks;
+#ifndef MWB_HOSTSIM
+  cudaStream_t copy_stream;
+  cudaEvent_t chunk_done[4], copies_done;
+#endif
 #ifndef MWB_HOSTSIM
   std::vector<cudaEvent_t> ev_k1, ev_k2;   // start/stop pairs
 #endif
@@ -155,7 +162,14 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
       ts = S.params.turn_step;
     }
     o = physics_step(S, i, actions[i], fs, fd, ts);
-    if (S.autoreset && (o.terminated || o.truncated)) S.needs_reset[i] = 1;
+    if (o.terminated || o.truncated) {
+      if (S.autoreset) S.needs_reset[i] = 1;
+#ifdef __CUDA_ARCH__
+      atomicAdd(S.episodes_done, 1ull);
+#else
+      *S.episodes_done += 1ull;
+#endif
+    }
   }
   if (reward) reward[i] = o.reward;
   if (term) term[i] = (uint8_t)o.terminated;
@@ -274,11 +288,11 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* 
     TriRec rec;
     int seg;
     for (int task = 0; task < 2 * fm.n_quads; ++task)
-      if (task_triangle(S, A, cam, fm, i, task, W, H, rec, seg)) tris.push_back(rec);
+      if (task_triangle(S, A, cam, fm, env_quads(S, i), i, task, W, H, rec, seg)) tris.push_back(rec);
     for (int k = 0; k < fm.n_ents; ++k) {
       if (fm.ent_kind[k] == MWB_KIND_BOX) {
         for (int t = 0; t < 12; ++t)
-          if (task_triangle(S, A, cam, fm, i, fm.ent_task0[k] + t, W, H, rec, seg)) tris.push_back(rec);
+          if (task_triangle(S, A, cam, fm, env_quads(S, i), i, fm.ent_task0[k] + t, W, H, rec, seg)) tris.push_back(rec);
       } else {
         const mwb_proto& pr = S.protos[fm.ent_proto[k]];
         const EntPose P = entity_pose(S, i, fm.ent_slot[k]);
@@ -341,6 +355,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->cfg = *cfg;
   h->launches = 0;
   h->profiling = false;
+  h->frames_copied = false;
   h->have_params = h->have_protos = h->have_template = false;
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
   h->protos = h->ops = nullptr;
@@ -348,10 +363,13 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
 #ifndef MWB_HOSTSIM
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(MWB_ECUDA, "cudaStreamCreate failed");
   }
+  for (int c = 0; c < 4; ++c) cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming);
 #else
   h->stream = nullptr;
 #endif
@@ -360,7 +378,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   S.N = cfg->num_envs;
   S.E = cfg->max_ents;
   S.R = cfg->max_rooms;
-  S.Q = cfg->max_quads;
+  S.Q = (cfg->max_quads + 1) & ~1;   // even: per-env quad blocks stay 16-byte aligned (TMA source)
   S.S = cfg->max_segs;
   S.shared_geom = cfg->shared_geometry;
   S.obs_w = cfg->obs_width;
@@ -376,11 +394,11 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
 #define AL(field, count) if (!rc) rc = alloc_arr(h, &S.field, (count))
   AL(ent_proto, E * N); AL(ent_px, E * N); AL(ent_py, E * N); AL(ent_pz, E * N); AL(ent_dir, E * N);
   AL(ent_col, E * 3 * N); AL(num_slots, N); AL(agent_slot, N); AL(carrying, N); AL(step_count, N);
-  AL(num_picked, N); AL(needs_reset, N); AL(cam, 4 * N); AL(envp, 12 * N); AL(ghost_slot, N);
+  AL(num_picked, N); AL(needs_reset, N); AL(episodes_done, 1); AL(cam, 4 * N); AL(envp, 12 * N); AL(ghost_slot, N);
   AL(ghost_proto, N); AL(ghost_pose, 4 * N); AL(ghost_col, 3 * N);
   AL(rng_s_hi, N); AL(rng_s_lo, N); AL(rng_inc_hi, N); AL(rng_inc_lo, N); AL(rng_has32, N); AL(rng_cache, N);
   AL(num_rooms, G); AL(num_quads, G); AL(num_segs, G);
-  AL(rooms, G * S.R); AL(quads, G * S.Q); AL(segs, G * S.S); AL(room_tex, N * S.R * 3);
+  AL(rooms, G * S.R); AL(quads, G * S.Q + 2); AL(segs, G * S.S); AL(room_tex, N * S.R * 3);
   AL(mesh_seg, N * E);
 #undef AL
   if (!rc) rc = alloc_arr(h, &h->d_actions, N);
@@ -403,8 +421,12 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   dev_memset(S.carrying, 0xFF, N * sizeof(int32_t));
   h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);
   if (h->tri_cap > 1500) h->tri_cap = 1500;
+  // static quads are staged in shared memory (TMA bulk copy) when they fit in 16 KB; the
+  // quad capacity is kept even so that every env's block starts 16-byte aligned
+  h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
+  if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * (int)sizeof(TriRec);
+  const int smem = h->tri_cap * (int)sizeof(TriRec) + h->stage_bytes;
   CK(cudaFuncSetAttribute(render_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -432,6 +454,10 @@ extern "C" int mwb_destroy(mwb_handle* h) {
   for (void* p : extra)
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
+  cudaStreamSynchronize(h->copy_stream);
+  for (int c = 0; c < 4; ++c) cudaEventDestroy(h->chunk_done[c]);
+  cudaEventDestroy(h->copies_done);
+  cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
 #endif
   delete h;
@@ -774,17 +800,12 @@ extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int
 }
 
 // ------------------------------------------------------------------ ABI: the hot path
-static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s) {
-  if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
+// Launch K2 for envs [env0, env0 + count) (obs / depth point at env 0 of the full buffers).
+static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int count, stream_t s) {
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * (int)sizeof(TriRec);
-  if (h->S.mesh_cap > 0) {
-    mesh_setup_kernel<<<dim3(h->S.N, h->S.E), 256, 0, s>>>(h->S, h->A);
-    h->launches++;
-    CK(cudaGetLastError());
-  }
+  const int smem = h->tri_cap * (int)sizeof(TriRec) + h->stage_bytes;
   prof_mark(h, h->ev_k2, s);
-#define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<h->S.N, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, h->tri_cap, h->d_overflow)
+#define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<count, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, env0, h->tri_cap, h->stage_bytes, h->d_overflow)
   if (h->k2_minblocks == 2) {
     switch (h->S.msaa) {
       case 1: MWB_LAUNCH_K2(1, 2); break;
@@ -801,6 +822,46 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s) 
   prof_mark(h, h->ev_k2, s);
   h->launches++;
   CK(cudaGetLastError());
+#endif
+  return MWB_OK;
+}
+
+// Render all envs.  With host destinations the frame batch is cut into chunks: chunk c is
+// copied device->host on a second stream while chunk c + 1 is being rasterised, so the PCIe
+// transfer of the observations overlaps the render instead of following it.
+static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, uint8_t* host_obs = nullptr,
+                         float* host_depth = nullptr) {
+  if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
+#ifndef MWB_HOSTSIM
+  if (h->S.mesh_cap > 0) {
+    mesh_setup_kernel<<<dim3(h->S.N, h->S.E), 256, 0, s>>>(h->S, h->A);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  const int N = h->S.N;
+  const size_t px = (size_t)h->S.obs_w * h->S.obs_h;
+  const bool pipelined = (host_obs || host_depth) && N >= 256;
+  const int chunks = pipelined ? 4 : 1;
+  for (int c = 0; c < chunks; ++c) {
+    const int e0 = (int)((long long)N * c / chunks), e1 = (int)((long long)N * (c + 1) / chunks);
+    int rc = launch_k2(h, obs, depth, e0, e1 - e0, s);
+    if (rc) return rc;
+    if (pipelined) {
+      CK(cudaEventRecord(h->chunk_done[c], s));
+      CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+      if (host_obs)
+        CK(cudaMemcpyAsync(host_obs + (size_t)e0 * px * 3, obs + (size_t)e0 * px * 3, (size_t)(e1 - e0) * px * 3,
+                           cudaMemcpyDeviceToHost, h->copy_stream));
+      if (host_depth)
+        CK(cudaMemcpyAsync(host_depth + (size_t)e0 * px, depth + (size_t)e0 * px, (size_t)(e1 - e0) * px * sizeof(float),
+                           cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+  }
+  if (pipelined) {
+    h->frames_copied = true;
+    CK(cudaEventRecord(h->copies_done, h->copy_stream));
+    CK(cudaStreamWaitEvent(s, h->copies_done, 0));   // later work on s (and its sync) sees the copies
+  }
 #else
   hostsim_render(h->S, h->A, obs, depth);
 #endif
@@ -812,8 +873,9 @@ static int finish_outputs(mwb_handle* h, uint8_t* obs, bool obs_host, float* dep
   const size_t N = h->S.N, px = (size_t)h->S.obs_w * h->S.obs_h;
   int rc = 0;
   bool any_host = false;
-  if (obs && obs_host) { rc |= d2h(obs, h->d_obs, N * px * 3, s); any_host = true; }
-  if (depth && depth_host) { rc |= d2h(depth, h->d_depth, N * px * sizeof(float), s); any_host = true; }
+  if (obs && obs_host) { if (!h->frames_copied) rc |= d2h(obs, h->d_obs, N * px * 3, s); any_host = true; }
+  if (depth && depth_host) { if (!h->frames_copied) rc |= d2h(depth, h->d_depth, N * px * sizeof(float), s); any_host = true; }
+  h->frames_copied = false;
   if (reward && !is_device_ptr(reward)) { rc |= d2h(reward, h->d_reward, N * sizeof(double), s); any_host = true; }
   if (term && !is_device_ptr(term)) { rc |= d2h(term, h->d_term, N, s); any_host = true; }
   if (trunc && !is_device_ptr(trunc)) { rc |= d2h(trunc, h->d_trunc, N, s); any_host = true; }
@@ -858,7 +920,8 @@ extern "C" int mwb_step(mwb_handle* h, const int32_t* actions, const double* ste
 #endif
   const bool obs_host = obs && !is_device_ptr(obs), depth_host = depth && !is_device_ptr(depth);
   if (obs || depth) {
-    int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s);
+    int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s,
+                           obs_host ? obs : nullptr, depth_host ? depth : nullptr);
     if (rc) return rc;
   }
   return finish_outputs(h, obs, obs_host, depth, depth_host, reward, terminated, truncated, s, stream != nullptr);
@@ -868,7 +931,8 @@ extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* s
   if (!h || (!obs && !depth)) return fail(MWB_EINVAL, "null argument");
   stream_t s = stream ? (stream_t)stream : h->stream;
   const bool obs_host = obs && !is_device_ptr(obs), depth_host = depth && !is_device_ptr(depth);
-  int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s);
+  int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s,
+                         obs_host ? obs : nullptr, depth_host ? depth : nullptr);
   if (rc) return rc;
   return finish_outputs(h, obs, obs_host, depth, depth_host, nullptr, nullptr, nullptr, s, stream != nullptr);
 }
@@ -908,5 +972,10 @@ extern "C" int mwb_get_state(mwb_handle* h, const mwb_state_view* out) {
     if (out->rng) out->rng[i] = u.rng;
   }
   if (out->room_tex) memcpy(out->room_tex, rtex.data(), rtex.size() * sizeof(int32_t));
+  if (out->episodes_done) {
+    unsigned long long v = 0;
+    if (d2h(&v, h->S.episodes_done, sizeof(v), h->stream) != 0 || sync_stream(h->stream) != 0) return fail(MWB_ECUDA, "readback failed");
+    *out->episodes_done = (int64_t)v;
+  }
   return MWB_OK;
 }

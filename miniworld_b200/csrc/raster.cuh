@@ -28,6 +28,31 @@
 #define MWB_RENDER_THREADS 320
 #define MWB_RENDER_WARPS (MWB_RENDER_THREADS / 32)
 #define MWB_MAX_SEGS (1 + MWB_MAX_DRAWN)
+#define MWB_STAGE_QUAD_BYTES 16384   // static quads up to this size are staged in shared memory
+
+// ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier -----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
 
 // ---- mesh pre-pass: block (env i, entity slot e) sets up that entity's triangles ----------
 __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAssets A) {
@@ -104,8 +129,8 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
 // ---- K2 --------------------------------------------------------------------------------
 template <int MSAA, int MINB>
 __global__ void __launch_bounds__(MWB_RENDER_THREADS, MINB)
-render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int tri_cap,
-              int* __restrict__ overflow) {
+render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0, int tri_cap,
+              int stage_bytes, int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TriRec* tris = reinterpret_cast<TriRec*>(smem_raw);
   __shared__ Camera cam;
@@ -114,17 +139,30 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   __shared__ int seg_count[MWB_MAX_SEGS];
   __shared__ int warp_tot[MWB_RENDER_WARPS];
   __shared__ __align__(8) uint8_t stage[MWB_RENDER_WARPS][4][24];
+  __shared__ __align__(8) uint64_t quad_bar;
 
-  const int i = blockIdx.x;
+  const int i = env0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = S.obs_w, H = S.obs_h;
 
+  // static room quads of this env: staged into shared memory by one TMA bulk copy that overlaps
+  // the camera set-up (fixed-layout levels: 56 quads = 7.6 KB); larger templates are read from L2
+  const mwb_quad* gquads = env_quads(S, i);
+  const int nq = S.num_quads[geom_index(S, i)];
+  const uint32_t quad_bytes = ((uint32_t)nq * (uint32_t)sizeof(mwb_quad) + 15u) & ~15u;
+  const bool staged = quad_bytes > 0 && quad_bytes <= (uint32_t)stage_bytes;
+  mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + (size_t)tri_cap * sizeof(TriRec));
+  if (tid == 0) mbar_init(&quad_bar, 1);
+  if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
+  __syncthreads();
   if (tid == 0) {
+    if (staged) tma_bulk_g2s(squads, gquads, quad_bytes, &quad_bar);
     cam = make_camera(S, i);
     fmap = build_frame_map(S, i);
   }
-  if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
+  if (staged) mbar_wait(&quad_bar, 0);
+  const mwb_quad* quads = staged ? squads : gquads;
 
   // ---- B. room + box triangles -> shared memory, draw order preserved
   int ntris = 0;
@@ -132,7 +170,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
     const int task = start + tid;
     TriRec rec;
     int keep = 0, seg = 0;
-    if (task < fmap.n_tasks) keep = task_triangle(S, A, cam, fmap, i, task, W, H, rec, seg) ? 1 : 0;
+    if (task < fmap.n_tasks) keep = task_triangle(S, A, cam, fmap, quads, i, task, W, H, rec, seg) ? 1 : 0;
     int incl = keep;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -187,13 +225,20 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
 
   // ---- C/D. one warp per 8x8 tile, rasterised as two 8x4 halves (lane = one pixel) so that a
   //      single copy of the unrolled per-sample code serves both halves (instruction cache)
-  const int tiles_x = (W + 7) >> 3, tiles_y = (H + 7) >> 3;
+  const int tiles_x = (W + 7) >> 3;
   const int lx = lane & 7, ly = lane >> 3;
   const SegLookup fetch{segs, nsegs};
+  // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x
+  const int halves_y = (H + 3) >> 2;
+  int hcol = warp % tiles_x, hrow = warp / tiles_x;
 #pragma unroll 1
-  for (int half = warp; half < 2 * tiles_x * tiles_y; half += MWB_RENDER_WARPS) {
-    const int tile = half >> 1;
-    const int tx0 = (tile % tiles_x) << 3, ty0 = ((tile / tiles_x) << 3) + ((half & 1) << 2);
+  for (int half = warp; half < tiles_x * halves_y; half += MWB_RENDER_WARPS) {
+    const int tx0 = hcol << 3, ty0 = hrow << 2;
+    hcol += MWB_RENDER_WARPS;
+    while (hcol >= tiles_x) {
+      hcol -= tiles_x;
+      ++hrow;
+    }
     const int px = tx0 + lx, py = ty0 + ly;
     uint32_t keys[MSAA];
 #pragma unroll

@@ -335,24 +335,35 @@ MWB_DEV void raster_pixel(const HotTri& t, int slot, int px, int py, uint32_t (&
 
 // ---------------------------------------------------------------------------- shading
 
-MWB_DEV int wrap_repeat(int i, int n) {
-  int m = i % n;
-  return m < 0 ? m + n : m;
+// GL_REPEAT + GL_LINEAR on one mip level.  The texcoord is reduced to [0, 1) first (exact in
+// float32), so the texel index needs one conditional add instead of an integer modulo; 8-bit
+// texels are widened with the 2^23 "magic number" trick (byte dropped into the mantissa of
+// 8388608.0f), which also makes the differences c10 - c00 exact.
+MWB_DEV float texel_f(uint32_t t, int k) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__byte_perm(t, 0x4B000000u, k == 0 ? 0x7650u : (k == 1 ? 0x7651u : 0x7652u)));
+#else
+  union { uint32_t u; float f; } c;
+  c.u = 0x4B000000u | ((t >> (8 * k)) & 255u);
+  return c.f;
+#endif
 }
 
 MWB_DEV void bilinear(const RenderAssets& A, const TexDev& T, int level, float u, float v, float out[3]) {
-  int w = T.lw[level], h = T.lh[level];
+  const int w = T.lw[level], h = T.lh[level];
   const uint32_t* base = A.texels + T.off[level];
-  float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
-  float xf = floorf(x), yf = floorf(y);
-  float fx = x - xf, fy = y - yf;
-  int x0 = wrap_repeat((int)xf, w), y0 = wrap_repeat((int)yf, h);
-  int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
-  uint32_t t00 = base[y0 * w + x0], t10 = base[y0 * w + x1], t01 = base[y1 * w + x0], t11 = base[y1 * w + x1];
+  const float x = (u - floorf(u)) * (float)w - 0.5f, y = (v - floorf(v)) * (float)h - 0.5f;   // in [-0.5, size - 0.5)
+  const float xf = floorf(x), yf = floorf(y);
+  const float fx = x - xf, fy = y - yf;
+  int x0 = (int)xf, y0 = (int)yf;
+  x0 = x0 < 0 ? x0 + w : (x0 >= w ? x0 - w : x0);
+  y0 = y0 < 0 ? y0 + h : (y0 >= h ? y0 - h : y0);
+  const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
+  const uint32_t t00 = base[y0 * w + x0], t10 = base[y0 * w + x1], t01 = base[y1 * w + x0], t11 = base[y1 * w + x1];
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
-    float c00 = (float)((t00 >> (8 * k)) & 255u), c10 = (float)((t10 >> (8 * k)) & 255u);
-    float c01 = (float)((t01 >> (8 * k)) & 255u), c11 = (float)((t11 >> (8 * k)) & 255u);
-    float top = c00 + fx * (c10 - c00), bot = c01 + fx * (c11 - c01);
+    const float m00 = texel_f(t00, k), m10 = texel_f(t10, k), m01 = texel_f(t01, k), m11 = texel_f(t11, k);
+    const float top = (m00 - 8388608.0f) + fx * (m10 - m00), bot = (m01 - 8388608.0f) + fx * (m11 - m01);
     out[k] = (top + fy * (bot - top)) * (1.0f / 255.0f);
   }
 }
@@ -521,8 +532,9 @@ MWB_DEV bool finish_triangle(const Camera& cam, const TriInput& in, int W, int H
 }
 
 // half `half` (fan (0,1,2) / (0,2,3)) of static quad q of env i
-MWB_DEV bool room_triangle(const DevState& S, const RenderAssets& A, int i, int q, int half, TriInput& in) {
-  const mwb_quad& Q = S.quads[(size_t)geom_index(S, i) * S.Q + q];
+MWB_DEV bool room_triangle(const DevState& S, const RenderAssets& A, const mwb_quad* quads, int i, int q, int half,
+                           TriInput& in) {
+  const mwb_quad& Q = quads[q];   // this env's static quads: HBM/L2, or the TMA-staged shared-memory copy
   if (half == 1 && Q.num_verts < 4) return false;
   const int tex = S.room_tex[((size_t)i * S.R + Q.room) * 3 + Q.surf];
   const TexDev& T = A.tex[tex];
@@ -603,13 +615,15 @@ MWB_DEV void mesh_triangle(const RenderAssets& A, const mwb_proto& pr, const Ent
   in.tex = -1;   // ball_* / key_* carry no texture (objmesh.py:226-230)
 }
 
+MWB_DEV const mwb_quad* env_quads(const DevState& S, int i) { return S.quads + (size_t)geom_index(S, i) * S.Q; }
+
 // shared-memory triangle task -> (segment, record); false if culled / nonexistent
-MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camera& cam, const FrameMap& m, int i,
-                           int task, int W, int H, TriRec& out, int& seg) {
+MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camera& cam, const FrameMap& m,
+                           const mwb_quad* quads, int i, int task, int W, int H, TriRec& out, int& seg) {
   TriInput in;
   if (task < 2 * m.n_quads) {
     seg = 0;
-    if (!room_triangle(S, A, i, task >> 1, task & 1, in)) return false;
+    if (!room_triangle(S, A, quads, i, task >> 1, task & 1, in)) return false;
   } else {
     int k = 0;
     while (k + 1 < m.n_ents && (m.ent_task0[k] < 0 || task >= m.ent_task0[k] + 12)) ++k;

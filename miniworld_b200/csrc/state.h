@@ -30,6 +30,7 @@ struct DevState {
   int32_t* step_count;          // [N]
   int32_t* num_picked;          // [N]
   int32_t* needs_reset;         // [N] set by a terminated|truncated step when autoreset
+  unsigned long long* episodes_done;   // [1] device counter of episode-ending steps
   double* cam;                  // [4][N]  cam_height, cam_fwd_disp, cam_pitch, cam_fov_y
   double* envp;                 // [12][N] sky_color, light_pos, light_color, light_ambient
   // object removed by the level rule AFTER this step's observation (pickupobjects.py:86-90)

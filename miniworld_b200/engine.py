@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 RULE_NONE, RULE_GOAL, RULE_PICKUP = 0, 1, 2
 SURF_WALL, SURF_FLOOR, SURF_CEIL = 0, 1, 2
 OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE = 0, 1, 2, 3
@@ -94,7 +94,7 @@ class World(C.Structure):
 class StateView(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "agent_pos", "agent_dir", "step_count", "carrying", "num_slots", "agent_slot", "ents",
-        "cam", "env_params", "rng", "room_tex", "num_picked_up")]
+        "cam", "env_params", "rng", "room_tex", "num_picked_up", "episodes_done")]
 
 
 _EXPECTED_SIZES = None
@@ -367,7 +367,8 @@ class Engine:
         out = dict(agent_pos=np.zeros((N, 3)), agent_dir=np.zeros(N), step_count=np.zeros(N, np.int32),
                    carrying=np.zeros(N, np.int32), num_slots=np.zeros(N, np.int32),
                    agent_slot=np.zeros(N, np.int32), ents=np.zeros((N, E), ENTITY_DTYPE),
-                   cam=np.zeros((N, 4)), env_params=np.zeros((N, 12)), num_picked_up=np.zeros(N, np.int32))
+                   cam=np.zeros((N, 4)), env_params=np.zeros((N, 12)), num_picked_up=np.zeros(N, np.int32),
+                   episodes_done=np.zeros(1, np.int64))
         if rng:
             out["rng"] = np.zeros(N, RNG_DTYPE)
         if room_tex:
