@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -304,23 +305,51 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* 
         }
       }
     }
+    // test-only experiment: visit triangles front to back (MWB_HS_SORT=1); slots keep draw order
+    std::vector<int> order(tris.size());
+    for (size_t j = 0; j < tris.size(); ++j) order[j] = (int)j;
+    if (!getenv("MWB_HS_NOSORT")) {
+      std::vector<float> zmin(tris.size());
+      for (size_t j = 0; j < tris.size(); ++j) {
+        const TriRec& t = tris[j];
+        float x0 = (float)(t.bx & 0xFFFF), x1 = (float)((t.bx >> 16) + 1), y0 = (float)(t.by & 0xFFFF), y1 = (float)((t.by >> 16) + 1);
+        zmin[j] = t.Zc + fminf(t.Za * x0, t.Za * x1) + fminf(t.Zb * y0, t.Zb * y1);
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return zmin[a] < zmin[b]; });
+    }
     VecTris fetch{tris.data()};
     for (int py = 0; py < H; ++py)
       for (int px = 0; px < W; ++px) {
-        uint32_t keys[MSAA];
-        for (int s = 0; s < MSAA; ++s) keys[s] = MWB_SKY_KEY;
-        uint32_t kmax = MWB_SKY_KEY;
-        for (size_t j = 0; j < tris.size(); ++j) {
+        PixelState<MSAA> P;
+        pixel_init(P);
+        for (size_t jj = 0; jj < tris.size(); ++jj) {
+          const int j = order[jj];
           const TriRec& t = tris[j];
           if ((t.bx & 0xFFFF) > px || (t.bx >> 16) < px || (t.by & 0xFFFF) > py || (t.by >> 16) < py) continue;
-          raster_pixel<MSAA>(load_hot(&t), (int)j, px, py, keys, kmax);
+          if (!classify_pixel<MSAA>(load_class(&t), j, px, py, P)) continue;
+          if (P.mode == MWB_PX_LAZY) {     // materialise the lazily held triangle first
+            raster_pixel<MSAA>(load_hot(&tris[P.lazy_slot]), P.lazy_slot, px, py, P.keys, P.kmax);
+          }
+          P.mode = MWB_PX_EXPLICIT;
+          raster_pixel<MSAA>(load_hot(&t), j, px, py, P.keys, P.kmax);
         }
-        if (obs) {
-          uint8_t rgb[3];
-          resolve_pixel<MSAA>(A, cam, fetch, keys, px, py, rgb);
-          memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
+        uint32_t code0;
+        if (P.mode == MWB_PX_LAZY) {
+          const TriRec& t = tris[P.lazy_slot];
+          float c[3];
+          shade_pixel(A, t, px, py, c);
+          uint8_t rgb[3] = {to_unorm8(c[0]), to_unorm8(c[1]), to_unorm8(c[2])};
+          if (obs) memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
+          code0 = sample0_code<MSAA>(t, px, py);
+        } else {
+          if (obs) {
+            uint8_t rgb[3];
+            resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
+            memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
+          }
+          code0 = P.keys[0] >> 16;
         }
-        if (depth) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(keys[0] >> 16);
+        if (depth) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(code0);
       }
   }
 }
@@ -426,7 +455,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * (int)sizeof(TriRec) + h->stage_bytes;
+  const int smem = h->tri_cap * ((int)sizeof(TriRec) + 6) + 8 + h->stage_bytes;
   CK(cudaFuncSetAttribute(render_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -465,6 +494,11 @@ extern "C" int mwb_destroy(mwb_handle* h) {
 }
 
 extern "C" int64_t mwb_launch_count(mwb_handle* h) { return h ? h->launches : 0; }
+#ifdef MWB_HOSTSIM
+extern "C" void hs_counters(long long* out, int reset) {
+  for (int k = 0; k < 6; ++k) { out[k] = g_cnt[k]; if (reset) g_cnt[k] = 0; }
+}
+#endif
 
 extern "C" int mwb_abi_sizes(int32_t* out, int cap) {
   const int32_t sz[] = {(int32_t)sizeof(mwb_config), (int32_t)sizeof(mwb_params), (int32_t)sizeof(mwb_tex_desc),
@@ -803,7 +837,7 @@ extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int
 // Launch K2 for envs [env0, env0 + count) (obs / depth point at env 0 of the full buffers).
 static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int count, stream_t s) {
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * (int)sizeof(TriRec) + h->stage_bytes;
+  const int smem = h->tri_cap * ((int)sizeof(TriRec) + 6) + 8 + h->stage_bytes;
   prof_mark(h, h->ev_k2, s);
 #define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<count, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, env0, h->tri_cap, h->stage_bytes, h->d_overflow)
   if (h->k2_minblocks == 2) {

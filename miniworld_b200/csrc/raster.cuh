@@ -28,6 +28,7 @@
 #define MWB_RENDER_THREADS 320
 #define MWB_RENDER_WARPS (MWB_RENDER_THREADS / 32)
 #define MWB_MAX_SEGS (1 + MWB_MAX_DRAWN)
+#define MWB_SORT_LIMIT 512            // room triangle lists up to this length are depth-sorted
 #define MWB_STAGE_QUAD_BYTES 16384   // static quads up to this size are staged in shared memory
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier -----------
@@ -140,6 +141,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   __shared__ int warp_tot[MWB_RENDER_WARPS];
   __shared__ __align__(8) uint8_t stage[MWB_RENDER_WARPS][4][24];
   __shared__ __align__(8) uint64_t quad_bar;
+  __shared__ int chunk_idx[MWB_RENDER_WARPS][32];   // triangle tested by each lane in the current chunk
 
   const int i = env0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -152,6 +154,8 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   const uint32_t quad_bytes = ((uint32_t)nq * (uint32_t)sizeof(mwb_quad) + 15u) & ~15u;
   const bool staged = quad_bytes > 0 && quad_bytes <= (uint32_t)stage_bytes;
   mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + (size_t)tri_cap * sizeof(TriRec));
+  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)tri_cap * sizeof(TriRec) + stage_bytes);
+  float* zkey = reinterpret_cast<float*>(order + ((tri_cap + 1) & ~1));
   if (tid == 0) mbar_init(&quad_bar, 1);
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
@@ -223,8 +227,33 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   __syncthreads();
   const int nsegs = 1 + fmap.n_ents;
 
-  // ---- C/D. one warp per 8x8 tile, rasterised as two 8x4 halves (lane = one pixel) so that a
-  //      single copy of the unrolled per-sample code serves both halves (instruction cache)
+  // ---- visiting order of the room triangles: front to back by their nearest possible depth, so
+  // that the conservative occlusion tests fire early (the result does not depend on the order)
+  {
+    const int n0 = segs[0].count;
+    for (int t = tid; t < n0; t += MWB_RENDER_THREADS) {
+      const TriRec& T = tris[t];
+      const float x0 = (float)(T.bx & 0xFFFF), x1 = (float)((T.bx >> 16) + 1), y0 = (float)(T.by & 0xFFFF), y1 = (float)((T.by >> 16) + 1);
+      zkey[t] = T.Zc + fminf(T.Za * x0, T.Za * x1) + fminf(T.Zb * y0, T.Zb * y1);
+    }
+    __syncthreads();
+    if (n0 <= MWB_SORT_LIMIT) {
+      for (int t = tid; t < n0; t += MWB_RENDER_THREADS) {
+        const float z = zkey[t];
+        int rank = 0;
+        for (int q = 0; q < n0; ++q) {
+          const float zq = zkey[q];
+          rank += (zq < z || (zq == z && q < t)) ? 1 : 0;
+        }
+        order[rank] = (uint16_t)t;
+      }
+    } else {
+      for (int t = tid; t < n0; t += MWB_RENDER_THREADS) order[t] = (uint16_t)t;
+    }
+    __syncthreads();
+  }
+
+  // ---- C/D. one warp per 8x4 half-tile (lane = one pixel; an 8x8 tile is two of them)
   const int tiles_x = (W + 7) >> 3;
   const int lx = lane & 7, ly = lane >> 3;
   const SegLookup fetch{segs, nsegs};
@@ -240,24 +269,26 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
       ++hrow;
     }
     const int px = tx0 + lx, py = ty0 + ly;
-    uint32_t keys[MSAA];
-#pragma unroll
-    for (int s = 0; s < MSAA; ++s) keys[s] = MWB_SKY_KEY;
-    uint32_t kmax = MWB_SKY_KEY;
+    PixelState<MSAA> P;
+    pixel_init(P);
 
 #pragma unroll 1
     for (int sgi = 0; sgi < nsegs; ++sgi) {
       const Segment sg = segs[sgi];
       if (sg.count == 0) continue;
       if ((sg.bx & 0xFFFF) > tx0 + 7 || (sg.bx >> 16) < tx0 || (sg.by & 0xFFFF) > ty0 + 3 || (sg.by >> 16) < ty0) continue;
+      const uint16_t* ord = sgi == 0 ? order : nullptr;      // front-to-back visiting order of segment 0
 #pragma unroll 1
       for (int cb = 0; cb < sg.count; cb += 32) {
+        // largest depth code stored anywhere in this half-tile: a triangle that cannot beat it is dropped whole
+        const float tile_bound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(pixel_bound(P), 0.0f))));
         const int j = cb + lane;
-        bool hit = false;
+        int idx = -1;
         if (j < sg.count) {
-          const TriRec& t = sg.tris[j];
+          idx = ord ? (int)ord[j] : j;
+          const TriRec& t = sg.tris[idx];
           const int bx0 = t.bx & 0xFFFF, bx1 = t.bx >> 16, by0 = t.by & 0xFFFF, by1 = t.by >> 16;
-          hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0;
+          bool hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0;
           if (hit) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {   // half-tile entirely outside one edge?
@@ -265,21 +296,66 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
               const float cy = t.B[k] > 0.0f ? (float)(ty0 + 4) : (float)ty0;
               if (t.A[k] * cx + t.B[k] * cy + t.C[k] + t.R[k] < 0.0f) hit = false;
             }
+            // nearest depth the triangle can have inside the half-tile vs everything already stored
+            const float zx = t.Za > 0.0f ? (float)tx0 : (float)(tx0 + 8), zy = t.Zb > 0.0f ? (float)ty0 : (float)(ty0 + 4);
+            const float zmin = t.Za * zx + t.Zb * zy + t.Zc - t.Zr;
+            if (zmin * 65535.0f - 1.0f > tile_bound) hit = false;
           }
+          if (!hit) idx = -1;
         }
-        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        uint32_t mask = __ballot_sync(0xffffffffu, idx >= 0);
+        __syncwarp();
+        chunk_idx[warp][lane] = idx;
+        __syncwarp();
+        // phase 1 (warp-uniform): triage every surviving triangle at this lane's pixel
+        uint32_t mine = 0;
 #pragma unroll 1
         while (mask) {
           const int b = __ffs(mask) - 1;
           mask &= mask - 1;
-          const HotTri t = load_hot(sg.tris + cb + b);
-          raster_pixel<MSAA>(t, sg.base + cb + b, px, py, keys, kmax);
+          const int tb = chunk_idx[warp][b];
+          const ClassTri ct = load_class(sg.tris + tb);
+          if (classify_pixel<MSAA>(ct, sg.base + tb, px, py, P)) mine |= 1u << b;
+        }
+        // phase 2 (per-lane lists): exact per-sample processing of what each pixel could not decide
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, mine != 0)) {
+          if (mine) {
+            const TriRec* rec;
+            int slot;
+            if (P.mode == MWB_PX_LAZY) {           // first materialise the lazily held triangle
+              slot = P.lazy_slot;
+              rec = &fetch(slot);
+              P.mode = MWB_PX_EXPLICIT;
+            } else {
+              const int b = __ffs(mine) - 1;
+              mine &= mine - 1;
+              const int tb = chunk_idx[warp][b];
+              slot = sg.base + tb;
+              rec = sg.tris + tb;
+              P.mode = MWB_PX_EXPLICIT;
+            }
+            const HotTri t = load_hot(rec);
+            raster_pixel<MSAA>(t, slot, px, py, P.keys, P.kmax);
+          }
         }
       }
     }
 
     uint8_t rgb[3];
-    resolve_pixel<MSAA>(A, cam, fetch, keys, px, py, rgb);
+    uint32_t code0;
+    if (P.mode == MWB_PX_LAZY) {       // one surface owns every sample: shade it once
+      const TriRec& t = fetch(P.lazy_slot);
+      float c[3];
+      shade_pixel(A, t, px, py, c);
+      rgb[0] = to_unorm8(c[0]);
+      rgb[1] = to_unorm8(c[1]);
+      rgb[2] = to_unorm8(c[2]);
+      code0 = sample0_code<MSAA>(t, px, py);
+    } else {
+      resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
+      code0 = P.keys[0] >> 16;
+    }
     if (obs != nullptr) {
       __syncwarp();
 #pragma unroll
@@ -299,7 +375,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
         }
       }
     }
-    if (depth != nullptr && px < W && py < H) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(keys[0] >> 16);
+    if (depth != nullptr && px < W && py < H) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(code0);
   }
 }
 

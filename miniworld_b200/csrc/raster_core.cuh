@@ -299,18 +299,27 @@ MWB_DEV uint32_t max_key(const uint32_t (&keys)[MSAA]) {
 // slots ascend in draw order, so on equal codes the earlier draw keeps the sample).
 // `kmax` caches max(keys): a triangle whose nearest possible depth code over the pixel is
 // already behind every stored sample cannot win any GL_LESS test and is skipped.
+#ifdef MWB_HOSTSIM
+static long long g_cnt[6];   // test-only statistics: pairs, outside, zclip, occluded, sampled, changed
+#define MWB_COUNT(k) (++g_cnt[k])
+#else
+#define MWB_COUNT(k)
+#endif
+
 template <int MSAA>
 MWB_DEV void raster_pixel(const HotTri& t, int slot, int px, int py, uint32_t (&keys)[MSAA], uint32_t& kmax) {
+  MWB_COUNT(0);
   const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
   const float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
   const float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
   const float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
-  if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) return;   // certainly outside
+  if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) { MWB_COUNT(1); return; }   // certainly outside
   const float zc = t.Za * cx + t.Zb * cy + t.Zc;
   const float zlo = zc - t.Zr;
-  if (zlo > 1.0f || zc + t.Zr < 0.0f) return;                                    // beyond far / before near
+  if (zlo > 1.0f || zc + t.Zr < 0.0f) { MWB_COUNT(2); return; }                  // beyond far / before near
   // smallest code any sample of this pixel can get (one code of slack for the rounding of z * 65535)
-  if (zlo * 65535.0f - 1.0f > (float)(kmax >> 16)) return;                      // certainly occluded
+  if (zlo * 65535.0f - 1.0f > (float)(kmax >> 16)) { MWB_COUNT(3); return; }    // certainly occluded
+  MWB_COUNT(4);
   const bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;   // certainly inside
   const float fx = (float)px, fy = (float)py;
   bool changed = false;
@@ -330,10 +339,103 @@ MWB_DEV void raster_pixel(const HotTri& t, int slot, int px, int py, uint32_t (&
       changed = true;
     }
   }
-  if (changed) kmax = max_key<MSAA>(keys);
+  if (changed) { MWB_COUNT(5); kmax = max_key<MSAA>(keys); }
 }
 
 // ---------------------------------------------------------------------------- shading
+
+// ---- lazy visibility ---------------------------------------------------------------------
+// Most pixels of a frame end up entirely inside ONE triangle.  For them the eight exact
+// per-sample depth codes are never needed: PixelState keeps such a pixel in LAZY mode ("all
+// samples belong to triangle `lazy_slot`, whose depth codes lie in [lazy_clo, lazy_chi]") and only
+// MATERIALISES the explicit per-sample keys when a later triangle cannot be ordered against
+// it by conservative bounds alone.  Every shortcut is one-sided: a triangle is skipped only if
+// it would certainly lose every GL_LESS test, installed lazily only if it certainly covers all
+// samples, is not clipped and certainly wins them all.  The final image is therefore identical
+// to plain per-sample processing (and independent of the order triangles are visited in, since
+// the per-sample result is min over (depth code, slot)).
+#define MWB_PX_EMPTY 0
+#define MWB_PX_LAZY 1
+#define MWB_PX_EXPLICIT 2
+
+template <int MSAA>
+struct PixelState {
+  uint32_t keys[MSAA];
+  uint32_t kmax;
+  int32_t mode;
+  int32_t lazy_slot;
+  float lazy_clo, lazy_chi;      // conservative bounds of the lazy triangle's depth codes here
+};
+
+template <int MSAA>
+MWB_DEV void pixel_init(PixelState<MSAA>& p) {
+#pragma unroll
+  for (int s = 0; s < MSAA; ++s) p.keys[s] = MWB_SKY_KEY;
+  p.kmax = MWB_SKY_KEY;
+  p.mode = MWB_PX_EMPTY;
+  p.lazy_slot = -1;
+  p.lazy_clo = p.lazy_chi = 65535.0f;
+}
+
+// largest depth code that can currently be stored at any sample of the pixel
+template <int MSAA>
+MWB_DEV float pixel_bound(const PixelState<MSAA>& p) {
+  return p.mode == MWB_PX_LAZY ? p.lazy_chi : (float)(p.kmax >> 16);
+}
+
+// the 16 floats classification needs (A, B, C, R, Z plane), broadcast to the whole warp
+struct ClassTri {
+  float A[3], B[3], C[3], R[3];
+  float Za, Zb, Zc, Zr;
+};
+
+MWB_DEV ClassTri load_class(const TriRec* t) {
+  ClassTri h;
+#ifdef __CUDA_ARCH__
+  const float4* p = reinterpret_cast<const float4*>(t);
+  const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+  h.A[0] = q0.x; h.A[1] = q0.y; h.A[2] = q0.z; h.B[0] = q0.w;
+  h.B[1] = q1.x; h.B[2] = q1.y; h.C[0] = q1.z; h.C[1] = q1.w;
+  h.C[2] = q2.x; h.R[0] = q2.y; h.R[1] = q2.z; h.R[2] = q2.w;
+  h.Za = q3.x; h.Zb = q3.y; h.Zc = q3.z; h.Zr = q3.w;
+#else
+  for (int k = 0; k < 3; ++k) { h.A[k] = t->A[k]; h.B[k] = t->B[k]; h.C[k] = t->C[k]; h.R[k] = t->R[k]; }
+  h.Za = t->Za; h.Zb = t->Zb; h.Zc = t->Zc; h.Zr = t->Zr;
+#endif
+  return h;
+}
+
+// Cheap per-pixel triage of one triangle.  Returns true if the triangle still needs exact
+// per-sample processing at this pixel (raster_pixel); false if it was skipped or installed lazily.
+template <int MSAA>
+MWB_DEV bool classify_pixel(const ClassTri& t, int slot, int px, int py, PixelState<MSAA>& p) {
+  MWB_COUNT(0);
+  const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
+  const float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
+  const float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
+  const float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
+  if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) { MWB_COUNT(1); return false; }   // certainly outside
+  const float zc = t.Za * cx + t.Zb * cy + t.Zc;
+  const float zlo = zc - t.Zr, zhi = zc + t.Zr;
+  if (zlo > 1.0f || zhi < 0.0f) { MWB_COUNT(2); return false; }                       // certainly clipped away
+  // depth codes any sample of this pixel can get lie in [clo, chi] (one code of slack each way)
+  const float clo = zlo * 65535.0f - 1.0f, chi = zhi * 65535.0f + 1.5f;
+  if (clo > pixel_bound(p)) { MWB_COUNT(3); return false; }                           // certainly occluded
+  const bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;   // covers every sample
+  const bool unclipped = zlo >= 0.0f && zhi <= 1.0f && chi < 65535.0f;
+  if (full && unclipped) {
+    const bool wins = p.mode == MWB_PX_EMPTY || (p.mode == MWB_PX_LAZY && chi < p.lazy_clo);
+    if (wins) {                      // every sample now certainly belongs to this triangle
+      p.mode = MWB_PX_LAZY;
+      p.lazy_slot = slot;
+      p.lazy_clo = clo;
+      p.lazy_chi = chi;
+      MWB_COUNT(5);
+      return false;
+    }
+  }
+  return true;
+}
 
 // GL_REPEAT + GL_LINEAR on one mip level.  The texcoord is reduced to [0, 1) first (exact in
 // float32), so the texel index needs one conditional add instead of an integer modulo; 8-bit
@@ -660,6 +762,14 @@ struct MeshSegInfo {
 // distinct-surface loop is deliberately not unrolled: one copy of the shading code.
 template <int MSAA>
 MWB_DEV uint32_t key_id(uint32_t key) { return key >= MWB_SKY_KEY ? 0xFFFFu : (key & 0xFFFFu); }
+
+// exact depth code of triangle t at sample 0 of pixel (px, py) (lazy pixels: t is unclipped there)
+template <int MSAA>
+MWB_DEV uint32_t sample0_code(const TriRec& t, int px, int py) {
+  const float xs = (float)px + sample_x<MSAA>(0), ys = (float)py + sample_y<MSAA>(0);
+  const float z = f_add(f_add(f_mul(t.Za, xs), f_mul(t.Zb, ys)), t.Zc);
+  return (uint32_t)f_add(f_mul(z, 65535.0f), 0.5f);
+}
 
 template <int MSAA, typename TriFetch>
 MWB_DEV void resolve_pixel(const RenderAssets& A, const Camera& cam, const TriFetch& tris, const uint32_t (&keys)[MSAA],
