@@ -65,6 +65,8 @@ extern "C" {
 #define MWB_OP_CHOICE 1   /* ireg[a] = np_random.choice(b)            (== integers(0, b))      */
 #define MWB_OP_UNIFORM 2  /* freg[a] = np_random.uniform(f[0], f[1])                           */
 #define MWB_OP_PLACE 3    /* place_entity(); see mwb_op                                         */
+#define MWB_OP_MAZE 4     /* Maze._gen_world() room topology (reference envs/maze.py:73-153): recursive  */
+                          /* backtracker on the env's RNG stream, geometry from mwb_set_maze templates   */
 
 typedef struct mwb_handle mwb_handle;
 
@@ -248,6 +250,28 @@ int mwb_set_protos(mwb_handle* h, const mwb_proto* protos, int n);         /* en
 int mwb_set_template(mwb_handle* h, const mwb_geometry* g);                /* shared static rooms */
 int mwb_set_program(mwb_handle* h, const mwb_op* ops, int n);              /* lowered _gen_world  */
 
+/* Maze level (reference envs/maze.py): every episode's world is a translate-and-select of these
+ * templates -- one grid cell and one connector room per neighbour direction, in the order of
+ * maze.py:110 `orders = [(0, 1), (0, -1), (-1, 0), (1, 0)]` as (dj, di).  All records are for
+ * cell (0, 0); the kernel adds (i, j) * pitch. */
+typedef struct mwb_maze_desc {
+  int32_t rows, cols;
+  double pitch;                      /* room_size + gap_size                                       */
+  mwb_room cell_room;
+  mwb_quad cell_quads[6];            /* floor, ceiling, walls of edges 0..3                        */
+  mwb_seg cell_segs[4];
+  int32_t open_a[4], open_b[4];      /* edge opened in the current cell / in the neighbour          */
+  mwb_room conn_room[4];             /* connector created by connect_rooms (miniworld.py:768-837)  */
+  mwb_quad conn_quads[4][4];         /* floor, ceiling, two side walls                             */
+  mwb_seg conn_segs[4][2];
+  const double* cdf;                 /* [2 rows cols - 1] cumulative room_probs (list order fixed) */
+} mwb_maze_desc;
+int mwb_set_maze(mwb_handle* h, const mwb_maze_desc* maze);
+
+/* static geometry of one env as currently on the device (tests, debugging); arrays sized by the
+ * handle's max_rooms / max_quads / max_segs */
+int mwb_get_geometry(mwb_handle* h, int env, int32_t counts[3], mwb_room* rooms, mwb_quad* quads, mwb_seg* segs);
+
 /* ---- reset: MiniWorldEnv.reset (miniworld.py:544-604) ----------------------------------
  * mwb_seed      = gym.Env.reset(seed=...): installs Generator(PCG64(SeedSequence(seed))) state
  * mwb_reset     = device-side reset of the listed envs with the lowered program (RNG on device)
@@ -276,6 +300,9 @@ int mwb_get_state(mwb_handle* h, const mwb_state_view* out);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mwb_launch_count(mwb_handle* h);
 
+/* frames whose culled triangle list did not fit the kernel's shared-memory budget (must stay 0) */
+int64_t mwb_overflow_count(mwb_handle* h);
+
 /* Device-side timing of the two kernels: when enabled, every K1 / K2 launch is bracketed by
  * CUDA events on the launching stream; mwb_profile_read synchronises, returns the summed
  * milliseconds and launch counts since the last read, and clears them (bench.py roofline). */
@@ -283,7 +310,7 @@ int mwb_profile(mwb_handle* h, int enable);
 int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int64_t* k1_launches, int64_t* k2_launches);
 
 /* sizeof() of every ABI struct, in declaration order (config, params, tex_desc, mesh_desc,
- * room, quad, seg, proto, entity, op, geometry, world, rng_state, state_view): lets a
+ * room, quad, seg, proto, entity, op, geometry, world, rng_state, state_view, maze_desc): lets a
  * binding verify its mirror of this header.  Returns the number of entries written. */
 int mwb_abi_sizes(int32_t* out, int cap);
 

@@ -60,19 +60,34 @@ class BatchedMiniWorld:
         self.device_reset = getattr(pe, "device_program", None) is not None
 
         rooms, quads, segs = pack.pack_geometry(pe)
+        self.maze_template = None
         if self.device_reset:
             self.program = ResetProgram()
             pe.device_program(self.program)
+            if self.program.uses_maze:
+                # per-episode topology on the device: only if the translated templates reproduce
+                # host-generated worlds exactly; otherwise fall back to host-side resets
+                from .maze_lowering import MazeTemplate
+                try:
+                    tmpl = MazeTemplate(self.level_cls, domain_rand=self.domain_rand, **self.level_kwargs)
+                    tmpl.verify(seeds=(0,))
+                    self.maze_template = tmpl
+                except AssertionError:
+                    self.device_reset = False
+        if self.device_reset:
             protos = self.program.proto_array()
             max_ents = max(8, self.program.num_placed)
             caps = (len(rooms), len(quads), len(segs))
+            if self.maze_template is not None:
+                caps = (len(rooms), len(quads) + 8, len(segs) + 8)
         else:
             self.program = None
             protos = None
             max_ents = 8
             caps = tuple(int(1.25 * n) + 4 for n in (len(rooms), len(quads), len(segs)))
+        shared = self.device_reset and self.maze_template is None
         self.engine = Engine(self.num_envs, obs_width, obs_height, msaa_samples,
-                             shared_geometry=self.device_reset, max_rooms=caps[0], max_quads=caps[1],
+                             shared_geometry=shared, max_rooms=caps[0], max_quads=caps[1],
                              max_segs=caps[2], max_ents=max_ents, rule=rule, domain_rand=self.domain_rand,
                              max_episode_steps=self.max_episode_steps, autoreset=autoreset and self.device_reset,
                              device=device, lib_path=lib_path)
@@ -82,7 +97,10 @@ class BatchedMiniWorld:
         eng.set_params(pe.params)
         if self.device_reset:
             eng.set_protos(protos)
-            eng.set_template(rooms, quads, segs)
+            if self.maze_template is not None:
+                eng.set_maze(self.maze_template, pack.room_cdf(pe.room_probs))
+            else:
+                eng.set_template(rooms, quads, segs)
             eng.set_program(self.program.op_array())
         else:
             # host-reset levels: one worker env per slot keeps that env's RNG stream

@@ -119,7 +119,7 @@ struct mwb_handle {
   std::vector<int> mesh_counts;   // triangles per uploaded mesh (host copy)
   void* mesh_tris_buf;
   // asset storage
-  void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops;
+  void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops, *maze, *maze_cdf;
 };
 
 template <typename T>
@@ -387,7 +387,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->frames_copied = false;
   h->have_params = h->have_protos = h->have_template = false;
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
-  h->protos = h->ops = nullptr;
+  h->protos = h->ops = h->maze = h->maze_cdf = nullptr;
   h->mesh_tris_buf = nullptr;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
@@ -449,7 +449,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   dev_memset(S.ghost_slot, 0xFF, N * sizeof(int32_t));
   dev_memset(S.carrying, 0xFF, N * sizeof(int32_t));
   h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);
-  if (h->tri_cap > 1500) h->tri_cap = 1500;
+  if (h->tri_cap > 640) h->tri_cap = 640;   // set-up triangles that survive culling (overflow is counted)
   // static quads are staged in shared memory (TMA bulk copy) when they fit in 16 KB; the
   // quad capacity is kept even so that every env's block starts 16-byte aligned
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
@@ -479,7 +479,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
 #endif
   for (void* p : h->allocs) dev_free(p);
   void* extra[] = {h->tex_desc, h->texels, h->mesh_desc, h->mesh_pos, h->mesh_nrm, h->mesh_uv, h->mesh_rgb,
-                   h->protos, h->ops, h->mesh_tris_buf};
+                   h->protos, h->ops, h->mesh_tris_buf, h->maze, h->maze_cdf};
   for (void* p : extra)
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
@@ -494,6 +494,13 @@ extern "C" int mwb_destroy(mwb_handle* h) {
 }
 
 extern "C" int64_t mwb_launch_count(mwb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int64_t mwb_overflow_count(mwb_handle* h) {
+  if (!h) return 0;
+  int v = 0;
+  if (d2h(&v, h->d_overflow, sizeof(int), h->stream) != 0 || sync_stream(h->stream) != 0) return -1;
+  return v;
+}
 #ifdef MWB_HOSTSIM
 extern "C" void hs_counters(long long* out, int reset) {
   for (int k = 0; k < 6; ++k) { out[k] = g_cnt[k]; if (reset) g_cnt[k] = 0; }
@@ -505,7 +512,7 @@ extern "C" int mwb_abi_sizes(int32_t* out, int cap) {
                         (int32_t)sizeof(mwb_mesh_desc), (int32_t)sizeof(mwb_room), (int32_t)sizeof(mwb_quad),
                         (int32_t)sizeof(mwb_seg), (int32_t)sizeof(mwb_proto), (int32_t)sizeof(mwb_entity),
                         (int32_t)sizeof(mwb_op), (int32_t)sizeof(mwb_geometry), (int32_t)sizeof(mwb_world),
-                        (int32_t)sizeof(mwb_rng_state), (int32_t)sizeof(mwb_state_view)};
+                        (int32_t)sizeof(mwb_rng_state), (int32_t)sizeof(mwb_state_view), (int32_t)sizeof(mwb_maze_desc)};
   const int n = (int)(sizeof(sz) / sizeof(sz[0]));
   for (int k = 0; k < n && k < cap; ++k) out[k] = sz[k];
   return n;
@@ -675,6 +682,48 @@ extern "C" int mwb_set_program(mwb_handle* h, const mwb_op* ops, int n) {
   h->S.ops = (const mwb_op*)h->ops;
   h->S.num_ops = n;
   return MWB_OK;
+}
+
+extern "C" int mwb_set_maze(mwb_handle* h, const mwb_maze_desc* mz) {
+  if (!h || !mz || !mz->cdf) return fail(MWB_EINVAL, "null argument");
+  if (h->S.shared_geom) return fail(MWB_ESTATE, "Maze needs per-env geometry (shared_geometry = 0)");
+  const int cells = mz->rows * mz->cols;
+  if (cells <= 0 || cells > MWB_MAZE_MAX_CELLS) return fail(MWB_ECAPACITY, "maze too large");
+  if (2 * cells - 1 > h->S.R) return fail(MWB_ECAPACITY, "max_rooms too small for this maze");
+  MazeDev m;
+  memset(&m, 0, sizeof(m));
+  m.rows = mz->rows;
+  m.cols = mz->cols;
+  m.pitch = mz->pitch;
+  m.cell_room = mz->cell_room;
+  memcpy(m.cell_quads, mz->cell_quads, sizeof(m.cell_quads));
+  memcpy(m.cell_segs, mz->cell_segs, sizeof(m.cell_segs));
+  memcpy(m.open_a, mz->open_a, sizeof(m.open_a));
+  memcpy(m.open_b, mz->open_b, sizeof(m.open_b));
+  memcpy(m.conn_room, mz->conn_room, sizeof(m.conn_room));
+  memcpy(m.conn_quads, mz->conn_quads, sizeof(m.conn_quads));
+  memcpy(m.conn_segs, mz->conn_segs, sizeof(m.conn_segs));
+  int rc = replace_buf(&h->maze, &m, sizeof(m), h->stream);
+  if (!rc) rc = replace_buf(&h->maze_cdf, mz->cdf, (size_t)(2 * cells - 1) * sizeof(double), h->stream);
+  if (rc) return rc;
+  h->S.maze = (const MazeDev*)h->maze;
+  h->S.maze_cdf = (const double*)h->maze_cdf;
+  return MWB_OK;
+}
+
+extern "C" int mwb_get_geometry(mwb_handle* h, int env, int32_t counts[3], mwb_room* rooms, mwb_quad* quads, mwb_seg* segs) {
+  if (!h || !counts) return fail(MWB_EINVAL, "null argument");
+  if (env < 0 || env >= h->S.N) return fail(MWB_EINVAL, "env out of range");
+  const size_t g = h->S.shared_geom ? 0 : (size_t)env;
+  int rc = 0;
+  rc |= d2h(&counts[0], h->S.num_rooms + g, sizeof(int32_t), h->stream);
+  rc |= d2h(&counts[1], h->S.num_quads + g, sizeof(int32_t), h->stream);
+  rc |= d2h(&counts[2], h->S.num_segs + g, sizeof(int32_t), h->stream);
+  if (rooms) rc |= d2h(rooms, h->S.rooms + g * h->S.R, (size_t)h->S.R * sizeof(mwb_room), h->stream);
+  if (quads) rc |= d2h(quads, h->S.quads + g * h->S.Q, (size_t)h->cfg.max_quads * sizeof(mwb_quad), h->stream);
+  if (segs) rc |= d2h(segs, h->S.segs + g * h->S.S, (size_t)h->S.S * sizeof(mwb_seg), h->stream);
+  rc |= sync_stream(h->stream);
+  return rc ? fail(MWB_ECUDA, "readback failed") : MWB_OK;
 }
 
 // ------------------------------------------------------------------ ABI: reset

@@ -342,20 +342,18 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
       }
     }
 
+    // Lazy pixels join the common resolve path as "all samples see lazy_slot", so that the
+    // (expensive) shading code runs once for the whole warp instead of once per mode.
     uint8_t rgb[3];
     uint32_t code0;
-    if (P.mode == MWB_PX_LAZY) {       // one surface owns every sample: shade it once
-      const TriRec& t = fetch(P.lazy_slot);
-      float c[3];
-      shade_pixel(A, t, px, py, c);
-      rgb[0] = to_unorm8(c[0]);
-      rgb[1] = to_unorm8(c[1]);
-      rgb[2] = to_unorm8(c[2]);
-      code0 = sample0_code<MSAA>(t, px, py);
+    if (P.mode == MWB_PX_LAZY) {
+      code0 = sample0_code<MSAA>(fetch(P.lazy_slot), px, py);
+#pragma unroll
+      for (int s = 0; s < MSAA; ++s) P.keys[s] = (uint32_t)P.lazy_slot;
     } else {
-      resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
       code0 = P.keys[0] >> 16;
     }
+    resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
     if (obs != nullptr) {
       __syncwarp();
 #pragma unroll

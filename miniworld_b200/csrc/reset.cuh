@@ -10,6 +10,7 @@
 // shared static template.  Levels whose topology is random per episode (Maze) reset on the
 // host and arrive through mwb_set_world instead.
 #pragma once
+#include "maze.cuh"
 #include "physics.cuh"
 
 // Room.point_inside: all(sum(edge_norms * (p - outline), axis=1) > 0)
@@ -27,7 +28,7 @@ MWB_DEV void device_reset(const DevState& S, int i) {
   const mwb_params& P = S.params;
   const int g = geom_index(S, i);
   const mwb_room* rooms = S.rooms + (size_t)g * S.R;
-  const int n_rooms = S.num_rooms[g];
+  int n_rooms = S.num_rooms[g];
 
   S.step_count[i] = 0;
   S.carrying[i] = -1;
@@ -49,6 +50,10 @@ MWB_DEV void device_reset(const DevState& S, int i) {
   for (int pc = 0; pc < S.num_ops; ++pc) {
     const mwb_op& op = S.ops[pc];
     if (op.op == MWB_OP_END) break;
+    if (op.op == MWB_OP_MAZE) {          // per-episode topology: regenerate this env's rooms
+      if (S.maze != nullptr && !S.shared_geom && maze_generate(S, *S.maze, S.maze_cdf, i, rng)) n_rooms = S.num_rooms[g];
+      continue;
+    }
     if (op.op == MWB_OP_CHOICE) {
       ireg[op.a & 7] = (int)rng_integers(rng, (uint32_t)op.b);
     } else if (op.op == MWB_OP_UNIFORM) {

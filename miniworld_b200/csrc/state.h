@@ -11,6 +11,7 @@
 
 struct TriRec;
 struct MeshSegInfo;
+struct MazeDev;
 
 struct DevState {
   int32_t N, E, R, Q, S;        // envs, entity slots, room / quad / segment capacity
@@ -61,6 +62,8 @@ struct DevState {
   int32_t mesh_cap;             // 0 = the level has no mesh entities
 
   // ---- level definition (shared) ----
+  const MazeDev* maze;          // Maze templates (mwb_set_maze) or null
+  const double* maze_cdf;
   const mwb_proto* protos;
   int32_t num_protos;
   const mwb_op* ops;

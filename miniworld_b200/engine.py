@@ -13,7 +13,7 @@ import numpy as np
 ABI_VERSION = 4
 RULE_NONE, RULE_GOAL, RULE_PICKUP = 0, 1, 2
 SURF_WALL, SURF_FLOOR, SURF_CEIL = 0, 1, 2
-OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE = 0, 1, 2, 3
+OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE, OP_MAZE = 0, 1, 2, 3, 4
 MAX_EDGES = 8
 MAX_ENTS_CAP = 16
 
@@ -91,6 +91,14 @@ class World(C.Structure):
                 ("light_color", C.c_double * 3), ("light_ambient", C.c_double * 3)]
 
 
+class MazeDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("pitch", C.c_double),
+                ("cell_room", C.c_byte * ROOM_DTYPE.itemsize), ("cell_quads", C.c_byte * (6 * QUAD_DTYPE.itemsize)),
+                ("cell_segs", C.c_byte * (4 * SEG_DTYPE.itemsize)), ("open_a", C.c_int32 * 4), ("open_b", C.c_int32 * 4),
+                ("conn_room", C.c_byte * (4 * ROOM_DTYPE.itemsize)), ("conn_quads", C.c_byte * (16 * QUAD_DTYPE.itemsize)),
+                ("conn_segs", C.c_byte * (8 * SEG_DTYPE.itemsize)), ("cdf", C.c_void_p)]
+
+
 class StateView(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "agent_pos", "agent_dir", "step_count", "carrying", "num_slots", "agent_slot", "ents",
@@ -104,14 +112,15 @@ def _expected_sizes():
     return [C.sizeof(Config), C.sizeof(Params), C.sizeof(TexDesc), C.sizeof(MeshDesc),
             ROOM_DTYPE.itemsize, QUAD_DTYPE.itemsize, SEG_DTYPE.itemsize, PROTO_DTYPE.itemsize,
             ENTITY_DTYPE.itemsize, OP_DTYPE.itemsize, C.sizeof(Geometry), C.sizeof(World),
-            RNG_DTYPE.itemsize, C.sizeof(StateView)]
+            RNG_DTYPE.itemsize, C.sizeof(StateView), C.sizeof(MazeDesc)]
 
 
 EXPORTS = (
     "mwb_create", "mwb_destroy", "mwb_last_error", "mwb_upload_textures", "mwb_upload_meshes",
     "mwb_set_params", "mwb_set_protos", "mwb_set_template", "mwb_set_program", "mwb_seed",
     "mwb_reset", "mwb_set_world", "mwb_step", "mwb_render_obs", "mwb_get_state",
-    "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read",
+    "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read", "mwb_set_maze", "mwb_get_geometry",
+    "mwb_overflow_count",
 )
 
 _libs = {}
@@ -145,11 +154,15 @@ def load_library(lib_path=None):
     lib.mwb_launch_count.argtypes = [vp]
     lib.mwb_launch_count.restype = C.c_int64
     lib.mwb_abi_sizes.argtypes = [i32p, C.c_int]
+    lib.mwb_set_maze.argtypes = [vp, C.POINTER(MazeDesc)]
+    lib.mwb_get_geometry.argtypes = [vp, C.c_int, i32p, vp, vp, vp]
+    lib.mwb_overflow_count.argtypes = [vp]
+    lib.mwb_overflow_count.restype = C.c_int64
     lib.mwb_profile.argtypes = [vp, C.c_int]
     lib.mwb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int64)]
     for name in EXPORTS:
-        if name not in ("mwb_last_error", "mwb_launch_count"):
+        if name not in ("mwb_last_error", "mwb_launch_count", "mwb_overflow_count"):
             getattr(lib, name).restype = C.c_int
     sizes = (C.c_int32 * 32)()
     n = lib.mwb_abi_sizes(sizes, 32)
@@ -300,6 +313,39 @@ class Engine:
         self._keep = (rooms, quads, segs)
         g = self._geometry(rooms, quads, segs)
         self._check(self.lib.mwb_set_template(self.h, C.byref(g)))
+
+    def set_maze(self, tmpl, cdf):
+        """tmpl: maze_lowering.MazeTemplate; cdf: float64[2 rows cols - 1]."""
+        d = MazeDesc()
+        d.rows, d.cols, d.pitch = tmpl.rows, tmpl.cols, tmpl.pitch
+
+        def put(field, arr):
+            raw = np.ascontiguousarray(arr).tobytes()
+            assert len(raw) == C.sizeof(field), (len(raw), C.sizeof(field))
+            C.memmove(field, raw, len(raw))
+
+        put(d.cell_room, np.array(tmpl.cell_room, ROOM_DTYPE))
+        put(d.cell_quads, np.array(tmpl.cell_quads, QUAD_DTYPE))
+        put(d.cell_segs, np.array(tmpl.cell_segs, SEG_DTYPE))
+        for k in range(4):
+            d.open_a[k], d.open_b[k] = tmpl.open_a[k], tmpl.open_b[k]
+        put(d.conn_room, np.array([c[0] for c in tmpl.conn], ROOM_DTYPE))
+        put(d.conn_quads, np.array([c[1] for c in tmpl.conn], QUAD_DTYPE))
+        put(d.conn_segs, np.array([c[2] for c in tmpl.conn], SEG_DTYPE))
+        self._maze_cdf = np.ascontiguousarray(cdf, np.float64)
+        d.cdf = self._maze_cdf.ctypes.data
+        self._check(self.lib.mwb_set_maze(self.h, C.byref(d)))
+
+    def get_geometry(self, env):
+        counts = (C.c_int32 * 3)()
+        rooms = np.zeros(self.cfg.max_rooms, ROOM_DTYPE)
+        quads = np.zeros(self.cfg.max_quads, QUAD_DTYPE)
+        segs = np.zeros(self.cfg.max_segs, SEG_DTYPE)
+        self._check(self.lib.mwb_get_geometry(self.h, int(env), counts, _ptr(rooms), _ptr(quads), _ptr(segs)))
+        return rooms[:counts[0]], quads[:counts[1]], segs[:counts[2]]
+
+    def overflow_count(self):
+        return int(self.lib.mwb_overflow_count(self.h))
 
     def set_program(self, ops):
         ops = np.ascontiguousarray(ops, OP_DTYPE)

@@ -55,8 +55,12 @@ class Maze(GoalBoxRule, MiniWorldEnv, utils.EzPickle):
         self.box = self.place_entity(Box(color="red"))
         self.place_agent()
 
-    # topology is random per episode -> no shared static template (see batched.py)
-    device_program = None
+    def device_program(self, prog):
+        """Topology is random per episode: the carving itself is lowered (csrc/maze.cuh), using
+        geometry templates that maze_lowering.MazeTemplate cuts out of host-built worlds."""
+        prog.maze()
+        prog.place(prog.proto(Box(color="red")))
+        prog.place_agent()
 
 
 class MazeS2(Maze):

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from .engine import OP_CHOICE, OP_DTYPE, OP_PLACE, OP_UNIFORM, PROTO_DTYPE
+from .engine import OP_CHOICE, OP_DTYPE, OP_MAZE, OP_PLACE, OP_UNIFORM, PROTO_DTYPE
 from .entity import Agent
 from .pack import proto_record
 
@@ -33,6 +33,7 @@ class ResetProgram:
         self._freg = 0
         self.agent_proto = self.proto(Agent())
         self.num_placed = 0
+        self.uses_maze = False
 
     # ---- prototypes
     def proto(self, ent):
@@ -48,6 +49,14 @@ class ResetProgram:
             for ent in row:
                 self.proto(ent)
         return ProtoTable(base, (cols, 1))
+
+    # ---- per-episode topology
+    def maze(self):
+        """Maze._gen_world()'s room carving runs on the device (csrc/maze.cuh)."""
+        op = np.zeros((), OP_DTYPE)
+        op["op"] = OP_MAZE
+        self.ops.append(op)
+        self.uses_maze = True
 
     # ---- random draws
     def choice(self, n):

@@ -34,3 +34,30 @@ def test_render_matches_oracle(hostsim_path, softgl_lib):
         assert 0 < rgb.mean() < 255
     ts.close()
     env.close()
+
+
+@pytest.mark.parametrize("name,n", [("mazes3", 6), ("maze_dr", 4)])
+def test_device_maze_geometry_equals_host_world(hostsim_path, name, n):
+    """csrc/maze.cuh (recursive backtracker on the env's numpy stream + translated templates)
+    builds the same rooms / quads / collision segments as the Python `_gen_world()`."""
+    from miniworld_b200 import pack
+    from miniworld_b200.envs import LEVELS
+    level, dr = CASES[name]
+    g = golden(name)
+    env = make_env(name, g, hostsim_path, n=n)
+    assert env.device_reset and env.maze_template is not None
+    for i in range(n):
+        host = LEVELS[level](device=None, domain_rand=dr)
+        host.reset(seed=1000 + i)
+        want = pack.pack_geometry(host)
+        got = env.engine.get_geometry(i)
+        for w, d, what in zip(want, got, ("rooms", "quads", "segs")):
+            assert len(w) == len(d), (what, len(w), len(d))
+            for field in w.dtype.names:
+                if field != "reserved":
+                    assert np.array_equal(w[field], d[field]), (what, field, i)
+    env.close()
+
+
+def test_device_maze_long_rollout_with_resets(hostsim_path):
+    run_trajectory("mazes3", golden("mazes3"), hostsim_path, steps=300, n=8, check_every=25)
