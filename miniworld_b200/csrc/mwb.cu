@@ -462,9 +462,12 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   CK(cudaFuncSetAttribute(render_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(render_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   {
     const char* v = getenv("MWB_K2_MINBLOCKS");   // tuning knob: resident blocks per SM the kernel is compiled for
-    h->k2_minblocks = (v && atoi(v) == 2) ? 2 : 3;
+    h->k2_minblocks = (v && (atoi(v) == 2 || atoi(v) == 4)) ? atoi(v) : 3;
   }
 #endif
   *out = h;
@@ -894,6 +897,12 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
       case 1: MWB_LAUNCH_K2(1, 2); break;
       case 4: MWB_LAUNCH_K2(4, 2); break;
       default: MWB_LAUNCH_K2(8, 2); break;
+    }
+  } else if (h->k2_minblocks == 4) {
+    switch (h->S.msaa) {
+      case 1: MWB_LAUNCH_K2(1, 4); break;
+      case 4: MWB_LAUNCH_K2(4, 4); break;
+      default: MWB_LAUNCH_K2(8, 4); break;
     }
   } else {
     switch (h->S.msaa) {

@@ -165,7 +165,7 @@ MWB_DEV void light_vertex(const Camera& c, float x, float y, float z, float nx, 
   }
 }
 
-// One set-up triangle, 36 words (144 B, 16-byte aligned so the rasteriser's hot part -- the
+// One set-up triangle, 44 words (176 B, 16-byte aligned so the rasteriser's hot part -- the
 // first 64 bytes -- moves as four 128-bit loads).  Edge k is opposite vertex k, so
 // E_k / sum(E) is the perspective-correct weight of vertex k's attributes.
 struct MWB_ALIGN16 TriRec {
@@ -178,7 +178,8 @@ struct MWB_ALIGN16 TriRec {
   int32_t bx, by;                //                         smallest positive float, i.e. E > 0)
   float u[3], v[3];              // texcoords per vertex
   float r[3], g[3], b[3];        // lit colour per vertex
-  float pad[1];
+  float UA, UB, VA, VB, SA, SB;  // sum_k u_k A_k, sum_k u_k B_k, ... : per-triangle parts of du/dx, dv/dx, ...
+  float pad[3];
 };
 
 // the hot 76 bytes of a TriRec, held in registers while a tile is rasterised
@@ -244,7 +245,7 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   t.Zc = f_div(f_add(f_add(f_mul(v0.zeta, t.C[0]), f_mul(v1.zeta, t.C[1])), f_mul(v2.zeta, t.C[2])), det);
   // |z(sample) - z(centre)| <= 0.4375 (|Za| + |Zb|); plus a bound on evaluation rounding
   t.Zr = 0.4375f * (fabsf(t.Za) + fabsf(t.Zb)) + 4e-6f * (fabsf(t.Za) * (float)W + fabsf(t.Zb) * (float)H + fabsf(t.Zc)) + 1e-6f;
-  t.pad[0] = 0.0f;
+  t.pad[0] = t.pad[1] = t.pad[2] = 0.0f;
   for (int k = 0; k < 3; ++k) {
     float aa = fabsf(t.A[k]), ab = fabsf(t.B[k]);
     // |E(sample) - E(centre)| <= 0.4375 (|A| + |B|); plus a bound on evaluation rounding
@@ -261,6 +262,12 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   t.g[0] = b0.g; t.g[1] = b1.g; t.g[2] = b2.g;
   t.b[0] = b0.b; t.b[1] = b1.b; t.b[2] = b2.b;
   t.tex = tex;
+  t.UA = t.u[0] * t.A[0] + t.u[1] * t.A[1] + t.u[2] * t.A[2];
+  t.UB = t.u[0] * t.B[0] + t.u[1] * t.B[1] + t.u[2] * t.B[2];
+  t.VA = t.v[0] * t.A[0] + t.v[1] * t.A[1] + t.v[2] * t.A[2];
+  t.VB = t.v[0] * t.B[0] + t.v[1] * t.B[1] + t.v[2] * t.B[2];
+  t.SA = t.A[0] + t.A[1] + t.A[2];
+  t.SB = t.B[0] + t.B[1] + t.B[2];
   // screen bbox (conservative); any vertex at or behind the eye plane -> whole frame
   int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
   const float weps = 1e-3f;
@@ -477,7 +484,11 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
   float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
   float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
   float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
-  float inv = 1.0f / (e0 + e1 + e2);
+#ifdef __CUDA_ARCH__
+  const float inv = __frcp_rn(e0 + e1 + e2);
+#else
+  const float inv = 1.0f / (e0 + e1 + e2);
+#endif
   float b0 = e0 * inv, b1 = e1 * inv, b2 = e2 * inv;
   float r = b0 * t.r[0] + b1 * t.r[1] + b2 * t.r[2];
   float g = b0 * t.g[0] + b1 * t.g[1] + b2 * t.g[2];
@@ -486,11 +497,8 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
     const TexDev& T = A.tex[t.tex];
     float u = b0 * t.u[0] + b1 * t.u[1] + b2 * t.u[2];
     float v = b0 * t.v[0] + b1 * t.v[1] + b2 * t.v[2];
-    float sa = t.A[0] + t.A[1] + t.A[2], sb = t.B[0] + t.B[1] + t.B[2];
-    float dudx = (t.u[0] * t.A[0] + t.u[1] * t.A[1] + t.u[2] * t.A[2] - u * sa) * inv * (float)T.w;
-    float dvdx = (t.v[0] * t.A[0] + t.v[1] * t.A[1] + t.v[2] * t.A[2] - v * sa) * inv * (float)T.h;
-    float dudy = (t.u[0] * t.B[0] + t.u[1] * t.B[1] + t.u[2] * t.B[2] - u * sb) * inv * (float)T.w;
-    float dvdy = (t.v[0] * t.B[0] + t.v[1] * t.B[1] + t.v[2] * t.B[2] - v * sb) * inv * (float)T.h;
+    const float dudx = (t.UA - u * t.SA) * inv * (float)T.w, dvdx = (t.VA - v * t.SA) * inv * (float)T.h;
+    const float dudy = (t.UB - u * t.SB) * inv * (float)T.w, dvdy = (t.VB - v * t.SB) * inv * (float)T.h;
     float rho2 = fmaxf(dudx * dudx + dvdx * dvdx, dudy * dudy + dvdy * dvdy);
     float lambda = 0.5f * log2f(fmaxf(rho2, 1e-20f));
     // magnification: GL_LINEAR on level 0; else GL_LINEAR_MIPMAP_LINEAR between floor(lambda) and +1
