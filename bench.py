@@ -172,14 +172,22 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, args.warmup
     N = args.envs
-    env = BatchedMiniWorld(LEVEL, N, obs_width=W, obs_height=H, want_depth=True, device=local)
-    env.reset(seed=1000 + rank * N)
+    sharded, peer = None, False
+    if world > 1:
+        from miniworld_b200.dist import ShardedMiniWorld
+        sharded = ShardedMiniWorld(LEVEL, world * N, dist=dist, device=local, obs_width=W, obs_height=H, want_depth=True)
+        env = sharded.local
+        sharded.reset(1000)
+        peer = (not args.nccl_gather) and sharded.enable_peer_obs()
+    else:
+        env = BatchedMiniWorld(LEVEL, N, obs_width=W, obs_height=H, want_depth=True, device=local)
+        env.reset(seed=1000)
     total = Wm + K
     gen = np.random.default_rng(12345 + rank)
     acts_np = gen.integers(0, env.action_space.n, size=(total, N), dtype=np.int32)
     acts = torch.as_tensor(acts_np, device=dev)
     gather_list = None
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and not peer:
         gather_list = [torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(world)]
 
     def barrier():
@@ -188,10 +196,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def one_step(t):
+        if peer:                          # K2 writes into rank 0's HBM over NVLink; 4-byte all-reduce as the fence
+            return sharded.step_peer(acts[t])
         obs, rew, te, tr, info = env.step(acts[t])
         if world > 1:
             dist.gather(obs, gather_list, dst=0)
-        return obs, rew, te, tr
+        return obs
 
     # ---- device-resident arm
     for t in range(Wm):
@@ -259,7 +269,9 @@ def run_ours(args):
             "dtype": "f64+f32", "data": "synthetic",
             "config": {"workload": "%s N_envs=%d per GPU, 80x60 RGB+depth, 8x MSAA, random actions, next-step "
                                    "auto-reset on device" % (LEVEL, N),
-                       "global_envs": world * N, "obs_gather": "NCCL gather of uint8 obs to rank 0" if world > 1 else "none",
+                       "global_envs": world * N, "obs_gather": ("none" if world == 1 else "K2 stores its tiles straight into rank 0's buffer (CUDA IPC peer memory "
+                                      "over NVLink) + one 4-byte all-reduce per step" if peer else
+                                      "NCCL gather of uint8 obs to rank 0"),
                        "l2": "per-step outputs %.1f MB > 126 MB L2; no explicit flush" % (bytes_per_launch / 1e6),
                        "episodes_finished_in_timed_region": done_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -286,6 +298,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-gather", action="store_true", help="gather observations with NCCL instead of peer stores")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -309,6 +309,15 @@ int64_t mwb_overflow_count(mwb_handle* h);
 int mwb_profile(mwb_handle* h, int enable);
 int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int64_t* k1_launches, int64_t* k2_launches);
 
+/* ---- peer-memory observation buffer (multi-GPU, SURVEY 8e "fused option") ---------------
+ * One process per GPU: rank 0 allocates the global observation buffer with mwb_shared_alloc and
+ * publishes its 64-byte CUDA IPC handle; the other ranks map it with mwb_shared_open and pass
+ * `mapped + start_env * H * W * 3` as the `obs` argument of mwb_step, so K2's row-segment stores
+ * land directly in rank 0's HBM over NVLink -- the gather collective disappears.  */
+int mwb_shared_alloc(int device, size_t bytes, void** dev_ptr, unsigned char handle[64]);
+int mwb_shared_open(int device, const unsigned char handle[64], void** dev_ptr);
+int mwb_shared_close(void* dev_ptr, int opened /* 1: from mwb_shared_open, 0: from mwb_shared_alloc */);
+
 /* sizeof() of every ABI struct, in declaration order (config, params, tex_desc, mesh_desc,
  * room, quad, seg, proto, entity, op, geometry, world, rng_state, state_view, maze_desc): lets a
  * binding verify its mirror of this header.  Returns the number of entries written. */

@@ -104,6 +104,7 @@ struct mwb_handle {
   int* d_overflow;
   WorldUpload* d_upload;
   int tri_cap;
+  bool smem_tris;
   int stage_bytes;
   bool have_params, have_protos, have_template;
   bool profiling;
@@ -448,14 +449,24 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   dev_memset(S.ent_proto, 0xFF, E * N * sizeof(int32_t));
   dev_memset(S.ghost_slot, 0xFF, N * sizeof(int32_t));
   dev_memset(S.carrying, 0xFF, N * sizeof(int32_t));
+  // every room quad and box face can yield two set-up triangles.  Up to 512 of them live in
+  // shared memory; larger levels (Maze) keep the per-env lists in HBM instead.
   h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);
-  if (h->tri_cap > 640) h->tri_cap = 640;   // set-up triangles that survive culling (overflow is counted)
+  h->smem_tris = h->tri_cap <= 512;
+  if (!h->smem_tris) {
+    TriRec* buf = nullptr;
+    if (alloc_arr(h, &buf, (size_t)N * h->tri_cap)) {
+      mwb_destroy(h);
+      return fail(MWB_ECUDA, "triangle list allocation failed");
+    }
+    S.room_tris = buf;
+  }
   // static quads are staged in shared memory (TMA bulk copy) when they fit in 16 KB; the
   // quad capacity is kept even so that every env's block starts 16-byte aligned
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * ((int)sizeof(TriRec) + 6) + 8 + h->stage_bytes;
+  const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
   CK(cudaFuncSetAttribute(render_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(render_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -838,6 +849,44 @@ extern "C" int mwb_set_world(mwb_handle* h, const int32_t* env_ids, int n, const
   return launch_upload(h, up, false);
 }
 
+// ------------------------------------------------------------------ peer-memory buffers
+extern "C" int mwb_shared_alloc(int device, size_t bytes, void** dev_ptr, unsigned char handle[64]) {
+#ifndef MWB_HOSTSIM
+  if (!dev_ptr || !handle) return fail(MWB_EINVAL, "null argument");
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(dev_ptr, bytes));
+  cudaIpcMemHandle_t hd;
+  static_assert(sizeof(hd) == 64, "CUDA IPC handle size");
+  CK(cudaIpcGetMemHandle(&hd, *dev_ptr));
+  memcpy(handle, &hd, 64);
+  return MWB_OK;
+#else
+  return fail(MWB_ENOCUDA, "host simulator has no peer memory");
+#endif
+}
+
+extern "C" int mwb_shared_open(int device, const unsigned char handle[64], void** dev_ptr) {
+#ifndef MWB_HOSTSIM
+  if (!dev_ptr || !handle) return fail(MWB_EINVAL, "null argument");
+  CK(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  CK(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return MWB_OK;
+#else
+  return fail(MWB_ENOCUDA, "host simulator has no peer memory");
+#endif
+}
+
+extern "C" int mwb_shared_close(void* dev_ptr, int opened) {
+#ifndef MWB_HOSTSIM
+  if (!dev_ptr) return MWB_OK;
+  if (opened) CK(cudaIpcCloseMemHandle(dev_ptr));
+  else CK(cudaFree(dev_ptr));
+#endif
+  return MWB_OK;
+}
+
 // ------------------------------------------------------------------ profiling
 #ifndef MWB_HOSTSIM
 static void prof_mark(mwb_handle* h, std::vector<cudaEvent_t>& v, stream_t s) {
@@ -889,7 +938,7 @@ extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int
 // Launch K2 for envs [env0, env0 + count) (obs / depth point at env 0 of the full buffers).
 static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int count, stream_t s) {
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * ((int)sizeof(TriRec) + 6) + 8 + h->stage_bytes;
+  const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
   prof_mark(h, h->ev_k2, s);
 #define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<count, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, env0, h->tri_cap, h->stage_bytes, h->d_overflow)
   if (h->k2_minblocks == 2) {

@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(MWB_RENDER_THREADS, MINB)
 render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0, int tri_cap,
               int stage_bytes, int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TriRec* tris = reinterpret_cast<TriRec*>(smem_raw);
+  // set-up triangles of rooms + boxes: shared memory, or this env's HBM block for big levels
+  const size_t tri_bytes = S.room_tris ? 0 : (size_t)tri_cap * sizeof(TriRec);
+  TriRec* tris = S.room_tris ? S.room_tris + (size_t)(env0 + blockIdx.x) * tri_cap : reinterpret_cast<TriRec*>(smem_raw);
   __shared__ Camera cam;
   __shared__ FrameMap fmap;
   __shared__ Segment segs[MWB_MAX_SEGS];
@@ -153,8 +155,8 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   const int nq = S.num_quads[geom_index(S, i)];
   const uint32_t quad_bytes = ((uint32_t)nq * (uint32_t)sizeof(mwb_quad) + 15u) & ~15u;
   const bool staged = quad_bytes > 0 && quad_bytes <= (uint32_t)stage_bytes;
-  mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + (size_t)tri_cap * sizeof(TriRec));
-  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + (size_t)tri_cap * sizeof(TriRec) + stage_bytes);
+  mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + tri_bytes);
+  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + tri_bytes + stage_bytes);
   float* zkey = reinterpret_cast<float*>(order + ((tri_cap + 1) & ~1));
   if (tid == 0) mbar_init(&quad_bar, 1);
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;

@@ -60,6 +60,8 @@ struct DevState {
   TriRec* mesh_tris;
   MeshSegInfo* mesh_seg;        // [N][E]
   int32_t mesh_cap;             // 0 = the level has no mesh entities
+  TriRec* room_tris;            // [N][tri_cap] room + box triangle lists in HBM for levels whose lists do
+                                //   not fit shared memory (Maze); null = lists live in shared memory
 
   // ---- level definition (shared) ----
   const MazeDev* maze;          // Maze templates (mwb_set_maze) or null

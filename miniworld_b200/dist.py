@@ -68,6 +68,53 @@ class ShardedMiniWorld:
         self.dist.send(tensor.contiguous(), dst=0)
         return None
 
+    # ---- peer-memory observations: K2 of every rank stores straight into rank 0's buffer
+    def enable_peer_obs(self):
+        """Rank 0 allocates uint8 [total, H, W, 3] and shares it over CUDA IPC; the other ranks map
+        it and render into their slice of it (stores cross NVLink inside K2).  Returns True if
+        every rank succeeded; otherwise the NCCL-gather path stays in use."""
+        import torch
+        from .engine import EngineError, SharedDeviceBuffer
+        H, W = self.local.obs_height, self.local.obs_width
+        shape = (self.total, H, W, 3)
+        dev = self.local.device
+        ok, self._peer = 1, None
+        payload = [None]
+        try:
+            if self.rank == 0:
+                self._peer = SharedDeviceBuffer(dev, shape)
+                payload = [self._peer.handle]
+        except EngineError:
+            ok = 0
+        if self.dist is not None and self.world > 1:
+            self.dist.broadcast_object_list(payload, src=0)
+            if self.rank != 0 and payload[0] is not None:
+                try:
+                    self._peer = SharedDeviceBuffer(dev, shape, handle=payload[0])
+                except EngineError:
+                    ok = 0
+            flag = torch.tensor([ok if payload[0] is not None else 0], device=torch.device("cuda", dev))
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            if self._peer is not None:
+                self._peer.close()
+            self._peer = None
+            return False
+        self.obs_all = self._peer.tensor()                         # [total, H, W, 3] in rank 0's HBM
+        self.local._bufs_ready = self.local._ensure_torch()
+        self.local._bufs["obs"] = self.obs_all[self.start:self.start + self.count]   # this rank's slice
+        self._sync = torch.zeros(1, device=torch.device("cuda", dev))
+        return True
+
+    def step_peer(self, local_actions):
+        """K1 + K2 with observations written into rank 0's buffer; one tiny stream-ordered
+        all-reduce tells rank 0 that every slice is complete.  Returns obs_all on rank 0."""
+        obs, rew, te, tr, info = self.local.step(local_actions)
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(self._sync)
+        return self.obs_all if self.rank == 0 else None
+
     def step(self, local_actions):
         """Local K1 + K2, then the gather of obs / reward / flags to rank 0."""
         obs, rew, te, tr, info = self.local.step(local_actions)
@@ -75,4 +122,6 @@ class ShardedMiniWorld:
                 self.gather_to_root(tr.to(obs.dtype)))
 
     def close(self):
+        if getattr(self, "_peer", None) is not None:
+            self._peer.close()
         self.local.close()

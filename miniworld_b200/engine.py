@@ -120,7 +120,7 @@ EXPORTS = (
     "mwb_set_params", "mwb_set_protos", "mwb_set_template", "mwb_set_program", "mwb_seed",
     "mwb_reset", "mwb_set_world", "mwb_step", "mwb_render_obs", "mwb_get_state",
     "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read", "mwb_set_maze", "mwb_get_geometry",
-    "mwb_overflow_count",
+    "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
 )
 
 _libs = {}
@@ -156,6 +156,9 @@ def load_library(lib_path=None):
     lib.mwb_abi_sizes.argtypes = [i32p, C.c_int]
     lib.mwb_set_maze.argtypes = [vp, C.POINTER(MazeDesc)]
     lib.mwb_get_geometry.argtypes = [vp, C.c_int, i32p, vp, vp, vp]
+    lib.mwb_shared_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.mwb_shared_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    lib.mwb_shared_close.argtypes = [vp, C.c_int]
     lib.mwb_overflow_count.argtypes = [vp]
     lib.mwb_overflow_count.restype = C.c_int64
     lib.mwb_profile.argtypes = [vp, C.c_int]
@@ -171,6 +174,41 @@ def load_library(lib_path=None):
         raise EngineError("ABI struct size mismatch: library %r vs binding %r" % (got, want))
     _libs[path] = lib
     return lib
+
+
+class SharedDeviceBuffer:
+    """Device memory that other processes on the box can map (CUDA IPC), exposed to torch
+    through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, device, shape, handle=None, lib_path=None):
+        self.lib = load_library(lib_path)
+        self.shape = tuple(int(v) for v in shape)
+        self.nbytes = int(np.prod(self.shape))
+        self.device = int(device)
+        self.ptr = C.c_void_p()
+        self.opened = handle is not None
+        if handle is None:
+            buf = C.create_string_buffer(64)
+            rc = self.lib.mwb_shared_alloc(self.device, self.nbytes, C.byref(self.ptr), buf)
+            self.handle = buf.raw
+        else:
+            self.handle = bytes(handle)
+            rc = self.lib.mwb_shared_open(self.device, self.handle, C.byref(self.ptr))
+        if rc != 0:
+            raise EngineError("peer buffer: %s" % (self.lib.mwb_last_error() or b"").decode())
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "|u1", "data": (self.ptr.value, False), "version": 3, "strides": None}
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", self.device))
+
+    def close(self):
+        if self.ptr:
+            self.lib.mwb_shared_close(self.ptr, int(self.opened))
+            self.ptr = C.c_void_p()
 
 
 def rng_state_of(seed_or_generator):

@@ -1,0 +1,71 @@
+"""Two GPUs: the peer-memory observation path (K2 stores into rank 0's buffer over NVLink)
+returns exactly what the NCCL gather and a single-process run return.  Skipped with < 2 GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, total, steps, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from miniworld_b200.dist import ShardedMiniWorld
+    acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)
+    results = {}
+    for mode in ("nccl", "peer"):
+        env = ShardedMiniWorld("MiniWorld-FourRooms-v0", total, dist=dist, device=rank)
+        env.reset(1000)
+        ok = mode == "nccl" or env.enable_peer_obs()
+        frames = []
+        for t in range(steps):
+            mine = torch.as_tensor(acts_all[t, env.start:env.start + env.count], device="cuda")
+            if mode == "peer" and ok:
+                obs = env.step_peer(mine)
+            else:
+                obs = env.step(mine)[0]
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                frames.append(obs.cpu().numpy().copy())
+        results[mode] = (ok, frames)
+        env.close()
+    if rank == 0:
+        q.put({k: (v[0], np.stack(v[1])) for k, v in results.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_observation_buffer_equals_gather(libmwb_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    total, steps = 64, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, steps, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res["peer"][0], "CUDA IPC peer buffer could not be established"
+    assert np.array_equal(res["nccl"][1], res["peer"][1])
+    from miniworld_b200.batched import BatchedMiniWorld
+    env = BatchedMiniWorld("MiniWorld-FourRooms-v0", total)
+    env.reset(seed=1000)
+    acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)
+    for t in range(steps):
+        obs = env.step(torch.as_tensor(acts_all[t], device="cuda"))[0]
+        assert np.array_equal(obs.cpu().numpy(), res["peer"][1][t])
+    env.close()
