@@ -11,6 +11,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef __CUDACC__
+struct uint2 { unsigned int x, y; };
+#endif
+
 #ifdef __CUDACC__
 #define MWB_DEV __device__ __forceinline__
 #define MWB_DEVM __device__ __forceinline__

@@ -119,6 +119,7 @@ struct mwb_handle {
 #endif
   std::vector<int> mesh_counts;   // triangles per uploaded mesh (host copy)
   void* mesh_tris_buf;
+  void* mesh_bbox_buf;
   // asset storage
   void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops, *maze, *maze_cdf;
 };
@@ -390,6 +391,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
   h->protos = h->ops = h->maze = h->maze_cdf = nullptr;
   h->mesh_tris_buf = nullptr;
+  h->mesh_bbox_buf = nullptr;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
 #ifndef MWB_HOSTSIM
@@ -493,7 +495,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
 #endif
   for (void* p : h->allocs) dev_free(p);
   void* extra[] = {h->tex_desc, h->texels, h->mesh_desc, h->mesh_pos, h->mesh_nrm, h->mesh_uv, h->mesh_rgb,
-                   h->protos, h->ops, h->mesh_tris_buf, h->maze, h->maze_cdf};
+                   h->protos, h->ops, h->mesh_tris_buf, h->mesh_bbox_buf, h->maze, h->maze_cdf};
   for (void* p : extra)
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
@@ -655,9 +657,15 @@ extern "C" int mwb_set_protos(mwb_handle* h, const mwb_proto* protos, int n) {
   if (cap > h->S.mesh_cap) {
     if (h->mesh_tris_buf) dev_free(h->mesh_tris_buf);
     h->mesh_tris_buf = nullptr;
+  h->mesh_bbox_buf = nullptr;
     const size_t bytes = (size_t)h->S.N * h->S.E * cap * sizeof(TriRec);
     if (dev_alloc(&h->mesh_tris_buf, bytes) != 0) return fail(MWB_ECUDA, "mesh triangle buffer allocation failed");
     h->S.mesh_tris = (TriRec*)h->mesh_tris_buf;
+    if (h->mesh_bbox_buf) dev_free(h->mesh_bbox_buf);
+    h->mesh_bbox_buf = nullptr;
+    if (dev_alloc(&h->mesh_bbox_buf, (size_t)h->S.N * h->S.E * cap * sizeof(uint2)) != 0)
+      return fail(MWB_ECUDA, "mesh bbox buffer allocation failed");
+    h->S.mesh_bbox = (uint2*)h->mesh_bbox_buf;
     h->S.mesh_cap = cap;
   }
   return MWB_OK;

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
   const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
   const int ntris = A.meshes[pr.mesh_id].count;
   TriRec* out = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
+  uint2* out_bbox = S.mesh_bbox + ((size_t)i * S.E + e) * S.mesh_cap;
   int total = 0;
   int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
   for (int start = 0; start < ntris; start += 256) {
@@ -108,7 +109,10 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
     }
     if (keep) {
       const int pos = total + woff + incl - 1;
-      if (pos < S.mesh_cap) out[pos] = rec;
+      if (pos < S.mesh_cap) {
+        out[pos] = rec;
+        out_bbox[pos] = make_uint2((unsigned)rec.bx, (unsigned)rec.by);
+      }
       x0 = min(x0, rec.bx & 0xFFFF); x1 = max(x1, rec.bx >> 16);
       y0 = min(y0, rec.by & 0xFFFF); y1 = max(y1, rec.by >> 16);
     }
@@ -210,6 +214,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
       Segment& sg = segs[k];
       if (k == 0 || fmap.ent_kind[k - 1] == MWB_KIND_BOX) {
         sg.tris = tris + smem_pos;
+        sg.bbox = nullptr;
         sg.count = seg_count[k];
         smem_pos += sg.count;
         sg.bx = (W - 1) << 16;
@@ -218,6 +223,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
         const int e = fmap.ent_slot[k - 1];
         const MeshSegInfo mi = S.mesh_seg[(size_t)i * S.E + e];
         sg.tris = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
+        sg.bbox = S.mesh_bbox + ((size_t)i * S.E + e) * S.mesh_cap;
         sg.count = mi.count;
         sg.bx = mi.bx;
         sg.by = mi.by;
@@ -288,20 +294,24 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
         int idx = -1;
         if (j < sg.count) {
           idx = ord ? (int)ord[j] : j;
-          const TriRec& t = sg.tris[idx];
-          const int bx0 = t.bx & 0xFFFF, bx1 = t.bx >> 16, by0 = t.by & 0xFFFF, by1 = t.by >> 16;
-          bool hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0;
+          bool hit;
+          if (sg.bbox != nullptr) {          // mesh list: coalesced bbox test first, record only if it passes
+            const uint2 bb = sg.bbox[idx];
+            const int bx0 = bb.x & 0xFFFF, bx1 = bb.x >> 16, by0 = bb.y & 0xFFFF, by1 = bb.y >> 16;
+            hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0;
+          } else {
+            const TriRec& t = sg.tris[idx];
+            const int bx0 = t.bx & 0xFFFF, bx1 = t.bx >> 16, by0 = t.by & 0xFFFF, by1 = t.by >> 16;
+            hit = bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0;
+          }
           if (hit) {
+            const TriRec& t = sg.tris[idx];
+            const float fx0 = (float)tx0, fy0 = (float)ty0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {   // half-tile entirely outside one edge?
-              const float cx = t.A[k] > 0.0f ? (float)(tx0 + 8) : (float)tx0;
-              const float cy = t.B[k] > 0.0f ? (float)(ty0 + 4) : (float)ty0;
-              if (t.A[k] * cx + t.B[k] * cy + t.C[k] + t.R[k] < 0.0f) hit = false;
-            }
+            for (int k = 0; k < 3; ++k)   // half-tile entirely outside one edge?
+              if (t.A[k] * fx0 + t.B[k] * fy0 + t.K[k] < 0.0f) hit = false;
             // nearest depth the triangle can have inside the half-tile vs everything already stored
-            const float zx = t.Za > 0.0f ? (float)tx0 : (float)(tx0 + 8), zy = t.Zb > 0.0f ? (float)ty0 : (float)(ty0 + 4);
-            const float zmin = t.Za * zx + t.Zb * zy + t.Zc - t.Zr;
-            if (zmin * 65535.0f - 1.0f > tile_bound) hit = false;
+            if ((t.Za * fx0 + t.Zb * fy0 + t.Kz) * 65535.0f - 1.0f > tile_bound) hit = false;
           }
           if (!hit) idx = -1;
         }

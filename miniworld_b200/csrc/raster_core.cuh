@@ -179,7 +179,8 @@ struct MWB_ALIGN16 TriRec {
   float u[3], v[3];              // texcoords per vertex
   float r[3], g[3], b[3];        // lit colour per vertex
   float UA, UB, VA, VB, SA, SB;  // sum_k u_k A_k, sum_k u_k B_k, ... : per-triangle parts of du/dx, dv/dx, ...
-  float pad[3];
+  float K[3];                    // half-tile rejection: max of E_k over an 8x4 block at (x0, y0) is A x0 + B y0 + K
+  float Kz;                      // likewise min of z - Zr: Za x0 + Zb y0 + Kz
 };
 
 // the hot 76 bytes of a TriRec, held in registers while a tile is rasterised
@@ -245,13 +246,14 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   t.Zc = f_div(f_add(f_add(f_mul(v0.zeta, t.C[0]), f_mul(v1.zeta, t.C[1])), f_mul(v2.zeta, t.C[2])), det);
   // |z(sample) - z(centre)| <= 0.4375 (|Za| + |Zb|); plus a bound on evaluation rounding
   t.Zr = 0.4375f * (fabsf(t.Za) + fabsf(t.Zb)) + 4e-6f * (fabsf(t.Za) * (float)W + fabsf(t.Zb) * (float)H + fabsf(t.Zc)) + 1e-6f;
-  t.pad[0] = t.pad[1] = t.pad[2] = 0.0f;
+  t.Kz = t.Zc - t.Zr + 8.0f * fminf(t.Za, 0.0f) + 4.0f * fminf(t.Zb, 0.0f);
   for (int k = 0; k < 3; ++k) {
     float aa = fabsf(t.A[k]), ab = fabsf(t.B[k]);
     // |E(sample) - E(centre)| <= 0.4375 (|A| + |B|); plus a bound on evaluation rounding
     t.R[k] = 0.4375f * (aa + ab) + 4e-6f * (aa * (float)W + ab * (float)H + fabsf(t.C[k])) + 1e-30f;
     // tie rule: the edge with A > 0, or A == 0 and B > 0, owns samples with E == 0
     t.T[k] = (t.A[k] > 0.0f || (t.A[k] == 0.0f && t.B[k] > 0.0f)) ? 0.0f : 1.401298464e-45f;
+    t.K[k] = t.C[k] + t.R[k] + 8.0f * fmaxf(t.A[k], 0.0f) + 4.0f * fmaxf(t.B[k], 0.0f);
   }
   const VertAttr& b0 = a0;
   const VertAttr& b1 = a2;
@@ -746,6 +748,7 @@ MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camer
 // one triangle list of a frame
 struct Segment {
   const TriRec* tris;
+  const uint2* bbox;                 // mesh lists: packed bboxes (coalesced pre-test); null for shared-memory lists
   int base, count;                   // slots [base, base + count)
   int bx, by;                        // bbox lo | hi << 16 (pixels)
 };

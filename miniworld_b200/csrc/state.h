@@ -59,6 +59,7 @@ struct DevState {
   // ---- per-frame mesh triangle lists written by mesh_setup_kernel: [N][E][mesh_cap] ----
   TriRec* mesh_tris;
   MeshSegInfo* mesh_seg;        // [N][E]
+  uint2* mesh_bbox;             // [N][E][mesh_cap] packed (bx, by) of each listed triangle, coalesced for the tile scan
   int32_t mesh_cap;             // 0 = the level has no mesh entities
   TriRec* room_tris;            // [N][tri_cap] room + box triangle lists in HBM for levels whose lists do
                                 //   not fit shared memory (Maze); null = lists live in shared memory

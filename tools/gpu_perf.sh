@@ -12,4 +12,3 @@ print("value=%.0f e2e=%.0f k2_ms=%.3f k1_ms=%.3f cpu=%s frac=%.4f" % (d["value"]
 PY
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 4 -c 1 -f -o gpurun_out/prof_k2 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?"
 timeout 600 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; echo "configs rc=$?"; cat gpurun_out/configs.jsonl | cut -c1-400; tail -3 gpurun_out/configs.err
-for mb in 4; do MWB_K2_MINBLOCKS=$mb timeout 300 python bench.py --steps 60 --warmup 10 --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('minblocks=$mb value=%.0f k2_ms=%.3f'%(d['value'],d['roofline']['kernel_avg_ms']))"; done
