@@ -328,12 +328,13 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* 
           const int j = order[jj];
           const TriRec& t = tris[j];
           if ((t.bx & 0xFFFF) > px || (t.bx >> 16) < px || (t.by & 0xFFFF) > py || (t.by >> 16) < py) continue;
-          if (!classify_pixel<MSAA>(load_class(&t), j, px, py, P)) continue;
+          if (classify_pixel<MSAA>(load_class(&t), j, px, py, P) == 0) continue;
           if (P.mode == MWB_PX_LAZY) {     // materialise the lazily held triangle first
             raster_pixel<MSAA>(load_hot(&tris[P.lazy_slot]), P.lazy_slot, px, py, P.keys, P.kmax);
           }
           P.mode = MWB_PX_EXPLICIT;
           raster_pixel<MSAA>(load_hot(&t), j, px, py, P.keys, P.kmax);
+          P.bound = (float)(P.kmax >> 16);
         }
         uint32_t code0;
         if (P.mode == MWB_PX_LAZY) {

@@ -28,6 +28,7 @@
 #define MWB_RENDER_THREADS 320
 #define MWB_RENDER_WARPS (MWB_RENDER_THREADS / 32)
 #define MWB_MAX_SEGS (1 + MWB_MAX_DRAWN)
+#define MWB_EQ_CAP 96                // exact-phase queue entries per warp
 #define MWB_SORT_LIMIT 512            // room triangle lists up to this length are depth-sorted
 #define MWB_STAGE_QUAD_BYTES 16384   // static quads up to this size are staged in shared memory
 
@@ -148,6 +149,8 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   __shared__ __align__(8) uint8_t stage[MWB_RENDER_WARPS][4][24];
   __shared__ __align__(8) uint64_t quad_bar;
   __shared__ int chunk_idx[MWB_RENDER_WARPS][32];   // triangle tested by each lane in the current chunk
+  __shared__ uint32_t eq_keys[MWB_RENDER_WARPS][MSAA][32];       // per-sample keys of explicit pixels
+  __shared__ uint32_t eq_items[MWB_RENDER_WARPS][MWB_EQ_CAP];    // queued (pixel, triangle) exact items
 
   const int i = env0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -265,6 +268,18 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   const int tiles_x = (W + 7) >> 3;
   const int lx = lane & 7, ly = lane >> 3;
   const SegLookup fetch{segs, nsegs};
+  // exact-phase work is done sample-parallel: lane -> (queued item lane / MSAA, sample lane % MSAA)
+  constexpr int IPR = 32 / MSAA;                 // items per round
+  const int my_s = lane % MSAA;
+  float my_sx = 0.0f, my_sy = 0.0f;
+#pragma unroll
+  for (int s = 0; s < MSAA; ++s)
+    if (s == my_s) {
+      my_sx = sample_x<MSAA>(s);
+      my_sy = sample_y<MSAA>(s);
+    }
+  uint32_t(*skeys)[32] = eq_keys[warp];          // [sample][pixel lane] depth16 << 16 | slot
+  uint32_t* equeue = eq_items[warp];
   // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x
   const int halves_y = (H + 3) >> 2;
   int hcol = warp % tiles_x, hrow = warp / tiles_x;
@@ -279,6 +294,36 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
     const int px = tx0 + lx, py = ty0 + ly;
     PixelState<MSAA> P;
     pixel_init(P);
+#pragma unroll
+    for (int s = 0; s < MSAA; ++s) skeys[s][lane] = MWB_SKY_KEY;
+    int qn = 0;                                  // queued exact items (warp-uniform)
+
+    // Exact processing of the queued (pixel, triangle) items, MSAA lanes per item: every lane
+    // evaluates one sample and folds it into the pixel's key with an integer atomicMin
+    // (order-independent, hence deterministic).  Then explicit pixels refresh their bound.
+    auto flush = [&]() {
+      __syncwarp();
+#pragma unroll 1
+      for (int r = 0; r < qn; r += IPR) {
+        const int qi = r + lane / MSAA;
+        if (qi < qn) {
+          const uint32_t it = equeue[qi];
+          const int slot = (int)(it & 0xFFFFu), pl = (int)((it >> 16) & 31u);
+          const HotTri t = load_hot(&fetch(slot));
+          const float xs = (float)(tx0 + (pl & 7)) + my_sx, ys = (float)(ty0 + (pl >> 3)) + my_sy;
+          const uint32_t key = sample_key(t, slot, xs, ys, (it >> 21) & 1u);
+          if (key != 0xFFFFFFFFu) atomicMin(&skeys[my_s][pl], key);
+        }
+      }
+      __syncwarp();
+      if (P.mode == MWB_PX_EXPLICIT) {
+        uint32_t km = skeys[0][lane];
+#pragma unroll
+        for (int s = 1; s < MSAA; ++s) km = max(km, skeys[s][lane]);
+        P.bound = (float)(km >> 16);
+      }
+      qn = 0;
+    };
 
 #pragma unroll 1
     for (int sgi = 0; sgi < nsegs; ++sgi) {
@@ -320,39 +365,49 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
         chunk_idx[warp][lane] = idx;
         __syncwarp();
         // phase 1 (warp-uniform): triage every surviving triangle at this lane's pixel
-        uint32_t mine = 0;
+        uint32_t mine = 0, mine_full = 0;
 #pragma unroll 1
         while (mask) {
           const int b = __ffs(mask) - 1;
           mask &= mask - 1;
           const int tb = chunk_idx[warp][b];
           const ClassTri ct = load_class(sg.tris + tb);
-          if (classify_pixel<MSAA>(ct, sg.base + tb, px, py, P)) mine |= 1u << b;
+          const int cls = classify_pixel<MSAA>(ct, sg.base + tb, px, py, P);
+          if (cls) mine |= 1u << b;
+          if (cls == 2) mine_full |= 1u << b;
         }
-        // phase 2 (per-lane lists): exact per-sample processing of what each pixel could not decide
+        // phase 2: queue what this pixel could not decide (first the lazily held triangle, which
+        // must now be materialised); the queue is drained sample-parallel by flush()
+        bool need_mat = mine != 0 && P.mode == MWB_PX_LAZY;
+        if (mine != 0 && P.mode != MWB_PX_EXPLICIT) {
+          P.bound = P.mode == MWB_PX_LAZY ? P.lazy_chi : 65535.0f;   // still an upper bound after materialisation
+          P.mode = MWB_PX_EXPLICIT;
+        }
 #pragma unroll 1
-        while (__any_sync(0xffffffffu, mine != 0)) {
-          if (mine) {
-            const TriRec* rec;
-            int slot;
-            if (P.mode == MWB_PX_LAZY) {           // first materialise the lazily held triangle
-              slot = P.lazy_slot;
-              rec = &fetch(slot);
-              P.mode = MWB_PX_EXPLICIT;
+        for (;;) {
+          const bool has = need_mat || mine != 0;
+          const uint32_t bal = __ballot_sync(0xffffffffu, has);
+          if (!bal) break;
+          const int cnt = __popc(bal);
+          if (qn + cnt > MWB_EQ_CAP) flush();
+          if (has) {
+            const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+            uint32_t item;
+            if (need_mat) {
+              item = (1u << 21) | ((uint32_t)lane << 16) | (uint32_t)P.lazy_slot;
+              need_mat = false;
             } else {
               const int b = __ffs(mine) - 1;
               mine &= mine - 1;
-              const int tb = chunk_idx[warp][b];
-              slot = sg.base + tb;
-              rec = sg.tris + tb;
-              P.mode = MWB_PX_EXPLICIT;
+              item = (((mine_full >> b) & 1u) << 21) | ((uint32_t)lane << 16) | (uint32_t)(sg.base + chunk_idx[warp][b]);
             }
-            const HotTri t = load_hot(rec);
-            raster_pixel<MSAA>(t, slot, px, py, P.keys, P.kmax);
+            equeue[pos] = item;
           }
+          qn += cnt;
         }
       }
     }
+    if (qn) flush();
 
     // Lazy pixels join the common resolve path as "all samples see lazy_slot", so that the
     // (expensive) shading code runs once for the whole warp instead of once per mode.
@@ -363,6 +418,8 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
 #pragma unroll
       for (int s = 0; s < MSAA; ++s) P.keys[s] = (uint32_t)P.lazy_slot;
     } else {
+#pragma unroll
+      for (int s = 0; s < MSAA; ++s) P.keys[s] = skeys[s][lane];
       code0 = P.keys[0] >> 16;
     }
     resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);

@@ -374,6 +374,7 @@ struct PixelState {
   int32_t mode;
   int32_t lazy_slot;
   float lazy_clo, lazy_chi;      // conservative bounds of the lazy triangle's depth codes here
+  float bound;                   // EXPLICIT mode: an upper bound of every stored depth code
 };
 
 template <int MSAA>
@@ -384,12 +385,13 @@ MWB_DEV void pixel_init(PixelState<MSAA>& p) {
   p.mode = MWB_PX_EMPTY;
   p.lazy_slot = -1;
   p.lazy_clo = p.lazy_chi = 65535.0f;
+  p.bound = 65535.0f;
 }
 
 // largest depth code that can currently be stored at any sample of the pixel
 template <int MSAA>
 MWB_DEV float pixel_bound(const PixelState<MSAA>& p) {
-  return p.mode == MWB_PX_LAZY ? p.lazy_chi : (float)(p.kmax >> 16);
+  return p.mode == MWB_PX_LAZY ? p.lazy_chi : p.bound;
 }
 
 // the 16 floats classification needs (A, B, C, R, Z plane), broadcast to the whole warp
@@ -414,22 +416,23 @@ MWB_DEV ClassTri load_class(const TriRec* t) {
   return h;
 }
 
-// Cheap per-pixel triage of one triangle.  Returns true if the triangle still needs exact
-// per-sample processing at this pixel (raster_pixel); false if it was skipped or installed lazily.
+// Cheap per-pixel triage of one triangle.  Returns 0 if it was skipped or installed lazily; else it
+// still needs exact per-sample processing at this pixel: 1 = partial coverage possible, 2 = it
+// certainly covers every sample (edge tests can be skipped).
 template <int MSAA>
-MWB_DEV bool classify_pixel(const ClassTri& t, int slot, int px, int py, PixelState<MSAA>& p) {
+MWB_DEV int classify_pixel(const ClassTri& t, int slot, int px, int py, PixelState<MSAA>& p) {
   MWB_COUNT(0);
   const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
   const float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
   const float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
   const float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
-  if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) { MWB_COUNT(1); return false; }   // certainly outside
+  if (e0 + t.R[0] < 0.0f || e1 + t.R[1] < 0.0f || e2 + t.R[2] < 0.0f) { MWB_COUNT(1); return 0; }   // certainly outside
   const float zc = t.Za * cx + t.Zb * cy + t.Zc;
   const float zlo = zc - t.Zr, zhi = zc + t.Zr;
-  if (zlo > 1.0f || zhi < 0.0f) { MWB_COUNT(2); return false; }                       // certainly clipped away
+  if (zlo > 1.0f || zhi < 0.0f) { MWB_COUNT(2); return 0; }                           // certainly clipped away
   // depth codes any sample of this pixel can get lie in [clo, chi] (one code of slack each way)
   const float clo = zlo * 65535.0f - 1.0f, chi = zhi * 65535.0f + 1.5f;
-  if (clo > pixel_bound(p)) { MWB_COUNT(3); return false; }                           // certainly occluded
+  if (clo > pixel_bound(p)) { MWB_COUNT(3); return 0; }                               // certainly occluded
   const bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;   // covers every sample
   const bool unclipped = zlo >= 0.0f && zhi <= 1.0f && chi < 65535.0f;
   if (full && unclipped) {
@@ -440,10 +443,24 @@ MWB_DEV bool classify_pixel(const ClassTri& t, int slot, int px, int py, PixelSt
       p.lazy_clo = clo;
       p.lazy_chi = chi;
       MWB_COUNT(5);
-      return false;
+      return 0;
     }
   }
-  return true;
+  return full ? 2 : 1;
+}
+
+// One sample of the exact path: coverage by the three edge functions (unless the triangle is
+// known to cover the whole pixel), window z, 16-bit depth code.  Returns the packed key, or
+// 0xFFFFFFFF if the sample is not covered / clipped.
+MWB_DEV uint32_t sample_key(const HotTri& t, int slot, float xs, float ys, bool full) {
+  bool in = true;
+  if (!full)
+    in = edge_value(t.A[0], t.B[0], t.C[0], xs, ys) >= t.T[0] && edge_value(t.A[1], t.B[1], t.C[1], xs, ys) >= t.T[1] &&
+         edge_value(t.A[2], t.B[2], t.C[2], xs, ys) >= t.T[2];
+  const float z = f_add(f_add(f_mul(t.Za, xs), f_mul(t.Zb, ys)), t.Zc);
+  in = in && z >= 0.0f && z <= 1.0f;
+  const uint32_t code = (uint32_t)f_add(f_mul(z, 65535.0f), 0.5f);
+  return in ? ((code << 16) | (uint32_t)slot) : 0xFFFFFFFFu;
 }
 
 // GL_REPEAT + GL_LINEAR on one mip level.  The texcoord is reduced to [0, 1) first (exact in
