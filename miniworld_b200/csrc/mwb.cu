@@ -110,6 +110,7 @@ struct mwb_handle {
   bool profiling;
   bool frames_copied;
   int k2_minblocks;
+  int k2_parts;                   // blocks per env frame (1 at 80x60, 4 at 160x120)
 #ifndef MWB_HOSTSIM
   cudaStream_t copy_stream;
   cudaEvent_t chunk_done[4], copies_done;
@@ -454,11 +455,16 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   dev_memset(S.carrying, 0xFF, N * sizeof(int32_t));
   // every room quad and box face can yield two set-up triangles.  Up to 512 of them live in
   // shared memory; larger levels (Maze) keep the per-env lists in HBM instead.
+  {
+    const int halves = ((cfg->obs_width + 7) / 8) * ((cfg->obs_height + 3) / 4);
+    h->k2_parts = (halves + 149) / 150;
+    if (h->k2_parts < 1) h->k2_parts = 1;
+  }
   h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);
   h->smem_tris = h->tri_cap <= 512;
   if (!h->smem_tris) {
     TriRec* buf = nullptr;
-    if (alloc_arr(h, &buf, (size_t)N * h->tri_cap)) {
+    if (alloc_arr(h, &buf, (size_t)N * h->k2_parts * h->tri_cap)) {
       mwb_destroy(h);
       return fail(MWB_ECUDA, "triangle list allocation failed");
     }
@@ -949,7 +955,7 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
   prof_mark(h, h->ev_k2, s);
-#define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<count, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, env0, h->tri_cap, h->stage_bytes, h->d_overflow)
+#define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<count * h->k2_parts, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, h->d_overflow)
   if (h->k2_minblocks == 2) {
     switch (h->S.msaa) {
       case 1: MWB_LAUNCH_K2(1, 2); break;

@@ -135,12 +135,15 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
 // ---- K2 --------------------------------------------------------------------------------
 template <int MSAA, int MINB>
 __global__ void __launch_bounds__(MWB_RENDER_THREADS, MINB)
-render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0, int tri_cap,
-              int stage_bytes, int* __restrict__ overflow) {
+render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0, int parts,
+              int tri_cap, int stage_bytes, int* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // large frames are cut into `parts` blocks per env (each redoes the cheap geometry phase and
+  // rasterises its share of the half-tiles), which evens out the load when few envs are resident
+  const int i = env0 + (int)blockIdx.x / parts, part = (int)blockIdx.x % parts;
   // set-up triangles of rooms + boxes: shared memory, or this env's HBM block for big levels
   const size_t tri_bytes = S.room_tris ? 0 : (size_t)tri_cap * sizeof(TriRec);
-  TriRec* tris = S.room_tris ? S.room_tris + (size_t)(env0 + blockIdx.x) * tri_cap : reinterpret_cast<TriRec*>(smem_raw);
+  TriRec* tris = S.room_tris ? S.room_tris + ((size_t)i * parts + part) * tri_cap : reinterpret_cast<TriRec*>(smem_raw);
   __shared__ Camera cam;
   __shared__ FrameMap fmap;
   __shared__ Segment segs[MWB_MAX_SEGS];
@@ -152,7 +155,6 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   __shared__ uint32_t eq_keys[MWB_RENDER_WARPS][MSAA][32];       // per-sample keys of explicit pixels
   __shared__ uint32_t eq_items[MWB_RENDER_WARPS][MWB_EQ_CAP];    // queued (pixel, triangle) exact items
 
-  const int i = env0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = S.obs_w, H = S.obs_h;
 
@@ -282,9 +284,11 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   uint32_t* equeue = eq_items[warp];
   // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x
   const int halves_y = (H + 3) >> 2;
-  int hcol = warp % tiles_x, hrow = warp / tiles_x;
+  const int n_halves = tiles_x * halves_y, per_part = (n_halves + parts - 1) / parts;
+  const int h_begin = part * per_part, h_end = min(n_halves, h_begin + per_part);
+  int hcol = (h_begin + warp) % tiles_x, hrow = (h_begin + warp) / tiles_x;
 #pragma unroll 1
-  for (int half = warp; half < tiles_x * halves_y; half += MWB_RENDER_WARPS) {
+  for (int half = h_begin + warp; half < h_end; half += MWB_RENDER_WARPS) {
     const int tx0 = hcol << 3, ty0 = hrow << 2;
     hcol += MWB_RENDER_WARPS;
     while (hcol >= tiles_x) {

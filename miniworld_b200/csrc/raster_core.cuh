@@ -774,7 +774,8 @@ struct SegLookup {                   // slot -> record
   const Segment* seg;
   int n;
   MWB_DEVM const TriRec& operator()(uint32_t slot) const {
-    int k = 0;
+    if ((int)slot < seg[0].count) return seg[0].tris[slot];   // room triangles: slot == position (the common case)
+    int k = 1;
     while (k + 1 < n && (int)slot >= seg[k + 1].base) ++k;
     return seg[k].tris[(int)slot - seg[k].base];
   }
