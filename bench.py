@@ -263,6 +263,14 @@ def run_ours(args):
             v, n = cpu_port_throughput(1, 1.0, 12.0)
             cpu = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                    "sample": "%d env-steps of 1 env in 12 s (oracle/physics_port.py + oracle/softgl.c)" % n}
+        traffic = None
+        try:   # DRAM bytes of one K2 launch from the committed ncu --set full capture (profiles/)
+            with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
+                tj = json.load(f)
+            if N == N_ENVS:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -275,7 +283,7 @@ def run_ours(args):
                        "l2": "per-step outputs %.1f MB > 126 MB L2; no explicit flush" % (bytes_per_launch / 1e6),
                        "episodes_finished_in_timed_region": done_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if achieved else None, "traffic": None,
+                         "frac": achieved / peak if achieved else None, "traffic": traffic,
                          "kernel": "render_kernel<8>", "kernel_avg_ms": k2_avg_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "k1_avg_ms": k1_ms / max(1, n1), "kernel_share_of_step": k2_ms / ms if ms else None},

@@ -105,8 +105,6 @@ class StateView(C.Structure):
         "cam", "env_params", "rng", "room_tex", "num_picked_up", "episodes_done")]
 
 
-_EXPECTED_SIZES = None
-
 
 def _expected_sizes():
     return [C.sizeof(Config), C.sizeof(Params), C.sizeof(TexDesc), C.sizeof(MeshDesc),

@@ -73,9 +73,6 @@ def _fan(n):
     return [(0, k, k + 1) for k in range(1, n - 1)]
 
 
-_BOX_FACES = None
-
-
 def _box_faces(sx, sy, sz):
     """drawBox(x_min=-sx/2, x_max=+sx/2, y_min=0, y_max=sy, ...) vertex order (opengl.py:460-503)."""
     x0, x1, y0, y1, z0, z1 = f32(-sx / 2), f32(sx / 2), f32(0), f32(sy), f32(-sz / 2), f32(sz / 2)
