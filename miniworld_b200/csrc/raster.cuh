@@ -273,13 +273,8 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   // exact-phase work is done sample-parallel: lane -> (queued item lane / MSAA, sample lane % MSAA)
   constexpr int IPR = 32 / MSAA;                 // items per round
   const int my_s = lane % MSAA;
-  float my_sx = 0.0f, my_sy = 0.0f;
-#pragma unroll
-  for (int s = 0; s < MSAA; ++s)
-    if (s == my_s) {
-      my_sx = sample_x<MSAA>(s);
-      my_sy = sample_y<MSAA>(s);
-    }
+  float my_sx, my_sy;
+  sample_xy_dyn<MSAA>(my_s, my_sx, my_sy);
   uint32_t(*skeys)[32] = eq_keys[warp];          // [sample][pixel lane] depth16 << 16 | slot
   uint32_t* equeue = eq_items[warp];
   // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x

@@ -72,6 +72,15 @@ MWB_DEV float sample_y(int s) {
        : s == 4 ? 0.8125f : s == 5 ? 0.4375f : s == 6 ? 0.9375f : 0.0625f;
 }
 
+// the same offsets for a run-time sample index: sixteenths packed four bits per sample
+template <int MSAA>
+MWB_DEV void sample_xy_dyn(int s, float& x, float& y) {
+  const uint32_t XN = MSAA == 8 ? 0xfb135d79u : (MSAA == 4 ? 0xa2e6u : 0x8u);
+  const uint32_t YN = MSAA == 8 ? 0x1f7d39b5u : (MSAA == 4 ? 0xea62u : 0x8u);
+  x = (float)((XN >> (4 * s)) & 15u) * 0.0625f;
+  y = (float)((YN >> (4 * s)) & 15u) * 0.0625f;
+}
+
 struct Camera {
   float ex, ey, ez;              // eye
   float sx, sy, sz;              // right   (gluLookAt's s)
