@@ -69,13 +69,13 @@ struct CarryPos {
 };
 
 // _get_carry_pos(agent_pos, ent): agent_pos + dir_vec * 1.05 * dist, lifted to stay visible
-MWB_DEV CarryPos carry_pos(const DevState& S, int i, double apx, double apz, double c, double s, int slot) {
+MWB_DEV CarryPos carry_pos(const DevState& S, int i, double apx, double apz, double c, double s, int slot, double ar) {
   const mwb_proto& pr = S.protos[S.ent_proto[(size_t)slot * S.N + i]];
-  double dist;
+  double dist;   // agent.radius + ent.radius + max_forward_step, float32 as soon as ent.radius is
   if (pr.radius_is_f32)
-    dist = (double)f_add(f_add(0.4f, (float)pr.radius), (float)S.params.max_forward_step);
+    dist = (double)f_add(f_add((float)ar, (float)pr.radius), (float)S.params.max_forward_step);
   else
-    dist = d_add(d_add(0.4, pr.radius), S.params.max_forward_step);
+    dist = d_add(d_add(ar, pr.radius), S.params.max_forward_step);
   CarryPos o;
   o.x = d_add(apx, d_mul(d_mul(c, 1.05), dist));
   o.z = d_add(apz, d_mul(d_mul(-s, 1.05), dist));
@@ -96,6 +96,7 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
   const size_t N = S.N;
   const int as = S.agent_slot[i];
   double px = S.ent_px[as * N + i], pz = S.ent_pz[as * N + i], dir = S.ent_dir[as * N + i];
+  const double ar = S.protos[S.ent_proto[as * N + i]].radius;   // Agent.radius (0.4 unless the level changes it)
   int carrying = S.carrying[i];
   int sc = S.step_count[i] + 1;
   S.step_count[i] = sc;
@@ -106,9 +107,9 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
     double c = mwb_libm::cos_glibc(dir), s = mwb_libm::sin_glibc(dir);
     double nx = d_add(d_add(px, d_mul(c, fwd)), d_mul(s, fwd_drift));
     double nz = d_add(d_add(pz, d_mul(-s, fwd)), d_mul(c, fwd_drift));
-    bool ok = world_intersect(S, i, as, nx, nz, 0.4, false) == MWB_HIT_NONE;
+    bool ok = world_intersect(S, i, as, nx, nz, ar, false) == MWB_HIT_NONE;
     if (ok && carrying >= 0) {
-      CarryPos cp = carry_pos(S, i, nx, nz, c, s, carrying);
+      CarryPos cp = carry_pos(S, i, nx, nz, c, s, carrying, ar);
       const mwb_proto& pr = S.protos[S.ent_proto[carrying * N + i]];
       ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.radius_is_f32 != 0) == MWB_HIT_NONE;
       if (ok) {
@@ -129,7 +130,7 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
     bool ok = true;
     if (carrying >= 0) {
       double c = mwb_libm::cos_glibc(ndir), s = mwb_libm::sin_glibc(ndir);
-      CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying);
+      CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying, ar);
       const mwb_proto& pr = S.protos[S.ent_proto[carrying * N + i]];
       // the agent's dir is already updated when the reference tests this; intersect() does not read it
       ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.radius_is_f32 != 0) == MWB_HIT_NONE;
@@ -146,9 +147,9 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
     }
   } else if (action == 4) {   // pickup
     double c = mwb_libm::cos_glibc(dir), s = mwb_libm::sin_glibc(dir);
-    double tx = d_add(px, d_mul(d_mul(c, 1.5), 0.4));
-    double tz = d_add(pz, d_mul(d_mul(-s, 1.5), 0.4));
-    int hit = world_intersect(S, i, as, tx, tz, d_mul(1.2, 0.4), false);
+    double tx = d_add(px, d_mul(d_mul(c, 1.5), ar));
+    double tz = d_add(pz, d_mul(d_mul(-s, 1.5), ar));
+    int hit = world_intersect(S, i, as, tx, tz, d_mul(1.2, ar), false);
     if (carrying < 0 && hit >= 0 && !S.protos[S.ent_proto[hit * N + i]].is_static) carrying = hit;
   } else if (action == 5) {   // drop
     if (carrying >= 0) {
@@ -159,7 +160,7 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
 
   if (carrying >= 0) {   // carried object follows the agent
     double c = mwb_libm::cos_glibc(dir), s = mwb_libm::sin_glibc(dir);
-    CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying);
+    CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying, ar);
     S.ent_px[carrying * N + i] = cp.x;
     S.ent_py[carrying * N + i] = cp.y;
     S.ent_pz[carrying * N + i] = cp.z;
@@ -181,7 +182,7 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
       double dz = d_sub(S.ent_pz[b * N + i], pz);
       double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
       const mwb_proto& pr = S.protos[bp];
-      double thr = d_add(sum_radii(pr.radius, pr.radius_is_f32 != 0, 0.4, false), S.near_extra);
+      double thr = d_add(sum_radii(pr.radius, pr.radius_is_f32 != 0, ar, false), S.near_extra);
       if (d < thr) {
         o.reward = d_add(o.reward, d_sub(1.0, d_mul(0.2, d_div((double)sc, (double)S.max_episode_steps))));
         o.terminated = 1;

@@ -167,14 +167,20 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + tri_bytes);
   uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + tri_bytes + stage_bytes);
   float* zkey = reinterpret_cast<float*>(order + ((tri_cap + 1) & ~1));
+  __shared__ double trig[6];
   if (tid == 0) mbar_init(&quad_bar, 1);
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
-  if (tid == 0) {
-    if (staged) tma_bulk_g2s(squads, gquads, quad_bytes, &quad_bar);
-    cam = make_camera(S, i);
-    fmap = build_frame_map(S, i);
+  if (tid == 0 && staged) tma_bulk_g2s(squads, gquads, quad_bytes, &quad_bar);
+  if (tid < 6) {                       // six independent glibc-exact sin / cos evaluations, one per thread
+    double ang[3];
+    camera_angles(S, i, ang);
+    trig[tid] = (tid & 1) ? mwb_libm::sin_glibc(ang[tid >> 1]) : mwb_libm::cos_glibc(ang[tid >> 1]);
+  } else if (tid == 32) {
+    fmap = build_frame_map(S, i);      // meanwhile another warp lays out the frame's draw list
   }
+  __syncthreads();
+  if (tid == 0) cam = make_camera(S, i, trig);
   __syncthreads();
   if (staged) mbar_wait(&quad_bar, 0);
   const mwb_quad* quads = staged ? squads : gquads;

@@ -92,17 +92,25 @@ struct Camera {
   float light[3], lamb[3], ldif[3], sky[3];
 };
 
-// Camera of env i.  Angles go through the glibc-exact sin / cos so that the oracle, fed the
-// same (pos, dir, cam_*) doubles on the host, derives the identical float32 basis.
-MWB_DEV Camera make_camera(const DevState& S, int i) {
+// The three camera angles of env i (heading, pitch, half the vertical field of view), float64.
+MWB_DEV void camera_angles(const DevState& S, int i, double ang[3]) {
+  const size_t N = S.N;
+  const int as = S.agent_slot[i];
+  ang[0] = S.ent_dir[as * N + i];
+  ang[1] = d_div(d_mul(S.cam[2 * N + i], 3.141592653589793), 180.0);
+  ang[2] = d_div(d_mul(S.cam[3 * N + i], 3.141592653589793), 360.0);
+}
+
+// Camera of env i from trig = {cos, sin} of those angles.  Angles go through the glibc-exact
+// sin / cos so that the oracle, fed the same (pos, dir, cam_*) doubles on the host, derives the
+// identical float32 basis.  (The six evaluations are independent: the kernel spreads them over
+// six threads.)
+MWB_DEV Camera make_camera(const DevState& S, int i, const double trig[6]) {
   const size_t N = S.N;
   const int as = S.agent_slot[i];
   double px = S.ent_px[as * N + i], py = S.ent_py[as * N + i], pz = S.ent_pz[as * N + i];
-  double dir = S.ent_dir[as * N + i];
-  double h = S.cam[0 * N + i], fd = S.cam[1 * N + i], pitch = S.cam[2 * N + i], fov = S.cam[3 * N + i];
-  double ct = mwb_libm::cos_glibc(dir), st = mwb_libm::sin_glibc(dir);
-  double phi = d_div(d_mul(pitch, 3.141592653589793), 180.0);
-  double cp = mwb_libm::cos_glibc(phi), sp = mwb_libm::sin_glibc(phi);
+  double h = S.cam[0 * N + i], fd = S.cam[1 * N + i];
+  const double ct = trig[0], st = trig[1], cp = trig[2], sp = trig[3];
   Camera c;
   c.ex = (float)d_add(px, d_mul(fd, ct));
   c.ey = (float)d_add(py, h);
@@ -116,8 +124,7 @@ MWB_DEV Camera make_camera(const DevState& S, int i) {
   c.fx = (float)d_mul(cp, ct);
   c.fy = (float)sp;
   c.fz = (float)(-d_mul(cp, st));
-  double half = d_div(d_mul(fov, 3.141592653589793), 360.0);
-  double cot = d_div(mwb_libm::cos_glibc(half), mwb_libm::sin_glibc(half));
+  double cot = d_div(trig[4], trig[5]);
   c.py = (float)cot;
   c.px = (float)d_div(cot, d_div((double)S.obs_w, (double)S.obs_h));
   c.za = (float)((MWB_FAR + MWB_NEAR) / (MWB_FAR - MWB_NEAR));
@@ -131,6 +138,16 @@ MWB_DEV Camera make_camera(const DevState& S, int i) {
     c.lamb[k] = (float)S.envp[(9 + k) * N + i];
   }
   return c;
+}
+
+MWB_DEV Camera make_camera(const DevState& S, int i) {
+  double ang[3], trig[6];
+  camera_angles(S, i, ang);
+  for (int k = 0; k < 3; ++k) {
+    trig[2 * k] = mwb_libm::cos_glibc(ang[k]);
+    trig[2 * k + 1] = mwb_libm::sin_glibc(ang[k]);
+  }
+  return make_camera(S, i, trig);
 }
 
 // vertex after the exact part of the pipeline: window-homogeneous position + z numerator

@@ -466,8 +466,9 @@ class SingleEnvEngine:
     """N = 1 engine behind `world.MiniWorldEnv`: the env's Python objects stay authoritative;
     before each GPU call the (possibly user-modified) state is pushed, afterwards pulled."""
 
-    def __init__(self, obs_width, obs_height, msaa_samples, device):
+    def __init__(self, obs_width, obs_height, msaa_samples, device, lib_path=None):
         self.args = (obs_width, obs_height, msaa_samples)
+        self.lib_path = lib_path
         self.device = 0 if device in ("cuda", None) else int(str(device).split(":")[-1])
         self.engine = None
         self.caps = None
@@ -483,16 +484,17 @@ class SingleEnvEngine:
         world = pack.pack_world(env)
         need = (max(8, len(world["rooms"])), max(64, len(world["quads"])), max(64, len(world["segs"])),
                 max(8, len(world["ents"])))
+        max_steps = int(min(env.max_episode_steps, 2 ** 31 - 1))     # math.inf -> never truncates
         if self.engine is None or any(n > c for n, c in zip(need, self.caps)) or \
-                self.engine.cfg.max_episode_steps != env.max_episode_steps:
+                self.engine.cfg.max_episode_steps != max_steps:
             if self.engine is not None:
                 self.engine.close()
             caps = tuple(int(2 ** np.ceil(np.log2(n))) for n in need)
             W, H, msaa = self.args
             self.engine = Engine(1, W, H, msaa, shared_geometry=False, max_rooms=caps[0], max_quads=caps[1],
                                  max_segs=caps[2], max_ents=min(caps[3], MAX_ENTS_CAP), rule=(RULE_NONE, 0),
-                                 domain_rand=False, max_episode_steps=env.max_episode_steps, autoreset=False,
-                                 device=self.device)
+                                 domain_rand=False, max_episode_steps=max_steps, autoreset=False,
+                                 device=self.device, lib_path=self.lib_path)
             self.caps = caps
             self.engine.set_params(env.params)
         self.engine.sync_assets()

@@ -1,7 +1,10 @@
 """Level definitions and id registration (reference miniworld/envs/__init__.py:44-157).
 
-Only the levels on BASELINE.json's configured path live here; `MiniWorld-MazeS8-v0` is the
-8x8 maze (the reference's `MiniWorld-Maze-v0` default) under the name BASELINE.json uses.
+The five levels of BASELINE.json's configs (Hallway, OneRoom, FourRooms, Maze, PickupObjects) run on
+the batched engine with device-side resets and lowered rules; the others listed here use entity
+kinds the engine already renders (Box, Ball, Key) and run through the single-environment class.
+`MiniWorld-MazeS8-v0` is the 8x8 maze (the reference's `MiniWorld-Maze-v0` default) under the name
+BASELINE.json uses.
 """
 from .._gym import gym
 from .fourrooms import FourRooms
@@ -9,6 +12,10 @@ from .hallway import Hallway
 from .maze import Maze, MazeS2, MazeS3, MazeS3Fast
 from .oneroom import OneRoom, OneRoomS6, OneRoomS6Fast
 from .pickupobjects import PickupObjects
+from .putnext import PutNext
+from .roomobjects import RoomObjects
+from .tmaze import TMaze, TMazeLeft, TMazeRight
+from .ymaze import YMaze, YMazeLeft, YMazeRight
 
 LEVELS = {
     "MiniWorld-Hallway-v0": Hallway,
@@ -22,6 +29,15 @@ LEVELS = {
     "MiniWorld-MazeS3-v0": MazeS3,
     "MiniWorld-MazeS3Fast-v0": MazeS3Fast,
     "MiniWorld-PickupObjects-v0": PickupObjects,
+    # levels outside BASELINE.json's configs: single-env GPU path (world.MiniWorldEnv), Python rule
+    "MiniWorld-PutNext-v0": PutNext,
+    "MiniWorld-RoomObjects-v0": RoomObjects,
+    "MiniWorld-TMaze-v0": TMaze,
+    "MiniWorld-TMazeLeft-v0": TMazeLeft,
+    "MiniWorld-TMazeRight-v0": TMazeRight,
+    "MiniWorld-YMaze-v0": YMaze,
+    "MiniWorld-YMazeLeft-v0": YMazeLeft,
+    "MiniWorld-YMazeRight-v0": YMazeRight,
 }
 
 for _id, _cls in LEVELS.items():

@@ -181,7 +181,7 @@ class MiniWorldEnv(gym.Env):
 
     def __init__(self, max_episode_steps=1500, obs_width=80, obs_height=60, window_width=800,
                  window_height=600, params=DEFAULT_PARAMS, domain_rand=False, render_mode=None,
-                 view="agent", device="cuda", msaa_samples=8):
+                 view="agent", device="cuda", msaa_samples=8, engine_lib=None):
         self.actions = MiniWorldEnv.Actions
         self.action_space = spaces.Discrete(len(self.actions))
         self.observation_space = spaces.Box(low=0, high=255, shape=(obs_height, obs_width, 3), dtype=np.uint8)
@@ -196,6 +196,7 @@ class MiniWorldEnv(gym.Env):
         self.window_width, self.window_height = window_width, window_height
         self.msaa_samples = msaa_samples
         self.device = device
+        self.engine_lib = engine_lib     # None: the in-tree libmwb.so
         self._engine = None
         self.reset()
 
@@ -375,7 +376,8 @@ class MiniWorldEnv(gym.Env):
                                "stepping and rendering need the CUDA engine")
         if self._engine is None:
             from .engine import SingleEnvEngine
-            self._engine = SingleEnvEngine(self.obs_width, self.obs_height, self.msaa_samples, self.device)
+            self._engine = SingleEnvEngine(self.obs_width, self.obs_height, self.msaa_samples, self.device,
+                                           lib_path=self.engine_lib)
         return self._engine
 
     def _push_world(self):

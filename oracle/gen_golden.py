@@ -35,6 +35,11 @@ CASES = [
     ("pickup_dr", "MiniWorld-PickupObjects-v0", {"domain_rand": True}, 16, 300),
     ("maze_dr", "MiniWorld-Maze-v0", {"domain_rand": True}, 8, 200),
     ("mazes3", "MiniWorld-MazeS3-v0", {}, 16, 300),
+    # levels outside BASELINE.json's configs (single-env path)
+    ("tmaze", "MiniWorld-TMaze-v0", {}, 8, 300),
+    ("ymaze_dr", "MiniWorld-YMaze-v0", {"domain_rand": True}, 8, 300),
+    ("roomobjs", "MiniWorld-RoomObjects-v0", {}, 8, 300),
+    ("putnext_dr", "MiniWorld-PutNext-v0", {"domain_rand": True}, 8, 300),
 ]
 
 

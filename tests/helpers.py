@@ -88,3 +88,40 @@ def run_trajectory(name, g, lib_path=None, steps=None, n=None, check_every=1):
             assert np.array_equal(out["reward"], g["reward"][t + 1, :N]), "reward at step %d" % (t + 1)
     env.close()
     return T, N
+
+
+SINGLE_CASES = {
+    # golden name: (level id, kwargs)
+    "tmaze": ("MiniWorld-TMaze-v0", {}),
+    "ymaze_dr": ("MiniWorld-YMaze-v0", {"domain_rand": True}),
+    "roomobjs": ("MiniWorld-RoomObjects-v0", {}),
+    "putnext_dr": ("MiniWorld-PutNext-v0", {"domain_rand": True}),
+    "fourrooms": ("MiniWorld-FourRooms-v0", {}),
+    "pickup": ("MiniWorld-PickupObjects-v0", {}),
+}
+
+
+def run_single_env_trajectory(name, g, lib_path=None, envs=2, steps=120, device="cuda"):
+    """world.MiniWorldEnv (N = 1 engine, host RNG, the level's Python step() rule) against the
+    reference trajectory: pose, reward, flags and every entity pose, every step."""
+    from miniworld_b200.envs import LEVELS
+    level, kw = SINGLE_CASES[name]
+    for i in range(envs):
+        env = LEVELS[level](engine_lib=lib_path, device=device, **kw)
+        env.reset(seed=1000 + i)
+        done = False
+        for t in range(min(steps, g["actions"].shape[0])):
+            if done:
+                env.reset()
+                r, te, tr = 0.0, False, False
+            else:
+                obs, r, te, tr, _ = env.step(int(g["actions"][t, i]))
+            done = te or tr
+            assert np.array_equal(env.agent.pos, g["pos"][t + 1, i]), (name, i, t)
+            assert env.agent.dir == g["dir"][t + 1, i], (name, i, t)
+            assert r == g["reward"][t + 1, i] and te == g["terminated"][t + 1, i] and tr == g["truncated"][t + 1, i], (name, i, t)
+            assert len(env.entities) == g["n_ents"][t + 1, i]
+            for e, ent in enumerate(env.entities):
+                assert np.array_equal(np.asarray(ent.pos, float), g["ent_pos"][t + 1, i, e]), (name, i, t, e)
+        assert obs.shape == (60, 80, 3) and 0 < obs.mean() < 255
+        env.close()

@@ -61,3 +61,11 @@ def test_device_maze_geometry_equals_host_world(hostsim_path, name, n):
 
 def test_device_maze_long_rollout_with_resets(hostsim_path):
     run_trajectory("mazes3", golden("mazes3"), hostsim_path, steps=300, n=8, check_every=25)
+
+
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "roomobjs", "putnext_dr", "pickup"])
+def test_single_env_levels_follow_reference(hostsim_path, name):
+    """Levels outside the batched configs (and PickupObjects for the carry path) through the
+    N = 1 engine with the level's own Python rule."""
+    from helpers import run_single_env_trajectory
+    run_single_env_trajectory(name, golden(name), hostsim_path, envs=2, steps=100)
