@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MWB_ABI_VERSION 4
+#define MWB_ABI_VERSION 5
 
 /* error codes */
 #define MWB_OK 0
@@ -112,7 +112,9 @@ typedef struct mwb_tex_desc {
   int64_t offset;            /* byte offset of this texture's level 0 in the texel blob          */
 } mwb_tex_desc;
 
-/* one triangle mesh (reference objmesh.py:36-216): per face-vertex arrays */
+/* one triangle mesh (reference objmesh.py:36-216): per face-vertex arrays; each triangle names
+ * the texture of its material chunk (map_Kd) or -1.  ImageFrame / TextFrame (entity.py:168-383)
+ * are lowered to small meshes of this form too. */
 typedef struct mwb_mesh_desc {
   int32_t num_tris;
   int32_t reserved;
@@ -242,7 +244,7 @@ const char* mwb_last_error(void);
 int mwb_upload_textures(mwb_handle* h, const mwb_tex_desc* descs, int n, const uint8_t* texels_rgb8);
 int mwb_upload_meshes(mwb_handle* h, const mwb_mesh_desc* descs, int n, const float* pos /*[T][3][3]*/,
                       const float* nrm /*[T][3][3]*/, const float* uv /*[T][3][2]*/,
-                      const float* rgb /*[T][3][3]*/);
+                      const float* rgb /*[T][3][3]*/, const int32_t* tri_tex /*[T] texture id or -1*/);
 
 /* ---- level definition ------------------------------------------------------------------ */
 int mwb_set_params(mwb_handle* h, const mwb_params* p);                    /* params.py:115-130  */

@@ -99,6 +99,18 @@ class Texture:
             return [cls._by_key[(name, idx)] for idx in range(n)]
 
     @classmethod
+    def from_array(cls, key, texels):
+        """Register a one-off texture (a mesh's map_Kd image) under a unique key."""
+        with _lock:
+            tex = cls._by_key.get((key, 0))
+            if tex is None:
+                tex = Texture(key, 0, texels)
+                tex.tex_id = len(cls.registry)
+                cls.registry.append(tex)
+                cls._by_key[(key, 0)] = tex
+            return tex
+
+    @classmethod
     def get_variant(cls, name, idx):
         fam = cls.family(name)
         if not 0 <= idx < len(fam):
@@ -218,7 +230,27 @@ class ObjMesh:
         self.colors = np.ascontiguousarray(data["colors"], np.float32)
         self.min_coords = np.asarray(data["min_coords"], np.float32)
         self.max_coords = np.asarray(data["max_coords"], np.float32)
+        tt = data.get("tri_tex")
+        self.tri_tex = np.full(self.verts.shape[0], -1, np.int32) if tt is None else np.ascontiguousarray(tt, np.int32)
         self.mesh_id = -1
+
+    @classmethod
+    def from_arrays(cls, key, verts, norms, texcs, colors, tri_tex):
+        """Synthetic mesh (ImageFrame / TextFrame quads), cached by `key`."""
+        with _lock:
+            mesh = cls.cache.get(key)
+            if mesh is None:
+                verts = np.asarray(verts, np.float32).reshape(-1, 3, 3)
+                data = dict(verts=verts, norms=np.asarray(norms, np.float32).reshape(-1, 3, 3),
+                            texcs=np.asarray(texcs, np.float32).reshape(-1, 3, 2),
+                            colors=np.asarray(colors, np.float32).reshape(-1, 3, 3),
+                            min_coords=verts.min(axis=0).min(axis=0), max_coords=verts.max(axis=0).max(axis=0),
+                            tri_tex=tri_tex)
+                mesh = ObjMesh(key, data)
+                mesh.mesh_id = len(cls.registry)
+                cls.registry.append(mesh)
+                cls.cache[key] = mesh
+            return mesh
 
     @property
     def num_tris(self):
@@ -236,6 +268,14 @@ class ObjMesh:
                 path = os.path.join(d, "meshes", mesh_name + ".obj")
                 if os.path.exists(path):
                     data = parse_obj(path)
+                    data["tri_tex"] = np.full(len(data["verts"]), -1, np.int32)
+                    for start, end, tex_path in data["chunks"]:
+                        if tex_path is not None:
+                            from PIL import Image
+                            with Image.open(tex_path) as im:
+                                texels = np.asarray(im.convert("RGB"))
+                            data["tri_tex"][start:end] = -2 - len(data.setdefault("_tex", []))
+                            data["_tex"].append((os.path.basename(tex_path), texels))
             if data is None:
                 pack = _load_pack()
                 pre = "mesh/%s/" % mesh_name
@@ -244,8 +284,25 @@ class ObjMesh:
                     gpre = "meshgeom/%s/" % geo
                     data = {k: pack[gpre + k] for k in ("verts", "norms", "texcs", "min_coords", "max_coords")}
                     data["colors"] = pack[pre + "colors"]
+                    if (gpre + "tri_tex") in pack.files:      # textured chunks: -2 - k refers to meshtex k
+                        data["tri_tex"] = pack[gpre + "tri_tex"].copy()
+                        data["_tex"] = []
+                        k = 0
+                        while ("meshtex/%s/%d" % (geo, k)) in pack.files:
+                            data["_tex"].append(("%s#%d" % (geo, k), pack["meshtex/%s/%d" % (geo, k)]))
+                            k += 1
             if data is None:
                 raise ValueError('failed to load mesh "%s"' % mesh_name)
+            if data.get("_tex"):                              # resolve chunk textures to engine texture ids
+                tt = np.array(data["tri_tex"], np.int32)
+                for k, (tex_key, texels) in enumerate(data["_tex"]):
+                    _lock.release()
+                    try:
+                        tex = Texture.from_array("mesh:" + tex_key, texels)
+                    finally:
+                        _lock.acquire()
+                    tt[tt == -2 - k] = tex.tex_id
+                data["tri_tex"] = tt
             mesh = ObjMesh(mesh_name, data)
             mesh.mesh_id = len(cls.registry)
             cls.registry.append(mesh)

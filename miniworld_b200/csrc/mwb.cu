@@ -25,7 +25,7 @@
 #include <cuda_runtime.h>
 #endif
 
-#define MWB_MAX_ENTS_CAP 16
+#define MWB_MAX_ENTS_CAP 32
 #define MWB_STAGE_QUAD_BYTES_HOST 16384
 
 static thread_local std::string g_err;
@@ -122,7 +122,7 @@ struct mwb_handle {
   void* mesh_tris_buf;
   void* mesh_bbox_buf;
   // asset storage
-  void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *protos, *ops, *maze, *maze_cdf;
+  void *tex_desc, *texels, *mesh_desc, *mesh_pos, *mesh_nrm, *mesh_uv, *mesh_rgb, *mesh_tex, *protos, *ops, *maze, *maze_cdf;
 };
 
 template <typename T>
@@ -390,7 +390,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->profiling = false;
   h->frames_copied = false;
   h->have_params = h->have_protos = h->have_template = false;
-  h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = nullptr;
+  h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = h->mesh_tex = nullptr;
   h->protos = h->ops = h->maze = h->maze_cdf = nullptr;
   h->mesh_tris_buf = nullptr;
   h->mesh_bbox_buf = nullptr;
@@ -501,7 +501,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
   cudaStreamSynchronize(h->stream);
 #endif
   for (void* p : h->allocs) dev_free(p);
-  void* extra[] = {h->tex_desc, h->texels, h->mesh_desc, h->mesh_pos, h->mesh_nrm, h->mesh_uv, h->mesh_rgb,
+  void* extra[] = {h->tex_desc, h->texels, h->mesh_desc, h->mesh_pos, h->mesh_nrm, h->mesh_uv, h->mesh_rgb, h->mesh_tex,
                    h->protos, h->ops, h->mesh_tris_buf, h->mesh_bbox_buf, h->maze, h->maze_cdf};
   for (void* p : extra)
     if (p) dev_free(p);
@@ -610,7 +610,7 @@ extern "C" int mwb_upload_textures(mwb_handle* h, const mwb_tex_desc* descs, int
 }
 
 extern "C" int mwb_upload_meshes(mwb_handle* h, const mwb_mesh_desc* descs, int n, const float* pos, const float* nrm,
-                                 const float* uv, const float* rgb) {
+                                 const float* uv, const float* rgb, const int32_t* tri_tex) {
   if (!h || !descs || n <= 0) return fail(MWB_EINVAL, "bad arguments");
   std::vector<MeshDev> md(n);
   size_t total = 0;
@@ -627,7 +627,14 @@ extern "C" int mwb_upload_meshes(mwb_handle* h, const mwb_mesh_desc* descs, int 
   if (!rc) rc = replace_buf(&h->mesh_nrm, nrm, total * 9 * sizeof(float), h->stream);
   if (!rc) rc = replace_buf(&h->mesh_uv, uv, total * 6 * sizeof(float), h->stream);
   if (!rc) rc = replace_buf(&h->mesh_rgb, rgb, total * 9 * sizeof(float), h->stream);
+  std::vector<int32_t> none;
+  if (!tri_tex) {
+    none.assign(total, -1);
+    tri_tex = none.data();
+  }
+  if (!rc) rc = replace_buf(&h->mesh_tex, tri_tex, total * sizeof(int32_t), h->stream);
   if (rc) return rc;
+  h->A.mesh_tex = (const int32_t*)h->mesh_tex;
   h->A.meshes = (const MeshDev*)h->mesh_desc;
   h->A.mesh_pos = (const float*)h->mesh_pos;
   h->A.mesh_nrm = (const float*)h->mesh_nrm;

@@ -51,6 +51,7 @@ struct RenderAssets {
   const float* mesh_nrm;
   const float* mesh_uv;          // [T][3][2]
   const float* mesh_rgb;
+  const int32_t* mesh_tex;       // [T] texture id of each triangle's material, or -1
   int32_t num_meshes;
 };
 
@@ -594,7 +595,7 @@ MWB_DEV float depth_code_to_metres(uint32_t code) {
 // "slots" number the surviving triangles consecutively across segments, so slot order ==
 // draw order and the per-sample key (depth16 << 16 | slot) implements GL_LESS exactly.
 
-#define MWB_MAX_DRAWN 8
+#define MWB_MAX_DRAWN 24
 
 struct FrameMap {
   int n_quads;                       // room quads of this env
@@ -767,7 +768,7 @@ MWB_DEV void mesh_triangle(const RenderAssets& A, const mwb_proto& pr, const Ent
     in.mat[k][1] = m[1];
     in.mat[k][2] = m[2];
   }
-  in.tex = -1;   // ball_* / key_* carry no texture (objmesh.py:226-230)
+  in.tex = A.mesh_tex[base];   // -1 for ball_* / key_* (no map_Kd, objmesh.py:226-230)
 }
 
 MWB_DEV const mwb_quad* env_quads(const DevState& S, int i) { return S.quads + (size_t)geom_index(S, i) * S.Q; }

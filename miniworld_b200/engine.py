@@ -10,12 +10,12 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 RULE_NONE, RULE_GOAL, RULE_PICKUP = 0, 1, 2
 SURF_WALL, SURF_FLOOR, SURF_CEIL = 0, 1, 2
 OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE, OP_MAZE = 0, 1, 2, 3, 4
 MAX_EDGES = 8
-MAX_ENTS_CAP = 16
+MAX_ENTS_CAP = 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libmwb.so")
@@ -138,7 +138,7 @@ def load_library(lib_path=None):
     lib.mwb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     lib.mwb_destroy.argtypes = [vp]
     lib.mwb_upload_textures.argtypes = [vp, vp, C.c_int, vp]
-    lib.mwb_upload_meshes.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    lib.mwb_upload_meshes.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     lib.mwb_set_params.argtypes = [vp, C.POINTER(Params)]
     lib.mwb_set_protos.argtypes = [vp, vp, C.c_int]
     lib.mwb_set_template.argtypes = [vp, C.POINTER(Geometry)]
@@ -325,8 +325,9 @@ class Engine:
                 off += m.num_tris
             cat = lambda name: np.ascontiguousarray(np.concatenate([getattr(m, name) for m in ObjMesh.registry]), np.float32)
             pos, nrm, uv, rgb = cat("verts"), cat("norms"), cat("texcs"), cat("colors")
+            tri_tex = np.ascontiguousarray(np.concatenate([m.tri_tex for m in ObjMesh.registry]), np.int32)
             self._check(self.lib.mwb_upload_meshes(self.h, C.cast(descs, C.c_void_p), len(descs),
-                                                   _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(rgb)))
+                                                   _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(rgb), _ptr(tri_tex)))
             self._mesh_uploaded = len(ObjMesh.registry)
 
     # ---- level definition

@@ -9,7 +9,7 @@ import math
 
 import numpy as np
 
-from .assets import ObjMesh, mesh_ent_dims
+from .assets import ObjMesh, Texture, mesh_ent_dims
 from .math import X_VEC, Y_VEC, Z_VEC, gen_rot_matrix
 
 COLORS = {
@@ -69,6 +69,88 @@ class MeshEnt(Entity):
     @property
     def is_static(self):
         return self.static
+
+
+def _frame_border(sx, hy, hz):
+    """The four black border quads shared by ImageFrame and TextFrame (entity.py:223-260, 344-381):
+    (normal, four corners) for left, right, top, bottom."""
+    return [
+        ((0, 0, -1), [(0, +hy, -hz), (+sx, +hy, -hz), (+sx, -hy, -hz), (0, -hy, -hz)]),
+        ((0, 0, 1), [(+sx, +hy, +hz), (0, +hy, +hz), (0, -hy, +hz), (+sx, -hy, +hz)]),
+        ((0, 1, 0), [(+sx, +hy, +hz), (+sx, +hy, -hz), (0, +hy, -hz), (0, +hy, +hz)]),
+        ((0, -1, 0), [(+sx, -hy, -hz), (+sx, -hy, +hz), (0, -hy, +hz), (0, -hy, -hz)]),
+    ]
+
+
+class _QuadFrame(Entity):
+    """Wall-mounted frame drawn as a handful of quads.  The reference draws these with immediate
+    mode GL (ImageFrame.render / TextFrame.render); here the quads become a small synthetic mesh
+    (two triangles per quad, fan order) that the engine's mesh path renders with scale 1."""
+    kind = KIND_MESH
+    scale = np.float32(1.0)
+
+    @property
+    def is_static(self):
+        return True
+
+    def _build(self, key, quads):
+        """quads: list of (normal, corners[4], uv[4] or None, rgb, texture or None)."""
+        V, Nn, UV, C, TT = [], [], [], [], []
+        for normal, corners, uvs, rgb, tex in quads:
+            for a, b, c in ((0, 1, 2), (0, 2, 3)):
+                V.append([corners[a], corners[b], corners[c]])
+                Nn.append([normal] * 3)
+                UV.append([uvs[a], uvs[b], uvs[c]] if uvs else [(0, 0)] * 3)
+                C.append([rgb] * 3)
+                TT.append(tex.tex_id if tex is not None else -1)
+        self.mesh = ObjMesh.from_arrays(key, V, Nn, UV, C, np.array(TT, np.int32))
+
+
+class ImageFrame(_QuadFrame):
+    """Picture on a wall; `pos` is the middle of the frame, which faces +x before rotation
+    (reference entity.py:168-262)."""
+
+    def __init__(self, pos, dir, tex_name, width, depth=0.05):
+        super().__init__()
+        self.pos, self.dir = pos, dir
+        self.tex = Texture.get(tex_name)
+        self.width, self.depth = width, depth
+        self.height = (float(self.tex.height) / self.tex.width) * self.width
+        sx, hz, hy = self.depth, self.width / 2, self.height / 2
+        front = ((1, 0, 0), [(sx, +hy, -hz), (sx, +hy, +hz), (sx, -hy, +hz), (sx, -hy, -hz)],
+                 [(1, 1), (0, 1), (0, 0), (1, 0)], (1, 1, 1), self.tex)
+        border = [(n, c, None, (0, 0, 0), None) for n, c in _frame_border(sx, hy, hz)]
+        self._build("imageframe:%s:%r:%r" % (tex_name, width, depth), [front] + border)
+
+
+class TextFrame(_QuadFrame):
+    """Line of character tiles on a wall (reference entity.py:265-383); the glyph textures are
+    (re)drawn in `randomize`, i.e. once per reset."""
+
+    def __init__(self, pos, dir, str, height=0.15, depth=0.05):
+        super().__init__()
+        self.pos, self.dir, self.str = pos, dir, str
+        self.depth, self.height = depth, height
+        self.width = len(str) * height
+        self.mesh = None
+
+    def randomize(self, params, rng):
+        self.texs = []
+        for ch in self.str:
+            try:
+                self.texs.append(None if ch == " " else Texture.get("chars/ch_0x%d" % ord(ch), rng))
+            except Exception:
+                raise ValueError("only alphanumerical characters supported in TextFrame")
+        sx, hz, hy = 0.05, self.width / 2, self.height / 2
+        quads = []
+        for idx, tex in enumerate(self.texs):
+            z0 = hz - self.height * (idx + 1)
+            z1 = z0 + self.height
+            quads.append(((1, 0, 0), [(sx, +hy, z0), (sx, +hy, z1), (sx, -hy, z1), (sx, -hy, z0)],
+                          [(1, 1), (0, 1), (0, 0), (1, 0)], (1, 1, 1), tex))
+        quads += [(n, c, None, (0, 0, 0), None) for n, c in _frame_border(sx, hy, hz)]
+        key = "textframe:%s:%r:%s" % (self.str, self.height, ",".join(str(t.tex_id) if t else "-" for t in self.texs))
+        self._build(key, quads)
 
 
 class Box(Entity):

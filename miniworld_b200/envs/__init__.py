@@ -2,11 +2,13 @@
 
 The five levels of BASELINE.json's configs (Hallway, OneRoom, FourRooms, Maze, PickupObjects) run on
 the batched engine with device-side resets and lowered rules; the others listed here use entity
-kinds the engine already renders (Box, Ball, Key) and run through the single-environment class.
+kinds the engine renders too (Box, Ball, Key, textured meshes, image / text frames) and run through
+the single-environment class -- all 23 ids of the reference are registered.
 `MiniWorld-MazeS8-v0` is the 8x8 maze (the reference's `MiniWorld-Maze-v0` default) under the name
 BASELINE.json uses.
 """
 from .._gym import gym
+from .collecthealth import CollectHealth
 from .fourrooms import FourRooms
 from .hallway import Hallway
 from .maze import Maze, MazeS2, MazeS3, MazeS3Fast
@@ -14,7 +16,11 @@ from .oneroom import OneRoom, OneRoomS6, OneRoomS6Fast
 from .pickupobjects import PickupObjects
 from .putnext import PutNext
 from .roomobjects import RoomObjects
+from .sidewalk import Sidewalk
+from .sign import Sign
+from .threerooms import ThreeRooms
 from .tmaze import TMaze, TMazeLeft, TMazeRight
+from .wallgap import WallGap
 from .ymaze import YMaze, YMazeLeft, YMazeRight
 
 LEVELS = {
@@ -30,11 +36,16 @@ LEVELS = {
     "MiniWorld-MazeS3Fast-v0": MazeS3Fast,
     "MiniWorld-PickupObjects-v0": PickupObjects,
     # levels outside BASELINE.json's configs: single-env GPU path (world.MiniWorldEnv), Python rule
+    "MiniWorld-CollectHealth-v0": CollectHealth,
     "MiniWorld-PutNext-v0": PutNext,
     "MiniWorld-RoomObjects-v0": RoomObjects,
+    "MiniWorld-Sidewalk-v0": Sidewalk,
+    "MiniWorld-Sign-v0": Sign,
+    "MiniWorld-ThreeRooms-v0": ThreeRooms,
     "MiniWorld-TMaze-v0": TMaze,
     "MiniWorld-TMazeLeft-v0": TMazeLeft,
     "MiniWorld-TMazeRight-v0": TMazeRight,
+    "MiniWorld-WallGap-v0": WallGap,
     "MiniWorld-YMaze-v0": YMaze,
     "MiniWorld-YMazeLeft-v0": YMazeLeft,
     "MiniWorld-YMazeRight-v0": YMazeRight,

@@ -85,7 +85,7 @@ def proto_record(ent):
         p["size"] = np.asarray(ent.size, float)
         from .entity import COLORS
         p["color"] = COLORS[ent.color]
-    elif isinstance(ent, MeshEnt):
+    elif isinstance(ent, MeshEnt) or getattr(ent, "mesh", None) is not None:   # OBJ meshes and quad frames
         p["kind"] = KIND_MESH
         p["mesh_id"] = ent.mesh.mesh_id
         p["scale"] = np.float32(ent.scale)

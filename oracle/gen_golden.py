@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, ".."))
 from oracle.ref_stub import make_reference_env  # noqa: E402
 
-MAX_ENTS = 8
+MAX_ENTS = 20
 
 CASES = [
     # name, env id, kwargs, N, T
@@ -40,6 +40,11 @@ CASES = [
     ("ymaze_dr", "MiniWorld-YMaze-v0", {"domain_rand": True}, 8, 300),
     ("roomobjs", "MiniWorld-RoomObjects-v0", {}, 8, 300),
     ("putnext_dr", "MiniWorld-PutNext-v0", {"domain_rand": True}, 8, 300),
+    ("wallgap", "MiniWorld-WallGap-v0", {}, 6, 300),
+    ("sidewalk_dr", "MiniWorld-Sidewalk-v0", {"domain_rand": True}, 6, 300),
+    ("collecthealth", "MiniWorld-CollectHealth-v0", {}, 4, 300),
+    ("threerooms_dr", "MiniWorld-ThreeRooms-v0", {"domain_rand": True}, 6, 300),
+    ("sign", "MiniWorld-Sign-v0", {}, 6, 120),
 ]
 
 

@@ -144,8 +144,10 @@ def draw_list(env, tex_index):
                 cat = lambda key, k: np.concatenate([np.asarray(v.attrs[key], np.float32).reshape(-1, 3, k)
                                                      for v in m.vlists])
                 V, Nm, Tm, Cm = cat("v3f", 3), cat("n3f", 3), cat("t2f", 2), cat("c3f", 3)
-            else:                         # the package's host mirror (assets.ObjMesh)
+                tri_tex = np.full(len(V), -1, np.int32)      # textured reference meshes: not wired up here
+            else:                         # the package's host mirror (assets.ObjMesh / quad frames)
                 V, Nm, Tm, Cm = m.verts, m.norms, m.texcs, m.colors
+                tri_tex = m.tri_tex           # engine texture ids == oracle ids (same registry order)
             x, y, z = V[..., 0], V[..., 1], V[..., 2]
             wx = (x * c + z * s) * sc + t[0]
             wy = y * sc + t[1]
@@ -158,7 +160,7 @@ def draw_list(env, tex_index):
             Nn.extend(np.stack([nx, ny, nz], axis=-1).astype(np.float32))
             UV.extend(np.asarray(Tm, np.float32))
             RGB.extend(np.asarray(Cm, np.float32))
-            TX.extend([-1] * F)
+            TX.extend(int(v) for v in tri_tex)
 
     # display list first (static entities), then the dynamic ones, both in list order
     for ent in env.entities:

@@ -96,6 +96,11 @@ SINGLE_CASES = {
     "ymaze_dr": ("MiniWorld-YMaze-v0", {"domain_rand": True}),
     "roomobjs": ("MiniWorld-RoomObjects-v0", {}),
     "putnext_dr": ("MiniWorld-PutNext-v0", {"domain_rand": True}),
+    "wallgap": ("MiniWorld-WallGap-v0", {}),
+    "sidewalk_dr": ("MiniWorld-Sidewalk-v0", {"domain_rand": True}),
+    "collecthealth": ("MiniWorld-CollectHealth-v0", {}),
+    "threerooms_dr": ("MiniWorld-ThreeRooms-v0", {"domain_rand": True}),
+    "sign": ("MiniWorld-Sign-v0", {}),
     "fourrooms": ("MiniWorld-FourRooms-v0", {}),
     "pickup": ("MiniWorld-PickupObjects-v0", {}),
 }
@@ -123,5 +128,7 @@ def run_single_env_trajectory(name, g, lib_path=None, envs=2, steps=120, device=
             assert len(env.entities) == g["n_ents"][t + 1, i]
             for e, ent in enumerate(env.entities):
                 assert np.array_equal(np.asarray(ent.pos, float), g["ent_pos"][t + 1, i, e]), (name, i, t, e)
+        if isinstance(obs, dict):
+            obs = obs["obs"]
         assert obs.shape == (60, 80, 3) and 0 < obs.mean() < 255
         env.close()

@@ -63,7 +63,8 @@ def test_device_maze_long_rollout_with_resets(hostsim_path):
     run_trajectory("mazes3", golden("mazes3"), hostsim_path, steps=300, n=8, check_every=25)
 
 
-@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "roomobjs", "putnext_dr", "pickup"])
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "roomobjs", "putnext_dr", "pickup", "wallgap", "sidewalk_dr",
+                                  "collecthealth", "threerooms_dr", "sign"])
 def test_single_env_levels_follow_reference(hostsim_path, name):
     """Levels outside the batched configs (and PickupObjects for the carry path) through the
     N = 1 engine with the level's own Python rule."""

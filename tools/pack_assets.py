@@ -17,9 +17,11 @@ import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
-TEXTURES = ["concrete", "floor_tiles_bw", "concrete_tiles", "brick_wall", "asphalt"]
+TEXTURES = ["concrete", "floor_tiles_bw", "concrete_tiles", "brick_wall", "asphalt", "cinder_blocks", "slime",
+            "logo_mila"] + ["chars/ch_0x%d" % ord(c) for c in "BLUERDGN"]
 MESHES = ["ball_%s" % c for c in ("blue", "green", "grey", "purple", "red", "yellow")] + \
-         ["key_%s" % c for c in ("blue", "green", "grey", "purple", "red", "yellow")]
+         ["key_%s" % c for c in ("blue", "green", "grey", "purple", "red", "yellow")] + \
+         ["building", "cone", "medkit", "duckie"]
 
 
 def main():
@@ -46,6 +48,16 @@ def main():
             geoms[h] = name.split("_")[0]
             for k in ("verts", "norms", "texcs", "min_coords", "max_coords"):
                 out["meshgeom/%s/%s" % (geoms[h], k)] = d[k]
+            tri_tex = np.full(len(d["verts"]), -1, np.int32)
+            ntex = 0
+            for start, end, tex_path in d["chunks"]:
+                if tex_path is not None:
+                    with Image.open(tex_path) as im:
+                        out["meshtex/%s/%d" % (geoms[h], ntex)] = np.asarray(im.convert("RGB"))
+                    tri_tex[start:end] = -2 - ntex
+                    ntex += 1
+            if ntex:
+                out["meshgeom/%s/tri_tex" % geoms[h]] = tri_tex
         out["mesh/%s/geom" % name] = np.array(geoms[h])
         out["mesh/%s/colors" % name] = d["colors"]
     np.savez_compressed(args.out, **out)
