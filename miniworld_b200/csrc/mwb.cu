@@ -456,8 +456,14 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   // every room quad and box face can yield two set-up triangles.  Up to 512 of them live in
   // shared memory; larger levels (Maze) keep the per-env lists in HBM instead.
   {
+    // blocks per env frame: at least one per 150 half-tiles (80x60 -> 1, 160x120 -> 4), and more
+    // when few envs are resident so that the grid still covers ~4 waves of the 148 x 3 block
+    // slots (each part redoes the cheap geometry phase); never fewer than 30 half-tiles per part
     const int halves = ((cfg->obs_width + 7) / 8) * ((cfg->obs_height + 3) / 4);
-    h->k2_parts = (halves + 149) / 150;
+    const int base = (halves + 149) / 150, want = (1776 + cfg->num_envs - 1) / cfg->num_envs;
+    const int maxp = halves / 30 > 1 ? halves / 30 : 1;
+    h->k2_parts = base > want ? base : want;
+    if (h->k2_parts > maxp) h->k2_parts = maxp;
     if (h->k2_parts < 1) h->k2_parts = 1;
   }
   h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);

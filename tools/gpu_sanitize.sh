@@ -1,0 +1,32 @@
+#!/bin/bash
+# compute-sanitizer (memcheck + racecheck) over a small rollout of every batched level, and an
+# ncu summary of K1.  Logs -> gpurun_out/.
+mkdir -p gpurun_out
+cat > /tmp/san.py <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+from miniworld_b200.batched import BatchedMiniWorld
+from miniworld_b200.envs import LEVELS
+for level, kw in [("MiniWorld-FourRooms-v0", dict(want_depth=True)), ("MiniWorld-Hallway-v0", dict(domain_rand=True)),
+                  ("MiniWorld-MazeS3-v0", {}), ("MiniWorld-PickupObjects-v0", dict(obs_width=160, obs_height=120)),
+                  ("MiniWorld-OneRoom-v0", dict(msaa_samples=4))]:
+    env = BatchedMiniWorld(level, 48, **kw)
+    env.reset(seed=7)
+    acts = torch.as_tensor(np.random.default_rng(1).integers(0, env.action_space.n, size=(12, 48), dtype=np.int32), device="cuda")
+    for t in range(12):
+        obs, r, te, tr, _ = env.step(acts[t])
+    torch.cuda.synchronize()
+    print(level, float(obs.float().mean()), env.engine.overflow_count())
+    env.close()
+e = LEVELS["MiniWorld-ThreeRooms-v0"](domain_rand=True)
+e.reset(seed=1)
+for t in range(6):
+    e.step(t % 3)
+print("threerooms", e.render_obs().mean())
+PY
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard" gpurun_out/sanitizer_$tool.log | head -8
+done
+timeout 600 ncu --set full --clock-control none -k regex:step_kernel -s 6 -c 1 -f -o gpurun_out/prof_k1 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_k1.log 2>&1; echo "ncu k1 rc=$?"
+timeout 600 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; cut -c1-330 gpurun_out/configs.jsonl
