@@ -198,6 +198,7 @@ class MiniWorldEnv(gym.Env):
         self.device = device
         self.engine_lib = engine_lib     # None: the in-tree libmwb.so
         self._engine = None
+        self._vis_engine = None
         self.reset()
 
     # ------------------------------------------------------------------ episode control
@@ -401,11 +402,24 @@ class MiniWorldEnv(gym.Env):
         return eng.render(want_depth=True)[1]
 
     def render(self):
-        if self.render_mode == "rgb_array":
-            return self.render_obs()
-        return None
+        """render_mode="rgb_array": the agent's view at window_width x window_height (the
+        reference's vis_fb frame, miniworld.py:1340-1362).  The interactive window and the top
+        view are not part of this package."""
+        if self.render_mode != "rgb_array":
+            return None
+        if self.view != "agent":
+            raise NotImplementedError("only the agent view is rendered by the CUDA engine")
+        if self.device is None:
+            raise RuntimeError("MiniWorldEnv was built with device=None (world generation only)")
+        if self._vis_engine is None:
+            from .engine import SingleEnvEngine
+            self._vis_engine = SingleEnvEngine(self.window_width, self.window_height, self.msaa_samples, self.device,
+                                               lib_path=self.engine_lib)
+        self._vis_engine.push(self, full=True)
+        return self._vis_engine.render(want_depth=False)[0]
 
     def close(self):
-        if self._engine is not None:
-            self._engine.close()
-            self._engine = None
+        for name in ("_engine", "_vis_engine"):
+            if getattr(self, name, None) is not None:
+                getattr(self, name).close()
+                setattr(self, name, None)

@@ -79,21 +79,51 @@ def test_single_env_matches_golden_and_batched(libmwb_path):
 
 
 def test_all_levels_no_intersection_after_reset(libmwb_path):
-    """reference tests/test_miniworld.py:98-120 (domain_rand on; agent never spawns inside anything)."""
+    """reference tests/test_miniworld.py:98-120 over every registered id: construct, switch
+    domain randomisation on, reset repeatedly (agent never spawns inside anything), random actions."""
     from miniworld_b200.envs import LEVELS
     for eid, cls in LEVELS.items():
         if "Maze-v0" in eid or "MazeS8" in eid:
-            continue      # 8x8 maze: covered by the golden-trajectory test
-        env = cls(domain_rand=True)
-        rng = np.random.default_rng(0)
+            continue      # 8x8 maze: covered by the golden-trajectory tests (46 ms of Python per host reset)
+        env = cls()
+        env.domain_rand = True
         for _ in range(3):
             env.reset()
-            assert not env.intersect(env.agent, env.agent.pos, env.agent.radius)
+            assert not env.intersect(env.agent, env.agent.pos, env.agent.radius), eid
             for _ in range(20):
-                _, _, te, tr, _ = env.step(int(rng.integers(0, env.action_space.n)))
-                if te or tr:
+                action = int(env.np_random.integers(0, env.action_space.n))
+                _, _, te, tr, _ = env.step(action)
+                if te:
                     env.reset()
         env.close()
+
+
+def test_render_rgb_array_and_wrappers(libmwb_path):
+    """reference tests/test_miniworld.py:17-64: obs mean vs the 800x600 render, wrapper shapes."""
+    from miniworld_b200.envs import Hallway
+    from miniworld_b200.wrappers import GreyscaleWrapper, PyTorchObsWrapper, StochasticActionWrapper
+    env = Hallway(render_mode="rgb_array")
+    env.reset(seed=0)
+    for _ in range(10):
+        obs, _, _, _, _ = env.step(env.action_space.sample())
+        assert 0 < obs.mean() < 255 and obs.shape == env.observation_space.shape
+        frame = env.render()
+        assert frame.shape == (600, 800, 3)
+        assert abs(obs.mean() - frame.mean()) < 5
+    env.close()
+    wrapped = PyTorchObsWrapper(Hallway())
+    o, _ = wrapped.reset()
+    assert o.shape == (3, 80, 60) == wrapped.observation_space.shape
+    wrapped.close()
+    grey = GreyscaleWrapper(Hallway())
+    o, _ = grey.reset()
+    assert o.shape == (60, 80, 1)
+    grey.close()
+    stoch = StochasticActionWrapper(Hallway(), prob=0.5)
+    stoch.reset()
+    for _ in range(5):
+        stoch.step(0)
+    stoch.close()
 
 
 @pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "roomobjs", "putnext_dr", "pickup", "wallgap", "sidewalk_dr",

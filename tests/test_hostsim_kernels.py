@@ -70,3 +70,25 @@ def test_single_env_levels_follow_reference(hostsim_path, name):
     N = 1 engine with the level's own Python rule."""
     from helpers import run_single_env_trajectory
     run_single_env_trajectory(name, golden(name), hostsim_path, envs=2, steps=100)
+
+
+def test_render_mode_and_wrappers_on_host_sim(hostsim_path):
+    """reference tests/test_miniworld.py:17-64 (render vs obs mean, wrapper shapes), kernels on the CPU."""
+    from miniworld_b200.envs import Hallway
+    from miniworld_b200.wrappers import GreyscaleWrapper, PyTorchObsWrapper, StochasticActionWrapper
+    env = Hallway(render_mode="rgb_array", window_width=200, window_height=150, engine_lib=hostsim_path)
+    env.reset(seed=0)
+    for _ in range(3):
+        obs, _, _, _, _ = env.step(2)
+        frame = env.render()
+        assert frame.shape == (150, 200, 3) and abs(obs.mean() - frame.mean()) < 5
+    env.close()
+    w = PyTorchObsWrapper(Hallway(engine_lib=hostsim_path))
+    assert w.reset()[0].shape == (3, 80, 60) == tuple(w.observation_space.shape)
+    g = GreyscaleWrapper(Hallway(engine_lib=hostsim_path))
+    assert g.reset()[0].shape == (60, 80, 1)
+    s = StochasticActionWrapper(Hallway(engine_lib=hostsim_path), prob=0.5)
+    s.reset(seed=1)
+    s.step(0)
+    for e in (w, g, s):
+        e.close()
