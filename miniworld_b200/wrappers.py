@@ -47,7 +47,8 @@ class PyTorchObsWrapper(_Wrapper):
 
 
 class GreyscaleWrapper(_Wrapper):
-    """RGB -> one luminance channel (0.30 R + 0.59 G + 0.11 B), uint8."""
+    """RGB -> one luminance channel 0.30 R + 0.59 G + 0.11 B; like the reference (wrappers.py:43-46) the
+    result is the float64 array numpy's promotion produces, shape (H, W, 1), not re-quantised."""
 
     def __init__(self, env):
         super().__init__(env)
@@ -56,7 +57,7 @@ class GreyscaleWrapper(_Wrapper):
 
     def observation(self, obs):
         grey = 0.30 * obs[:, :, 0] + 0.59 * obs[:, :, 1] + 0.11 * obs[:, :, 2]
-        return np.expand_dims(grey.astype(obs.dtype), axis=2)
+        return np.expand_dims(grey, axis=2)
 
 
 class StochasticActionWrapper(_Wrapper):
