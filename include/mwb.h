@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MWB_ABI_VERSION 5
+#define MWB_ABI_VERSION 6
 
 /* error codes */
 #define MWB_OK 0
@@ -295,6 +295,18 @@ int mwb_step(mwb_handle* h, const int32_t* actions, const double* step_params, u
 
 /* render_obs / render_depth without stepping (observation returned by reset()) */
 int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* stream);
+
+/* render_top_view (miniworld.py:1088-1175): orthographic map of every env, rendered at the handle's
+ * observation size with its MSAA setting.  extents = {min_x, max_x, min_z, max_z} as the reference
+ * has them after the aspect-ratio adjustment (:1109-1133), i.e. glOrtho(min_x, max_x, -max_z, -min_z,
+ * -100, 100); render_agent != 0 also draws Agent.render()'s marker triangle (entity.py:518-539).
+ *   obs          uint8[N][H][W][3] (host or device)                                             */
+int mwb_render_top_view(mwb_handle* h, const double extents[4], int render_agent, uint8_t* obs, void* stream);
+
+/* get_visible_ents (miniworld.py:1238-1333): occlusion queries of a 0.2 m box at every entity
+ * against the rooms, at the observation frame buffer's resolution and sample count.
+ *   mask         uint32[N] (host or device): bit e = entity-list slot e passed its query          */
+int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream);
 
 /* ---- state exchange (env.agent.pos, env.entities[i].pos ... views; checkpointing) ------ */
 int mwb_get_state(mwb_handle* h, const mwb_state_view* out);

@@ -235,6 +235,27 @@ class BatchedMiniWorld:
         self.engine.render(depth=d, stream=torch.cuda.current_stream(self.device).cuda_stream)
         return d
 
+    def render_top_view(self, render_agent=True, out=None):
+        """Map view of every env, uint8 [N, H, W, 3] (reference render_top_view, miniworld.py:1088-1175).
+        Extents come from the level definition (all envs of a level share them).  `out`: optional numpy
+        array / CUDA tensor to fill; default a fresh CUDA tensor."""
+        ext = self.proto_env.top_view_extents(self.obs_width, self.obs_height)
+        if out is None:
+            torch = self._ensure_torch()
+            out = torch.zeros((self.num_envs, self.obs_height, self.obs_width, 3), dtype=torch.uint8,
+                              device=torch.device("cuda", self.device))
+        self.engine.render_top_view(ext, out, render_agent)
+        return out
+
+    def visible_ents(self, out=None):
+        """uint32 [N]: bit e set iff entity-list slot e of that env passes the reference's occlusion query
+        (get_visible_ents, miniworld.py:1238-1333)."""
+        if out is None:
+            torch = self._ensure_torch()
+            out = torch.zeros(self.num_envs, dtype=torch.int32, device=torch.device("cuda", self.device))
+        self.engine.visible_ents(out)
+        return out
+
     # ------------------------------------------------------------------ state views
     def get_state(self, **kw):
         return self.engine.get_state(**kw)

@@ -19,6 +19,7 @@
 
 #include "../../include/mwb.h"
 #include "raster.cuh"
+#include "visibility.cuh"
 #include "reset.cuh"
 
 #ifndef MWB_HOSTSIM
@@ -109,7 +110,9 @@ struct mwb_handle {
   bool have_params, have_protos, have_template;
   bool profiling;
   bool frames_copied;
-  int k2_minblocks;
+  int k2_variant;
+  TriRec* vis_tris;              // scratch of mwb_visible_ents, allocated on first use
+  ViewSpec view;                 // what the next render launch draws (agent camera unless mwb_render_top_view)
   int k2_parts;                   // blocks per env frame (1 at 80x60, 4 at 160x120)
 #ifndef MWB_HOSTSIM
   cudaStream_t copy_stream;
@@ -283,11 +286,11 @@ struct VecTris {
   const TriRec& operator()(uint32_t slot) const { return t[slot]; }
 };
 template <int MSAA>
-static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* obs, float* depth) {
+static void hostsim_render_t(const DevState& S, const RenderAssets& A, const ViewSpec& view, uint8_t* obs, float* depth) {
   const int W = S.obs_w, H = S.obs_h;
   for (int i = 0; i < S.N; ++i) {
-    Camera cam = make_camera(S, i);
-    FrameMap fm = build_frame_map(S, i);
+    Camera cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i);
+    FrameMap fm = build_frame_map(S, i, view.mode == 1 && view.render_agent != 0);
     std::vector<TriRec> tris;
     TriRec rec;
     int seg;
@@ -308,6 +311,7 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* 
         }
       }
     }
+    if (fm.agent_task >= 0 && task_triangle(S, A, cam, fm, env_quads(S, i), i, fm.agent_task, W, H, rec, seg)) tris.push_back(rec);
     // test-only experiment: visit triangles front to back (MWB_HS_SORT=1); slots keep draw order
     std::vector<int> order(tris.size());
     for (size_t j = 0; j < tris.size(); ++j) order[j] = (int)j;
@@ -357,10 +361,10 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, uint8_t* 
       }
   }
 }
-static void hostsim_render(const DevState& S, const RenderAssets& A, uint8_t* obs, float* depth) {
-  if (S.msaa == 1) hostsim_render_t<1>(S, A, obs, depth);
-  else if (S.msaa == 4) hostsim_render_t<4>(S, A, obs, depth);
-  else hostsim_render_t<8>(S, A, obs, depth);
+static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewSpec& view, uint8_t* obs, float* depth) {
+  if (S.msaa == 1) hostsim_render_t<1>(S, A, view, obs, depth);
+  else if (S.msaa == 4) hostsim_render_t<4>(S, A, view, obs, depth);
+  else hostsim_render_t<8>(S, A, view, obs, depth);
 }
 #endif
 
@@ -394,6 +398,8 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->protos = h->ops = h->maze = h->maze_cdf = nullptr;
   h->mesh_tris_buf = nullptr;
   h->mesh_bbox_buf = nullptr;
+  memset(&h->view, 0, sizeof(ViewSpec));
+  h->vis_tris = nullptr;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
 #ifndef MWB_HOSTSIM
@@ -466,7 +472,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     if (h->k2_parts > maxp) h->k2_parts = maxp;
     if (h->k2_parts < 1) h->k2_parts = 1;
   }
-  h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents);
+  h->tri_cap = 2 * (cfg->max_quads + 6 * cfg->max_ents) + 2;   // + the top view's agent marker
   h->smem_tris = h->tri_cap <= 512;
   if (!h->smem_tris) {
     TriRec* buf = nullptr;
@@ -478,22 +484,36 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   }
   // static quads are staged in shared memory (TMA bulk copy) when they fit in 16 KB; the
   // quad capacity is kept even so that every env's block starts 16-byte aligned
+  {
+    // tuning knob: 0 = 320 threads x 3 blocks/SM, warps stride over the half-tiles; 1 = same, warps claim
+    // half-tiles from a shared counter (default: -9 % kernel time on B200); 2 = 256 threads x 4 blocks/SM, dynamic
+    const char* v = getenv("MWB_K2_VARIANT");
+    h->k2_variant = v ? atoi(v) : MWB_K2_DEFAULT_VARIANT;
+    if (h->k2_variant < 0 || h->k2_variant > 2) h->k2_variant = MWB_K2_DEFAULT_VARIANT;
+  }
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
-  CK(cudaFuncSetAttribute(render_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(render_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  {
-    const char* v = getenv("MWB_K2_MINBLOCKS");   // tuning knob: resident blocks per SM the kernel is compiled for
-    h->k2_minblocks = (v && (atoi(v) == 2 || atoi(v) == 4)) ? atoi(v) : 3;
+#define MWB_K2_ATTR(T, B, D)                                                                                        \
+  CK(cudaFuncSetAttribute(render_kernel<1, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
+  CK(cudaFuncSetAttribute(render_kernel<4, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
+  CK(cudaFuncSetAttribute(render_kernel<8, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+  switch (h->k2_variant) {
+    case 0: MWB_K2_ATTR(320, 3, false); break;
+    case 1: MWB_K2_ATTR(320, 3, true); break;
+    default: MWB_K2_ATTR(256, 4, true); break;
+  }
+#undef MWB_K2_ATTR
+  if (getenv("MWB_DEBUG")) {
+    int nb = 0;
+    switch (h->k2_variant) {
+      case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, false>, 320, smem); break;
+      case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, true>, 320, smem); break;
+      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 4, true>, 256, smem); break;
+    }
+    fprintf(stderr, "[mwb] K2 variant %d: dynamic smem %d B, parts %d, resident blocks/SM (8x MSAA) %d\n", h->k2_variant, smem,
+            h->k2_parts, nb);
   }
 #endif
   *out = h;
@@ -968,25 +988,17 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
   prof_mark(h, h->ev_k2, s);
-#define MWB_LAUNCH_K2(M, B) render_kernel<M, B><<<count * h->k2_parts, MWB_RENDER_THREADS, smem, s>>>(h->S, h->A, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, h->d_overflow)
-  if (h->k2_minblocks == 2) {
-    switch (h->S.msaa) {
-      case 1: MWB_LAUNCH_K2(1, 2); break;
-      case 4: MWB_LAUNCH_K2(4, 2); break;
-      default: MWB_LAUNCH_K2(8, 2); break;
-    }
-  } else if (h->k2_minblocks == 4) {
-    switch (h->S.msaa) {
-      case 1: MWB_LAUNCH_K2(1, 4); break;
-      case 4: MWB_LAUNCH_K2(4, 4); break;
-      default: MWB_LAUNCH_K2(8, 4); break;
-    }
-  } else {
-    switch (h->S.msaa) {
-      case 1: MWB_LAUNCH_K2(1, 3); break;
-      case 4: MWB_LAUNCH_K2(4, 3); break;
-      default: MWB_LAUNCH_K2(8, 3); break;
-    }
+#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, h->d_overflow)
+#define MWB_LAUNCH_K2_MSAA(T, B, D)                 \
+  switch (h->S.msaa) {                              \
+    case 1: MWB_LAUNCH_K2(1, T, B, D); break;       \
+    case 4: MWB_LAUNCH_K2(4, T, B, D); break;       \
+    default: MWB_LAUNCH_K2(8, T, B, D); break;      \
+  }
+  switch (h->k2_variant) {
+    case 0: MWB_LAUNCH_K2_MSAA(320, 3, false); break;
+    case 1: MWB_LAUNCH_K2_MSAA(320, 3, true); break;
+    default: MWB_LAUNCH_K2_MSAA(256, 4, true); break;
   }
   prof_mark(h, h->ev_k2, s);
   h->launches++;
@@ -1003,7 +1015,7 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, 
   if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
 #ifndef MWB_HOSTSIM
   if (h->S.mesh_cap > 0) {
-    mesh_setup_kernel<<<dim3(h->S.N, h->S.E), 256, 0, s>>>(h->S, h->A);
+    mesh_setup_kernel<<<dim3(h->S.N, h->S.E), 256, 0, s>>>(h->S, h->A, h->view);
     h->launches++;
     CK(cudaGetLastError());
   }
@@ -1032,7 +1044,7 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, 
     CK(cudaStreamWaitEvent(s, h->copies_done, 0));   // later work on s (and its sync) sees the copies
   }
 #else
-  hostsim_render(h->S, h->A, obs, depth);
+  hostsim_render(h->S, h->A, h->view, obs, depth);
 #endif
   return MWB_OK;
 }
@@ -1104,6 +1116,81 @@ extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* s
                          obs_host ? obs : nullptr, depth_host ? depth : nullptr);
   if (rc) return rc;
   return finish_outputs(h, obs, obs_host, depth, depth_host, nullptr, nullptr, nullptr, s, stream != nullptr);
+}
+
+extern "C" int mwb_render_top_view(mwb_handle* h, const double extents[4], int render_agent, uint8_t* obs, void* stream) {
+  if (!h || !extents || !obs) return fail(MWB_EINVAL, "null argument");
+  if (!(extents[1] > extents[0]) || !(extents[3] > extents[2])) return fail(MWB_EINVAL, "empty extents");
+  stream_t s = stream ? (stream_t)stream : h->stream;
+  const bool obs_host = !is_device_ptr(obs);
+  // glOrtho(min_x, max_x, -max_z, -min_z, -100, 100) (miniworld.py:1137)
+  h->view.mode = 1;
+  h->view.render_agent = render_agent != 0;
+  h->view.l = extents[0];
+  h->view.r = extents[1];
+  h->view.b = -extents[3];
+  h->view.t = -extents[2];
+  int rc = launch_render(h, obs_host ? h->d_obs : obs, nullptr, s, obs_host ? obs : nullptr, nullptr);
+  memset(&h->view, 0, sizeof(ViewSpec));
+  if (rc) return rc;
+  return finish_outputs(h, obs, obs_host, nullptr, false, nullptr, nullptr, nullptr, s, stream != nullptr);
+}
+
+extern "C" int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream) {
+  if (!h || !mask) return fail(MWB_EINVAL, "null argument");
+  if (!h->have_protos) return fail(MWB_ESTATE, "protos not set");
+  stream_t s = stream ? (stream_t)stream : h->stream;
+  const int N = h->S.N, box0 = 2 * h->cfg.max_quads, cap = box0 + 12 * h->cfg.max_ents;
+  if (!h->vis_tris && alloc_arr(h, &h->vis_tris, (size_t)N * cap)) return fail(MWB_ECUDA, "scratch allocation failed");
+  const bool host = !is_device_ptr(mask);
+  uint32_t* d_mask = host ? reinterpret_cast<uint32_t*>(h->d_ids) : mask;   // d_ids: N x int32 staging, free between calls
+#ifndef MWB_HOSTSIM
+  switch (h->S.msaa) {
+    case 1: visible_ents_kernel<1><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
+    case 4: visible_ents_kernel<4><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
+    default: visible_ents_kernel<8><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+#else
+  const int W = h->S.obs_w, H = h->S.obs_h, M = h->S.msaa;
+  for (int i = 0; i < N; ++i) {
+    TriRec* tris = h->vis_tris + (size_t)i * cap;
+    const Camera cam = make_camera(h->S, i);
+    int ent_slot[32];
+    const int n_query = queried_entities(h->S, i, ent_slot);
+    int n_room = 0;
+    const mwb_quad* quads = env_quads(h->S, i);
+    const int nq = h->S.num_quads[geom_index(h->S, i)];
+    TriInput in;
+    TriRec rec;
+    for (int task = 0; task < 2 * nq; ++task)
+      if (room_triangle(h->S, h->A, quads, i, task >> 1, task & 1, in) && finish_triangle(cam, in, W, H, rec)) tris[n_room++] = rec;
+    for (int j = 0; j < 12 * n_query; ++j) {
+      query_box_triangle(entity_pose(h->S, i, ent_slot[j / 12]), j % 12, in);
+      if (!finish_triangle(cam, in, W, H, rec)) empty_bbox(rec);
+      tris[box0 + j] = rec;
+    }
+    uint32_t vis = 0;
+    for (int py = 0; py < H; ++py)
+      for (int px = 0; px < W; ++px)
+        for (int sm = 0; sm < M; ++sm) {
+          float ox, oy;
+          if (M == 8) sample_xy_dyn<8>(sm, ox, oy);
+          else if (M == 4) sample_xy_dyn<4>(sm, ox, oy);
+          else sample_xy_dyn<1>(sm, ox, oy);
+          vis |= visible_at_sample(tris, n_room, box0, n_query, ent_slot, px, py, (float)px + ox, (float)py + oy);
+        }
+    d_mask[i] = vis;
+  }
+#endif
+  if (host) {
+    if (d2h(mask, d_mask, (size_t)N * sizeof(uint32_t), s) != 0) return fail(MWB_ECUDA, "readback failed");
+    if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
+  } else if (!stream) {
+    if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
+  }
+  return MWB_OK;
 }
 
 // ------------------------------------------------------------------ ABI: state exchange

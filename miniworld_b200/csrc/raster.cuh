@@ -23,11 +23,11 @@
 #pragma once
 #include "raster_core.cuh"
 
+#define MWB_K2_DEFAULT_VARIANT 1
+
 #ifdef __CUDACC__
 
-#define MWB_RENDER_THREADS 320
-#define MWB_RENDER_WARPS (MWB_RENDER_THREADS / 32)
-#define MWB_MAX_SEGS (1 + MWB_MAX_DRAWN)
+#define MWB_MAX_SEGS (2 + MWB_MAX_DRAWN)   // rooms, drawn entities, the top view's agent marker
 #define MWB_EQ_CAP 96                // exact-phase queue entries per warp
 #define MWB_SORT_LIMIT 512            // room triangle lists up to this length are depth-sorted
 #define MWB_STAGE_QUAD_BYTES 16384   // static quads up to this size are staged in shared memory
@@ -57,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- mesh pre-pass: block (env i, entity slot e) sets up that entity's triangles ----------
-__global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAssets A) {
+__global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAssets A, ViewSpec view) {
   const int i = blockIdx.x, e = blockIdx.y;
   const size_t N = S.N;
   __shared__ Camera cam;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
     return;
   }
   if (tid == 0) {
-    cam = make_camera(S, i);
+    cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i);
     box[0] = box[1] = 0x7fffffff;
     box[2] = box[3] = -1;
   }
@@ -133,10 +133,13 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
 }
 
 // ---- K2 --------------------------------------------------------------------------------
-template <int MSAA, int MINB>
-__global__ void __launch_bounds__(MWB_RENDER_THREADS, MINB)
-render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0, int parts,
-              int tri_cap, int stage_bytes, int* __restrict__ overflow) {
+// THREADS x MINB: block size and resident blocks per SM the kernel is compiled for (64 registers per thread);
+// DYN: warps claim half-tiles from a shared counter instead of striding, which evens out the per-warp work.
+template <int MSAA, int THREADS, int MINB, bool DYN>
+__global__ void __launch_bounds__(THREADS, MINB)
+render_kernel(DevState S, RenderAssets A, ViewSpec view, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0,
+              int parts, int tri_cap, int stage_bytes, int* __restrict__ overflow) {
+  constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // large frames are cut into `parts` blocks per env (each redoes the cheap geometry phase and
   // rasterises its share of the half-tiles), which evens out the load when few envs are resident
@@ -148,12 +151,12 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   __shared__ FrameMap fmap;
   __shared__ Segment segs[MWB_MAX_SEGS];
   __shared__ int seg_count[MWB_MAX_SEGS];
-  __shared__ int warp_tot[MWB_RENDER_WARPS];
-  __shared__ __align__(8) uint8_t stage[MWB_RENDER_WARPS][4][24];
+  __shared__ int warp_tot[WARPS];
+  __shared__ __align__(8) uint8_t stage[WARPS][4][24];
   __shared__ __align__(8) uint64_t quad_bar;
-  __shared__ int chunk_idx[MWB_RENDER_WARPS][32];   // triangle tested by each lane in the current chunk
-  __shared__ uint32_t eq_keys[MWB_RENDER_WARPS][MSAA][32];       // per-sample keys of explicit pixels
-  __shared__ uint32_t eq_items[MWB_RENDER_WARPS][MWB_EQ_CAP];    // queued (pixel, triangle) exact items
+  __shared__ int chunk_idx[WARPS][32];   // triangle tested by each lane in the current chunk
+  __shared__ uint32_t eq_keys[WARPS][MSAA][32];       // per-sample keys of explicit pixels
+  __shared__ uint32_t eq_items[WARPS][MWB_EQ_CAP];    // queued (pixel, triangle) exact items
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = S.obs_w, H = S.obs_h;
@@ -168,6 +171,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + tri_bytes + stage_bytes);
   float* zkey = reinterpret_cast<float*>(order + ((tri_cap + 1) & ~1));
   __shared__ double trig[6];
+  __shared__ int next_half;
   if (tid == 0) mbar_init(&quad_bar, 1);
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
@@ -177,17 +181,17 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
     camera_angles(S, i, ang);
     trig[tid] = (tid & 1) ? mwb_libm::sin_glibc(ang[tid >> 1]) : mwb_libm::cos_glibc(ang[tid >> 1]);
   } else if (tid == 32) {
-    fmap = build_frame_map(S, i);      // meanwhile another warp lays out the frame's draw list
+    fmap = build_frame_map(S, i, view.mode == 1 && view.render_agent != 0);   // meanwhile another warp lays out the draw list
   }
   __syncthreads();
-  if (tid == 0) cam = make_camera(S, i, trig);
+  if (tid == 0) cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i, trig);
   __syncthreads();
   if (staged) mbar_wait(&quad_bar, 0);
   const mwb_quad* quads = staged ? squads : gquads;
 
   // ---- B. room + box triangles -> shared memory, draw order preserved
   int ntris = 0;
-  for (int start = 0; start < fmap.n_tasks; start += MWB_RENDER_THREADS) {
+  for (int start = 0; start < fmap.n_tasks; start += THREADS) {
     const int task = start + tid;
     TriRec rec;
     int keep = 0, seg = 0;
@@ -202,7 +206,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
     __syncthreads();
     int woff = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < MWB_RENDER_WARPS; ++w) {
+    for (int w = 0; w < WARPS; ++w) {
       int v = warp_tot[w];
       if (w < warp) woff += v;
       total += v;
@@ -221,9 +225,10 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
     if (ntris > tri_cap) atomicAdd(overflow, 1);
     // segment table: smem-resident lists are contiguous in draw order; mesh lists live in HBM
     int smem_pos = 0, slot = 0;
-    for (int k = 0; k <= fmap.n_ents; ++k) {
+    const int last = fmap.n_ents + (fmap.agent_task >= 0 ? 1 : 0);
+    for (int k = 0; k <= last; ++k) {
       Segment& sg = segs[k];
-      if (k == 0 || fmap.ent_kind[k - 1] == MWB_KIND_BOX) {
+      if (k == 0 || k > fmap.n_ents || fmap.ent_kind[k - 1] == MWB_KIND_BOX) {
         sg.tris = tris + smem_pos;
         sg.bbox = nullptr;
         sg.count = seg_count[k];
@@ -244,20 +249,20 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
     }
   }
   __syncthreads();
-  const int nsegs = 1 + fmap.n_ents;
+  const int nsegs = 1 + fmap.n_ents + (fmap.agent_task >= 0 ? 1 : 0);
 
   // ---- visiting order of the room triangles: front to back by their nearest possible depth, so
   // that the conservative occlusion tests fire early (the result does not depend on the order)
   {
     const int n0 = segs[0].count;
-    for (int t = tid; t < n0; t += MWB_RENDER_THREADS) {
+    for (int t = tid; t < n0; t += THREADS) {
       const TriRec& T = tris[t];
       const float x0 = (float)(T.bx & 0xFFFF), x1 = (float)((T.bx >> 16) + 1), y0 = (float)(T.by & 0xFFFF), y1 = (float)((T.by >> 16) + 1);
       zkey[t] = T.Zc + fminf(T.Za * x0, T.Za * x1) + fminf(T.Zb * y0, T.Zb * y1);
     }
     __syncthreads();
     if (n0 <= MWB_SORT_LIMIT) {
-      for (int t = tid; t < n0; t += MWB_RENDER_THREADS) {
+      for (int t = tid; t < n0; t += THREADS) {
         const float z = zkey[t];
         int rank = 0;
         for (int q = 0; q < n0; ++q) {
@@ -267,7 +272,7 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
         order[rank] = (uint16_t)t;
       }
     } else {
-      for (int t = tid; t < n0; t += MWB_RENDER_THREADS) order[t] = (uint16_t)t;
+      for (int t = tid; t < n0; t += THREADS) order[t] = (uint16_t)t;
     }
     __syncthreads();
   }
@@ -287,14 +292,21 @@ render_kernel(DevState S, RenderAssets A, uint8_t* __restrict__ obs, float* __re
   const int halves_y = (H + 3) >> 2;
   const int n_halves = tiles_x * halves_y, per_part = (n_halves + parts - 1) / parts;
   const int h_begin = part * per_part, h_end = min(n_halves, h_begin + per_part);
-  int hcol = (h_begin + warp) % tiles_x, hrow = (h_begin + warp) / tiles_x;
+  if (DYN) {
+    if (tid == 0) next_half = h_begin + WARPS;
+    __syncthreads();
+  }
+  int half = h_begin + warp;
 #pragma unroll 1
-  for (int half = h_begin + warp; half < h_end; half += MWB_RENDER_WARPS) {
+  while (half < h_end) {
+    const int hrow = half / tiles_x, hcol = half - hrow * tiles_x;
     const int tx0 = hcol << 3, ty0 = hrow << 2;
-    hcol += MWB_RENDER_WARPS;
-    while (hcol >= tiles_x) {
-      hcol -= tiles_x;
-      ++hrow;
+    if (DYN) {                 // claim the next half-tile now; the atomic's latency hides behind this one
+      int nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&next_half, 1);
+      half = __shfl_sync(0xffffffffu, nxt, 0);
+    } else {
+      half += WARPS;
     }
     const int px = tx0 + lx, py = ty0 + ly;
     PixelState<MSAA> P;

@@ -91,6 +91,17 @@ struct Camera {
   float za, zb;                  // z_clip = za * w_clip - zb
   float halfw, halfh;
   float light[3], lamb[3], ldif[3], sky[3];
+  int ortho;                     // 1: render_top_view's orthographic map projection
+  float osx, otx, osy, oty;      // x_clip = osx x + otx, y_clip = osy (-z) + oty, z_clip = -0.01 y, w = 1
+};
+
+// Which view a render launch draws: the agent's camera (render_obs, miniworld.py:1177-1221) or the
+// orthographic map of render_top_view (miniworld.py:1088-1175): glOrtho(l, r, b, t, -100, 100) under
+// the model-view that maps world (x, y, z) to eye (x, -z, y), plus the agent's marker triangle.
+struct ViewSpec {
+  int mode;                      // 0 = agent camera, 1 = top view
+  int render_agent;              // top view: draw Agent.render()'s triangle (entity.py:518-539)
+  double l, r, b, t;             // glOrtho extents (top view)
 };
 
 // The three camera angles of env i (heading, pitch, half the vertical field of view), float64.
@@ -100,6 +111,19 @@ MWB_DEV void camera_angles(const DevState& S, int i, double ang[3]) {
   ang[0] = S.ent_dir[as * N + i];
   ang[1] = d_div(d_mul(S.cam[2 * N + i], 3.141592653589793), 180.0);
   ang[2] = d_div(d_mul(S.cam[3 * N + i], 3.141592653589793), 360.0);
+}
+
+// view-independent part: viewport scale, sky colour, light
+MWB_DEV void camera_common(const DevState& S, int i, Camera& c) {
+  const size_t N = S.N;
+  c.halfw = 0.5f * (float)S.obs_w;
+  c.halfh = 0.5f * (float)S.obs_h;
+  for (int k = 0; k < 3; ++k) {
+    c.sky[k] = (float)S.envp[(0 + k) * N + i];
+    c.light[k] = (float)S.envp[(3 + k) * N + i];
+    c.ldif[k] = (float)S.envp[(6 + k) * N + i];
+    c.lamb[k] = (float)S.envp[(9 + k) * N + i];
+  }
 }
 
 // Camera of env i from trig = {cos, sin} of those angles.  Angles go through the glibc-exact
@@ -130,14 +154,25 @@ MWB_DEV Camera make_camera(const DevState& S, int i, const double trig[6]) {
   c.px = (float)d_div(cot, d_div((double)S.obs_w, (double)S.obs_h));
   c.za = (float)((MWB_FAR + MWB_NEAR) / (MWB_FAR - MWB_NEAR));
   c.zb = (float)(2.0 * MWB_FAR * MWB_NEAR / (MWB_FAR - MWB_NEAR));
-  c.halfw = 0.5f * (float)S.obs_w;
-  c.halfh = 0.5f * (float)S.obs_h;
-  for (int k = 0; k < 3; ++k) {
-    c.sky[k] = (float)S.envp[(0 + k) * N + i];
-    c.light[k] = (float)S.envp[(3 + k) * N + i];
-    c.ldif[k] = (float)S.envp[(6 + k) * N + i];
-    c.lamb[k] = (float)S.envp[(9 + k) * N + i];
-  }
+  c.ortho = 0;
+  c.osx = c.otx = c.osy = c.oty = 0.0f;
+  camera_common(S, i, c);
+  return c;
+}
+
+// render_top_view's camera: the projection matrix entries are formed in float64 and rounded once, as
+// glOrtho's GLdouble arguments end up in a float32 matrix.
+MWB_DEV Camera make_top_camera(const DevState& S, int i, const ViewSpec& v) {
+  Camera c;
+  c.ex = c.ey = c.ez = 0.0f;
+  c.sx = c.sy = c.sz = c.ux = c.uy = c.uz = c.fx = c.fy = c.fz = 0.0f;
+  c.px = c.py = c.za = c.zb = 0.0f;
+  c.ortho = 1;
+  c.osx = (float)d_div(2.0, d_sub(v.r, v.l));
+  c.otx = (float)(-d_div(d_add(v.r, v.l), d_sub(v.r, v.l)));
+  c.osy = (float)d_div(2.0, d_sub(v.t, v.b));
+  c.oty = (float)(-d_div(d_add(v.t, v.b), d_sub(v.t, v.b)));
+  camera_common(S, i, c);
   return c;
 }
 
@@ -162,15 +197,23 @@ MWB_DEV float dot3_rn(float ax, float ay, float az, float bx, float by, float bz
 }
 
 MWB_DEV HVert transform_vertex(const Camera& c, float x, float y, float z) {
-  float rx = f_sub(x, c.ex), ry = f_sub(y, c.ey), rz = f_sub(z, c.ez);
-  float xe = dot3_rn(c.sx, c.sy, c.sz, rx, ry, rz);
-  float ye = dot3_rn(c.ux, c.uy, c.uz, rx, ry, rz);
-  float w = dot3_rn(c.fx, c.fy, c.fz, rx, ry, rz);   // distance along the view axis
   HVert v;
+  float w;
+  if (c.ortho) {               // eye = (x, -z, y); clip = glOrtho row by row, w = 1
+    w = 1.0f;
+    v.xc = f_add(f_mul(c.osx, x), c.otx);
+    v.yc = f_add(f_mul(c.osy, -z), c.oty);
+    v.zc = f_mul((float)(-2.0 / 200.0), y);
+  } else {
+    float rx = f_sub(x, c.ex), ry = f_sub(y, c.ey), rz = f_sub(z, c.ez);
+    float xe = dot3_rn(c.sx, c.sy, c.sz, rx, ry, rz);
+    float ye = dot3_rn(c.ux, c.uy, c.uz, rx, ry, rz);
+    w = dot3_rn(c.fx, c.fy, c.fz, rx, ry, rz);   // distance along the view axis
+    v.xc = f_mul(c.px, xe);
+    v.yc = f_mul(c.py, ye);
+    v.zc = f_sub(f_mul(c.za, w), c.zb);
+  }
   v.w = w;
-  v.xc = f_mul(c.px, xe);
-  v.yc = f_mul(c.py, ye);
-  v.zc = f_sub(f_mul(c.za, w), c.zb);
   v.X = f_mul(f_add(v.xc, w), c.halfw);
   v.Y = f_mul(f_sub(w, v.yc), c.halfh);
   v.zeta = f_mul(0.5f, f_add(v.zc, w));
@@ -605,6 +648,7 @@ struct FrameMap {
   int ent_proto[MWB_MAX_DRAWN];
   int ent_kind[MWB_MAX_DRAWN];       // MWB_KIND_BOX / MWB_KIND_MESH
   int ent_task0[MWB_MAX_DRAWN];      // first task index (boxes), -1 for meshes
+  int agent_task;                    // task index of the agent's marker triangle (top view), else -1
 };
 
 struct EntPose {
@@ -631,7 +675,7 @@ MWB_DEV EntPose entity_pose(const DevState& S, int i, int e) {
   return p;
 }
 
-MWB_DEV FrameMap build_frame_map(const DevState& S, int i) {
+MWB_DEV FrameMap build_frame_map(const DevState& S, int i, bool agent_marker = false) {
   FrameMap m;
   const size_t N = S.N;
   m.n_quads = S.num_quads[geom_index(S, i)];
@@ -657,6 +701,7 @@ MWB_DEV FrameMap build_frame_map(const DevState& S, int i) {
       }
     }
   }
+  m.agent_task = agent_marker ? tasks++ : -1;   // drawn last (miniworld.py:1079-1080)
   m.n_tasks = tasks;
   return m;
 }
@@ -713,15 +758,21 @@ MWB_DEV bool room_triangle(const DevState& S, const RenderAssets& A, const mwb_q
   return true;
 }
 
-// triangle t (0..11) of a Box: face t / 2 in drawBox order (+z, -z, -x, +x, +y, -y), fan half t % 2
-MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput& in) {
-  const int f = t >> 1, half = t & 1;
-  const float hx = (float)(pr.size[0] / 2), sy = (float)pr.size[1], hz = (float)(pr.size[2] / 2);
-  // corner c of the face: sign pattern per drawBox (opengl.py:460-503)
-  // each entry: (x sign, y top?, z sign) for corners 0..3
+// corner v (0..3) of face f of drawBox (opengl.py:460-503; faces +z, -z, -x, +x, +y, -y): which end of
+// the box's x / z range (sign) and of its y range (top?) the vertex takes
+MWB_DEV void box_corner(int f, int v, int& sx, int& top, int& sz) {
   const signed char X[6][4] = {{1, -1, -1, 1}, {-1, 1, 1, -1}, {-1, -1, -1, -1}, {1, 1, 1, 1}, {1, 1, -1, -1}, {1, 1, -1, -1}};
   const signed char Y[6][4] = {{1, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 0, 0}, {1, 1, 1, 1}, {0, 0, 0, 0}};
   const signed char Z[6][4] = {{1, 1, 1, 1}, {-1, -1, -1, -1}, {1, -1, -1, 1}, {-1, 1, 1, -1}, {1, -1, -1, 1}, {-1, 1, 1, -1}};
+  sx = X[f][v];
+  top = Y[f][v];
+  sz = Z[f][v];
+}
+
+// triangle t (0..11) of a Box: face t / 2 in drawBox order, fan half t % 2
+MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput& in) {
+  const int f = t >> 1, half = t & 1;
+  const float hx = (float)(pr.size[0] / 2), sy = (float)pr.size[1], hz = (float)(pr.size[2] / 2);
   const float NX[6] = {0, 0, -1, 1, 0, 0}, NY[6] = {0, 0, 0, 0, 1, -1}, NZ[6] = {1, -1, 0, 0, 0, 0};
   // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = z c - x s
   const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
@@ -730,7 +781,9 @@ MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int v = k == 0 ? 0 : k + half;
-    const float x = X[f][v] > 0 ? hx : -hx, y = Y[f][v] ? sy : 0.0f, z = Z[f][v] > 0 ? hz : -hz;
+    int cx, top, cz;
+    box_corner(f, v, cx, top, cz);
+    const float x = cx > 0 ? hx : -hx, y = top ? sy : 0.0f, z = cz > 0 ? hz : -hz;
     in.pos[k][0] = f_add(f_add(f_mul(x, c), f_mul(z, s)), tx);
     in.pos[k][1] = f_add(y, ty);
     in.pos[k][2] = f_add(f_sub(f_mul(z, c), f_mul(x, s)), tz);
@@ -771,6 +824,50 @@ MWB_DEV void mesh_triangle(const RenderAssets& A, const mwb_proto& pr, const Ent
   in.tex = A.mesh_tex[base];   // -1 for ball_* / key_* (no map_Kd, objmesh.py:226-230)
 }
 
+// Agent.render() (entity.py:518-539): a red triangle at the top of the agent's cylinder pointing along
+// dir_vec; float64 vertex arithmetic as numpy evaluates it, rounded by glVertex3f.  It is untextured
+// (every entity draw leaves GL_TEXTURE_2D disabled) and lit with GL's *current normal*, which the
+// reference never sets here: it is whatever the previous draw left behind -- the last face normal of
+// drawBox (0, -1, 0), or the last vertex normal of the last mesh / wall quad, in object space.
+MWB_DEV void agent_triangle(const DevState& S, const RenderAssets& A, const FrameMap& m, const mwb_quad* quads, int i,
+                            TriInput& in) {
+  const size_t N = S.N;
+  const int as = S.agent_slot[i];
+  const mwb_proto& ap = S.protos[S.ent_proto[as * N + i]];
+  const double px = S.ent_px[as * N + i], py = d_add(S.ent_py[as * N + i], ap.height), pz = S.ent_pz[as * N + i];
+  const double d = S.ent_dir[as * N + i];
+  const double c = mwb_libm::cos_glibc(d), s = mwb_libm::sin_glibc(d);
+  const double r = ap.radius;
+  const double dvx = d_mul(c, r), dvz = d_mul(-s, r);          // dir_vec * radius
+  const double rvx = d_mul(s, r), rvz = d_mul(c, r);           // right_vec * radius
+  double vx[3], vz[3];
+  vx[0] = d_add(px, dvx);                                      // p0 = p + dv
+  vz[0] = d_add(pz, dvz);
+  vx[2] = d_add(px, d_mul(0.75, d_sub(rvx, dvx)));             // p1 = p + 0.75 (rv - dv)
+  vz[2] = d_add(pz, d_mul(0.75, d_sub(rvz, dvz)));
+  vx[1] = d_add(px, d_mul(0.75, d_sub(-rvx, dvx)));            // p2 = p + 0.75 (-rv - dv)
+  vz[1] = d_add(pz, d_mul(0.75, d_sub(-rvz, dvz)));            // submitted as p0, p2, p1
+  float n[3] = {0.0f, -1.0f, 0.0f};
+  if (m.n_ents > 0 && m.ent_kind[m.n_ents - 1] == MWB_KIND_MESH) {
+    const MeshDev& M = A.meshes[S.protos[m.ent_proto[m.n_ents - 1]].mesh_id];
+    const float* q = A.mesh_nrm + ((size_t)(M.first + M.count - 1) * 3 + 2) * 3;
+    n[0] = q[0]; n[1] = q[1]; n[2] = q[2];
+  } else if (m.n_ents == 0 && m.n_quads > 0) {
+    const mwb_quad& Q = quads[m.n_quads - 1];
+    n[0] = Q.nrm[0]; n[1] = Q.nrm[1]; n[2] = Q.nrm[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    in.pos[k][0] = (float)vx[k];
+    in.pos[k][1] = (float)py;
+    in.pos[k][2] = (float)vz[k];
+    in.uv[k][0] = in.uv[k][1] = 0.0f;
+    in.nrm[k][0] = n[0]; in.nrm[k][1] = n[1]; in.nrm[k][2] = n[2];
+    in.mat[k][0] = 1.0f; in.mat[k][1] = 0.0f; in.mat[k][2] = 0.0f;   // glColor3f(1, 0, 0)
+  }
+  in.tex = -1;
+}
+
 MWB_DEV const mwb_quad* env_quads(const DevState& S, int i) { return S.quads + (size_t)geom_index(S, i) * S.Q; }
 
 // shared-memory triangle task -> (segment, record); false if culled / nonexistent
@@ -780,6 +877,9 @@ MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camer
   if (task < 2 * m.n_quads) {
     seg = 0;
     if (!room_triangle(S, A, quads, i, task >> 1, task & 1, in)) return false;
+  } else if (task == m.agent_task) {
+    seg = 1 + m.n_ents;
+    agent_triangle(S, A, m, quads, i, in);
   } else {
     int k = 0;
     while (k + 1 < m.n_ents && (m.ent_task0[k] < 0 || task >= m.ent_task0[k] + 12)) ++k;

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 RULE_NONE, RULE_GOAL, RULE_PICKUP = 0, 1, 2
 SURF_WALL, SURF_FLOOR, SURF_CEIL = 0, 1, 2
 OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE, OP_MAZE = 0, 1, 2, 3, 4
@@ -119,6 +119,7 @@ EXPORTS = (
     "mwb_reset", "mwb_set_world", "mwb_step", "mwb_render_obs", "mwb_get_state",
     "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read", "mwb_set_maze", "mwb_get_geometry",
     "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
+    "mwb_render_top_view", "mwb_visible_ents",
 )
 
 _libs = {}
@@ -148,6 +149,8 @@ def load_library(lib_path=None):
     lib.mwb_set_world.argtypes = [vp, vp, C.c_int, vp]
     lib.mwb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mwb_render_obs.argtypes = [vp, vp, vp, vp]
+    lib.mwb_render_top_view.argtypes = [vp, C.POINTER(C.c_double), C.c_int, vp, vp]
+    lib.mwb_visible_ents.argtypes = [vp, vp, vp]
     lib.mwb_get_state.argtypes = [vp, C.POINTER(StateView)]
     lib.mwb_launch_count.argtypes = [vp]
     lib.mwb_launch_count.restype = C.c_int64
@@ -432,6 +435,15 @@ class Engine:
     def render(self, obs=None, depth=None, stream=None):
         self._check(self.lib.mwb_render_obs(self.h, _dev_or_host_ptr(obs), _dev_or_host_ptr(depth), stream))
 
+    def render_top_view(self, extents, obs, render_agent=True, stream=None):
+        """Map view of every env (reference render_top_view); extents = (min_x, max_x, min_z, max_z)."""
+        ext = (C.c_double * 4)(*[float(v) for v in extents])
+        self._check(self.lib.mwb_render_top_view(self.h, ext, int(bool(render_agent)), _dev_or_host_ptr(obs), stream))
+
+    def visible_ents(self, mask, stream=None):
+        """uint32[N] (numpy or CUDA tensor): bit e = entity slot e passes the reference's occlusion query."""
+        self._check(self.lib.mwb_visible_ents(self.h, _dev_or_host_ptr(mask), stream))
+
     def launch_count(self):
         return int(self.lib.mwb_launch_count(self.h))
 
@@ -526,3 +538,13 @@ class SingleEnvEngine:
         depth = np.zeros((self.H, self.W, 1), np.float32) if want_depth else None
         self.engine.render(obs=obs, depth=depth)
         return obs, depth
+
+    def render_top_view(self, extents, render_agent):
+        obs = np.zeros((self.H, self.W, 3), np.uint8)
+        self.engine.render_top_view(extents, obs, render_agent)
+        return obs
+
+    def visible_ents(self):
+        mask = np.zeros(1, np.uint32)
+        self.engine.visible_ents(mask)
+        return {ent for slot, ent in enumerate(self._slots) if (int(mask[0]) >> slot) & 1}

@@ -401,22 +401,71 @@ class MiniWorldEnv(gym.Env):
         self._push_world()
         return eng.render(want_depth=True)[1]
 
-    def render(self):
-        """render_mode="rgb_array": the agent's view at window_width x window_height (the
-        reference's vis_fb frame, miniworld.py:1340-1362).  The interactive window and the top
-        view are not part of this package."""
-        if self.render_mode != "rgb_array":
-            return None
-        if self.view != "agent":
-            raise NotImplementedError("only the agent view is rendered by the CUDA engine")
+    def top_view_extents(self, fb_width, fb_height):
+        """Scene extents of render_top_view after the aspect-ratio adjustment, float64 arithmetic of
+        the reference (miniworld.py:1109-1133): (min_x, max_x, min_z, max_z)."""
+        min_x, max_x = self.min_x - 1, self.max_x + 1
+        min_z, max_z = self.min_z - 1, self.max_z + 1
+        width, height = max_x - min_x, max_z - min_z
+        aspect = width / height
+        fb_aspect = fb_width / fb_height
+        if aspect > fb_aspect:
+            new_h = width / fb_aspect
+            h_diff = new_h - height
+            min_z -= h_diff / 2
+            max_z += h_diff / 2
+        elif aspect < fb_aspect:
+            new_w = height * fb_aspect
+            w_diff = new_w - width
+            min_x -= w_diff / 2
+            max_x += w_diff / 2
+        return float(min_x), float(max_x), float(min_z), float(max_z)
+
+    def render_top_view(self, frame_buffer=None, render_agent=True, return_scale=False):
+        """Orthographic map of the whole level, uint8[H, W, 3] (reference miniworld.py:1088-1175).
+        frame_buffer: None = observation size, "vis" = window size (the reference passes vis_fb)."""
+        if frame_buffer == "vis":
+            eng = self._require_vis_engine()
+            eng.push(self, full=True)
+        else:
+            eng = self._require_engine()
+            self._push_world()
+        ext = self.top_view_extents(eng.W, eng.H)
+        img = eng.render_top_view(ext, render_agent)
+        if not return_scale:
+            return img
+        x_scale, z_scale = eng.W / (ext[1] - ext[0]), eng.H / (ext[3] - ext[2])
+        return img, {"x_scale": x_scale, "z_scale": z_scale, "x_offset": int(0 - ext[0] * x_scale),
+                     "z_offset": int(0 - ext[2] * z_scale)}
+
+    def get_visible_ents(self):
+        """Set of entities whose occlusion query passes from the agent's camera (reference
+        miniworld.py:1238-1333: a 0.2 m box per entity against the rooms' depth)."""
+        eng = self._require_engine()
+        self._push_world()
+        return {e for e in eng.visible_ents() if any(e is x for x in self.entities)}
+
+    def _require_vis_engine(self):
         if self.device is None:
             raise RuntimeError("MiniWorldEnv was built with device=None (world generation only)")
         if self._vis_engine is None:
             from .engine import SingleEnvEngine
             self._vis_engine = SingleEnvEngine(self.window_width, self.window_height, self.msaa_samples, self.device,
                                                lib_path=self.engine_lib)
-        self._vis_engine.push(self, full=True)
-        return self._vis_engine.render(want_depth=False)[0]
+        return self._vis_engine
+
+    def render(self):
+        """render_mode="rgb_array": the human-view frame at window_width x window_height (the
+        reference's vis_fb image, miniworld.py:1340-1362) -- the agent's view, or the map when
+        view="top".  Samples per pixel follow msaa_samples (the reference asks for 16 and takes what the
+        driver grants).  The interactive pyglet window (render_mode="human") is not part of this package."""
+        if self.render_mode != "rgb_array":
+            return None
+        if self.view != "agent":
+            return self.render_top_view("vis")
+        eng = self._require_vis_engine()
+        eng.push(self, full=True)
+        return eng.render(want_depth=False)[0]
 
     def close(self):
         for name in ("_engine", "_vis_engine"):

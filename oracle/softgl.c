@@ -15,6 +15,8 @@
  *   MeshEnt.render              entity.py:150-161, objmesh.py:280-292
  *   Texture.load                opengl.py:147-184        RGB8 + mipmaps, LINEAR / LINEAR_MIPMAP_LINEAR, REPEAT
  *   FrameBuffer                 opengl.py:197-435        N-sample RGBA32F + DEPTH16, resolve, get_depth_map
+ *   render_top_view             miniworld.py:1088-1175   glOrtho map view (Scene.view = 1)
+ *   get_visible_ents            miniworld.py:1238-1333   GL_ANY_SAMPLES_PASSED queries (Scene.tri_query)
  *
  * PARITY STATUS: **unpinned**.  The reference ships no golden images and its pixels come out
  * of a third-party GL driver (pyglet<2 -> libGL; Mesa llvmpipe in its CI); neither exists in
@@ -117,6 +119,14 @@ typedef struct {
   const float* tri_uv;  /* [T][3][2] */
   const float* tri_rgb; /* [T][3][3] material (glColor / c3f) per vertex */
   const int* tri_tex;   /* [T] */
+  /* view: 0 = the agent's perspective camera; 1 = render_top_view: glOrtho(ortho[0..3] = l, r, b, t,
+   * near -100, far 100) under the model-view (x, y, z) -> (x, -z, y) (miniworld.py:1135-1162) */
+  int view;
+  double ortho[4];
+  /* occlusion queries (get_visible_ents): tri_query[t] = query id of triangle t or -1 (NULL: none);
+   * query_out[q] is set to 1 when any sample of a triangle of query q passes the depth test */
+  const int* tri_query;
+  uint8_t* query_out;
 } Scene;
 
 /* D3D standard sample patterns in image space (x right, y down), offsets from the pixel's
@@ -171,6 +181,15 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
   float Py = (float)cot, Px = (float)(cot / ((double)W / (double)H));
   float Za = (float)((ZFAR + ZNEAR) / (ZFAR - ZNEAR)), Zb = (float)(2.0 * ZFAR * ZNEAR / (ZFAR - ZNEAR));
   float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+  /* glOrtho's matrix entries: formed in double, stored as float32 */
+  float Osx = 0.0f, Otx = 0.0f, Osy = 0.0f, Oty = 0.0f, Osz = (float)(-2.0 / (100.0 - (-100.0)));
+  if (sc->view == 1) {
+    double l = sc->ortho[0], r = sc->ortho[1], b = sc->ortho[2], t = sc->ortho[3];
+    Osx = (float)(2.0 / (r - l));
+    Otx = (float)(-((r + l) / (r - l)));
+    Osy = (float)(2.0 / (t - b));
+    Oty = (float)(-((t + b) / (t - b)));
+  }
   float lpos[3], lamb[3], ldif[3], sky[3];
   for (int c = 0; c < 3; ++c) {
     lpos[c] = (float)sc->light_pos[c];
@@ -196,15 +215,24 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
       const float* p = sc->tri_pos + ((size_t)ti * 3 + k) * 3;
       const float* n = sc->tri_nrm + ((size_t)ti * 3 + k) * 3;
       const float* m = sc->tri_rgb + ((size_t)ti * 3 + k) * 3;
-      /* eye space: subtract the eye, project on (s, u, f) -- each op rounds to float32 */
-      float rx = p[0] - eye[0], ry = p[1] - eye[1], rz = p[2] - eye[2];
-      float xe = (Sv[0] * rx + Sv[1] * ry) + Sv[2] * rz;
-      float ye = (Uv[0] * rx + Uv[1] * ry) + Uv[2] * rz;
-      float we = (Fv[0] * rx + Fv[1] * ry) + Fv[2] * rz; /* = -z_eye = w_clip */
+      float we;
+      if (sc->view == 1) {
+        /* map view: eye = (x, -z, y) exactly (a permutation matrix), clip = glOrtho * eye, w = 1 */
+        we = 1.0f;
+        g[k].cx = Osx * p[0] + Otx;
+        g[k].cy = Osy * (-p[2]) + Oty;
+        g[k].cz = Osz * p[1];
+      } else {
+        /* eye space: subtract the eye, project on (s, u, f) -- each op rounds to float32 */
+        float rx = p[0] - eye[0], ry = p[1] - eye[1], rz = p[2] - eye[2];
+        float xe = (Sv[0] * rx + Sv[1] * ry) + Sv[2] * rz;
+        float ye = (Uv[0] * rx + Uv[1] * ry) + Uv[2] * rz;
+        we = (Fv[0] * rx + Fv[1] * ry) + Fv[2] * rz; /* = -z_eye = w_clip */
+        g[k].cx = Px * xe;
+        g[k].cy = Py * ye;
+        g[k].cz = Za * we - Zb;
+      }
       g[k].W = we;
-      g[k].cx = Px * xe;
-      g[k].cy = Py * ye;
-      g[k].cz = Za * we - Zb;
       g[k].X = (g[k].cx + we) * hw; /* ((x_ndc + 1) W / 2) w */
       g[k].Y = (we - g[k].cy) * hh; /* ((1 - y_ndc) H / 2) w : row 0 at the top */
       g[k].Z = 0.5f * (g[k].cz + we);
@@ -288,6 +316,7 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
           }
         }
         if (!pass) continue;
+        if (sc->tri_query && sc->query_out && sc->tri_query[ti] >= 0) sc->query_out[sc->tri_query[ti]] = 1;
         /* fragment colour, evaluated once at the pixel centre (multisampling, not supersampling) */
         float cxp = (float)px + 0.5f, cyp = (float)py + 0.5f;
         float e[3], esum = 0.0f;

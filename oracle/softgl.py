@@ -32,7 +32,8 @@ class _Scene(C.Structure):
                 ("sky", C.c_double * 3), ("light_pos", C.c_double * 3), ("light_color", C.c_double * 3),
                 ("light_ambient", C.c_double * 3), ("width", C.c_int), ("height", C.c_int), ("samples", C.c_int),
                 ("num_tris", C.c_int), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("tri_uv", C.c_void_p),
-                ("tri_rgb", C.c_void_p), ("tri_tex", C.c_void_p)]
+                ("tri_rgb", C.c_void_p), ("tri_tex", C.c_void_p),
+                ("view", C.c_int), ("ortho", C.c_double * 4), ("tri_query", C.c_void_p), ("query_out", C.c_void_p)]
 
 
 _lib = None
@@ -93,11 +94,15 @@ def _rot_y(v, c, s):
     return (f32(f32(x * c) + f32(z * s)), y, f32(f32(z * c) - f32(x * s)))
 
 
-def draw_list(env, tex_index):
-    """Triangles of one frame in submission order.  tex_index(texture_object) -> oracle id."""
+def draw_list(env, tex_index, agent_marker=False, rooms_only=False):
+    """Triangles of one frame in submission order.  tex_index(texture_object) -> oracle id.
+    agent_marker: append Agent.render()'s triangle (top view, entity.py:518-539); rooms_only: stop after
+    the rooms (get_visible_ents draws no entity, only their query boxes)."""
     P, Nn, UV, RGB, TX = [], [], [], [], []
+    last_normal = [(0.0, 1.0, 0.0)]      # GL's "current normal": what the latest glNormal3f / array draw left behind
 
     def emit(verts, normals, uvs, color, tex):
+        last_normal[0] = tuple(float(v) for v in normals[-1])
         for a, b, c in _fan(len(verts)):
             P.append([verts[a], verts[b], verts[c]])
             Nn.append([normals[a], normals[b], normals[c]])
@@ -132,6 +137,7 @@ def draw_list(env, tex_index):
                     vs.append((f32(rx + t[0]), f32(ry + t[1]), f32(rz + t[2])))
                 nn = _rot_y(nrm, c, s)
                 emit(vs, [nn] * 4, [(0.0, 0.0)] * 4, col, -1)
+            last_normal[0] = (0.0, -1.0, 0.0)     # glNormal3f of drawBox's last face, object space
         elif hasattr(ent, "mesh"):
             # glTranslatef(pos) glScalef(s, s, s) glRotatef(dir): v' = pos + s * (R v); the normal
             # goes through the inverse transpose, R n / s, and is NOT renormalised
@@ -161,24 +167,116 @@ def draw_list(env, tex_index):
             UV.extend(np.asarray(Tm, np.float32))
             RGB.extend(np.asarray(Cm, np.float32))
             TX.extend(int(v) for v in tri_tex)
+            last_normal[0] = tuple(float(v) for v in np.asarray(Nm, np.float32).reshape(-1, 3)[-1])   # object space
 
     # display list first (static entities), then the dynamic ones, both in list order
-    for ent in env.entities:
-        if ent.is_static and ent is not env.agent:
-            draw_entity(ent)
-    for ent in env.entities:
-        if not ent.is_static and ent is not env.agent:
-            draw_entity(ent)
+    if not rooms_only:
+        for ent in env.entities:
+            if ent.is_static and ent is not env.agent:
+                draw_entity(ent)
+        for ent in env.entities:
+            if not ent.is_static and ent is not env.agent:
+                draw_entity(ent)
+    if agent_marker:
+        # Agent.render(): float64 numpy arithmetic, glVertex3f rounds; red, untextured, lit with the
+        # current normal (never set by the reference here: a state leak from the previous draw)
+        a = env.agent
+        dirv = np.array([math.cos(a.dir), 0.0, -math.sin(a.dir)])
+        right = np.array([math.sin(a.dir), 0.0, math.cos(a.dir)])
+        p = np.asarray(a.pos, np.float64) + np.array([0.0, 1.0, 0.0]) * a.height
+        dv, rv = dirv * a.radius, right * a.radius
+        p0, p1, p2 = p + dv, p + 0.75 * (rv - dv), p + 0.75 * (-rv - dv)
+        tri = [tuple(f32(v) for v in q) for q in (p0, p2, p1)]
+        n = last_normal[0]
+        P.append(tri)
+        Nn.append([n, n, n])
+        UV.append([(0.0, 0.0)] * 3)
+        RGB.append([(1.0, 0.0, 0.0)] * 3)
+        TX.append(-1)
     T = len(P)
     return (np.asarray(P, np.float32).reshape(T, 3, 3), np.asarray(Nn, np.float32).reshape(T, 3, 3),
             np.asarray(UV, np.float32).reshape(T, 3, 2), np.asarray(RGB, np.float32).reshape(T, 3, 3),
             np.asarray(TX, np.int32))
 
 
+def _query_boxes(env):
+    """get_visible_ents' drawBox(pos -/+ 0.1, pos.y .. pos.y + 0.2) per entity except the agent, world space
+    (miniworld.py:1299-1314): (triangles float32[12 Q, 3, 3], query id per triangle, entity per query)."""
+    tris, qid, ents = [], [], []
+    for ent in env.entities:
+        if ent is env.agent:
+            continue
+        q = len(ents)
+        ents.append(ent)
+        pos = ent.pos
+        x0, x1 = f32(pos[0] - 0.1), f32(pos[0] + 0.1)
+        y0, y1 = f32(pos[1]), f32(pos[1] + 0.2)
+        z0, z1 = f32(pos[2] - 0.1), f32(pos[2] + 0.1)
+        faces = [[(x1, y1, z1), (x0, y1, z1), (x0, y0, z1), (x1, y0, z1)], [(x0, y1, z0), (x1, y1, z0), (x1, y0, z0), (x0, y0, z0)],
+                 [(x0, y1, z1), (x0, y1, z0), (x0, y0, z0), (x0, y0, z1)], [(x1, y1, z0), (x1, y1, z1), (x1, y0, z1), (x1, y0, z0)],
+                 [(x1, y1, z1), (x1, y1, z0), (x0, y1, z0), (x0, y1, z1)], [(x1, y0, z0), (x1, y0, z1), (x0, y0, z1), (x0, y0, z0)]]
+        for quad in faces:
+            for a, b, c in _fan(4):
+                tris.append([quad[a], quad[b], quad[c]])
+                qid.append(q)
+    return np.asarray(tris, np.float32).reshape(-1, 3, 3), np.asarray(qid, np.int32), ents
+
+
+def visible_ents(env, texset, tex_index, width=80, height=60, samples=8):
+    """Oracle of MiniWorldEnv.get_visible_ents: the set of entities whose occlusion query passes."""
+    pos, nrm, uv, rgb, tx = draw_list(env, tex_index, rooms_only=True)
+    bpos, qid, ents = _query_boxes(env)
+    nb = len(qid)
+    if nb == 0:
+        return set()
+    query = np.concatenate([np.full(len(tx), -1, np.int32), qid])
+    pos = np.concatenate([pos, bpos]).astype(np.float32)
+    nrm = np.concatenate([nrm, np.tile(np.float32([0, 1, 0]), (nb, 3, 1))]).astype(np.float32)
+    uv = np.concatenate([uv, np.zeros((nb, 3, 2), np.float32)]).astype(np.float32)
+    rgb = np.concatenate([rgb, np.ones((nb, 3, 3), np.float32)]).astype(np.float32)
+    tx = np.concatenate([tx, np.full(nb, -1, np.int32)]).astype(np.int32)
+    flags = np.zeros(len(ents), np.uint8)
+    _run(env, texset, (pos, nrm, uv, rgb, tx), width, height, samples, query=query, query_out=flags)
+    return {e for e, f in zip(ents, flags) if f}
+
+
+def top_view_extents(env, fb_width, fb_height):
+    """(min_x, max_x, min_z, max_z) of render_top_view after the aspect adjustment (miniworld.py:1109-1133)."""
+    min_x, max_x, min_z, max_z = env.min_x - 1, env.max_x + 1, env.min_z - 1, env.max_z + 1
+    width, height = max_x - min_x, max_z - min_z
+    aspect, fb_aspect = width / height, fb_width / fb_height
+    if aspect > fb_aspect:
+        h_diff = width / fb_aspect - height
+        min_z -= h_diff / 2
+        max_z += h_diff / 2
+    elif aspect < fb_aspect:
+        w_diff = height * fb_aspect - width
+        min_x -= w_diff / 2
+        max_x += w_diff / 2
+    return float(min_x), float(max_x), float(min_z), float(max_z)
+
+
+def render_top_view(env, texset, tex_index, width=80, height=60, samples=8, render_agent=True):
+    """Oracle of MiniWorldEnv.render_top_view: rgb u8[H, W, 3]."""
+    lst = draw_list(env, tex_index, agent_marker=render_agent)
+    x0, x1, z0, z1 = top_view_extents(env, width, height)
+    return _run(env, texset, lst, width, height, samples, ortho=(x0, x1, -z1, -z0))[0]
+
+
 def render(env, texset, tex_index, width=80, height=60, samples=8, want_codes=False):
     """Oracle observation of `env` (reference env or host mirror): (rgb u8[H,W,3], depth f32[H,W,1])."""
-    pos, nrm, uv, rgb, tx = draw_list(env, tex_index)
+    return _run(env, texset, draw_list(env, tex_index), width, height, samples, want_codes=want_codes)
+
+
+def _run(env, texset, lst, width, height, samples, want_codes=False, ortho=None, query=None, query_out=None):
+    pos, nrm, uv, rgb, tx = lst
     sc = _Scene()
+    if ortho is not None:
+        sc.view = 1
+        for k in range(4):
+            sc.ortho[k] = float(ortho[k])
+    if query is not None:
+        sc.tri_query, sc.query_out = query.ctypes.data, query_out.ctypes.data
     a = env.agent
     for k in range(3):
         sc.pos[k] = float(a.pos[k])

@@ -92,3 +92,30 @@ def test_render_mode_and_wrappers_on_host_sim(hostsim_path):
     s.step(0)
     for e in (w, g, s):
         e.close()
+
+
+@pytest.mark.parametrize("level", ["MiniWorld-Hallway-v0", "MiniWorld-FourRooms-v0", "MiniWorld-PickupObjects-v0",
+                                   "MiniWorld-ThreeRooms-v0"])
+def test_top_view_and_visible_ents_match_oracle(hostsim_path, softgl_lib, level):
+    """render_top_view / get_visible_ents (reference miniworld.py:1088-1175, 1238-1333): kernels' arithmetic on
+    the CPU vs the immediate-mode oracle (depth-buffered draws with GL_ANY_SAMPLES_PASSED bookkeeping)."""
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.envs import LEVELS
+    env = LEVELS[level](engine_lib=hostsim_path)
+    seen = 0
+    for seed in (3, 4):
+        env.reset(seed=seed)
+        for _ in range(4):
+            env.step(env.action_space.sample())
+        ts = softgl_lib.TextureSet([t.texels for t in Texture.registry])
+        top = env.render_top_view()
+        ref = softgl_lib.render_top_view(env, ts, lambda tex: tex.tex_id)
+        assert np.abs(top.astype(int) - ref.astype(int)).max() <= 1
+        assert (top == ref).mean() > 0.999 and 0 < top.mean() < 255
+        vis = env.get_visible_ents()
+        assert vis == softgl_lib.visible_ents(env, ts, lambda tex: tex.tex_id)
+        seen += len(vis)
+        ts.close()
+    img, scale = env.render_top_view(return_scale=True)
+    assert img.shape == (60, 80, 3) and scale["x_scale"] > 0 and scale["z_scale"] > 0
+    env.close()
