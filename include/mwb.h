@@ -293,6 +293,12 @@ int mwb_set_world(mwb_handle* h, const int32_t* env_ids, int n, const mwb_world*
 int mwb_step(mwb_handle* h, const int32_t* actions, const double* step_params, uint8_t* obs,
              float* depth, double* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* StochasticActionWrapper (reference wrappers.py:49-71) applied inside mwb_step: before an env steps, one
+ * np_random.uniform() is drawn from ITS stream; if it is not below `prob` the action is replaced by
+ * `random_action`, or, when that is negative, by np_random.integers(0, 6).  Envs that reset in this
+ * step draw nothing.  enabled = 0 turns it off (the default). */
+int mwb_set_action_noise(mwb_handle* h, int enabled, double prob, int random_action);
+
 /* render_obs / render_depth without stepping (observation returned by reset()) */
 int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* stream);
 
@@ -310,6 +316,14 @@ int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream);
 
 /* ---- state exchange (env.agent.pos, env.entities[i].pos ... views; checkpointing) ------ */
 int mwb_get_state(mwb_handle* h, const mwb_state_view* out);
+
+/* ---- checkpointing: the complete restorable state of all N envs (entity lists, counters, camera and
+ * lighting parameters, numpy streams, pending auto-resets, geometry on the device) as one host blob.
+ * Restoring into a handle created with the same configuration and level definition resumes every env
+ * bit for bit.  (The reference has no equivalent: its state lives in Python objects.) */
+int mwb_snapshot_size(mwb_handle* h, size_t* bytes);
+int mwb_snapshot(mwb_handle* h, void* blob, size_t bytes);
+int mwb_restore(mwb_handle* h, const void* blob, size_t bytes);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mwb_launch_count(mwb_handle* h);

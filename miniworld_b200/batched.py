@@ -235,6 +235,23 @@ class BatchedMiniWorld:
         self.engine.render(depth=d, stream=torch.cuda.current_stream(self.device).cuda_stream)
         return d
 
+    def snapshot(self):
+        """Checkpoint of all envs (numpy uint8 blob); `restore` resumes them bit for bit."""
+        if not self.device_reset:
+            raise TypeError("snapshot covers the device-resident state; host-reset levels keep RNG streams in Python")
+        return self.engine.snapshot()
+
+    def restore(self, blob):
+        self.engine.restore(blob)
+        self._seeded = True
+
+    def set_action_noise(self, prob=0.9, random_action=None):
+        """Device-side StochasticActionWrapper (reference wrappers.py:49-71) for every env: the replacement draws
+        come from each env's own numpy stream, in the order the wrapper would make them.  prob=None disables."""
+        if not self.device_reset and prob is not None:
+            raise TypeError("action noise needs the env streams on the device (levels with a device reset program)")
+        self.engine.set_action_noise(prob, random_action)
+
     def render_top_view(self, render_agent=True, out=None):
         """Map view of every env, uint8 [N, H, W, 3] (reference render_top_view, miniworld.py:1088-1175).
         Extents come from the level definition (all envs of a level share them).  `out`: optional numpy

@@ -152,6 +152,12 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
     o.terminated = 0;
     o.truncated = 0;
   } else {
+    int action = actions[i];
+    if (S.act_noise) {            // wrapper.action() runs before env.step() draws its three parameters
+      NpRng r = load_rng(S, i);
+      if (!(rng_uniform(r, 0.0, 1.0) < S.act_prob)) action = S.act_random >= 0 ? S.act_random : (int)rng_integers(r, 6u);
+      store_rng(S, i, r);
+    }
     double fs, fd, ts;
     if (step_params) {
       fs = step_params[i * 3 + 0];
@@ -168,7 +174,7 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
       fd = S.params.forward_drift;
       ts = S.params.turn_step;
     }
-    o = physics_step(S, i, actions[i], fs, fd, ts);
+    o = physics_step(S, i, action, fs, fd, ts);
     if (o.terminated || o.truncated) {
       if (S.autoreset) S.needs_reset[i] = 1;
 #ifdef __CUDA_ARCH__
@@ -1118,6 +1124,16 @@ extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* s
   return finish_outputs(h, obs, obs_host, depth, depth_host, nullptr, nullptr, nullptr, s, stream != nullptr);
 }
 
+extern "C" int mwb_set_action_noise(mwb_handle* h, int enabled, double prob, int random_action) {
+  if (!h) return fail(MWB_EINVAL, "null handle");
+  if (enabled && !(prob >= 0.0 && prob <= 1.0)) return fail(MWB_EINVAL, "prob must be in [0, 1]");
+  if (enabled && random_action > 7) return fail(MWB_EINVAL, "random_action must be an Actions value (0..7) or negative");
+  h->S.act_noise = enabled != 0;
+  h->S.act_prob = prob;
+  h->S.act_random = random_action;
+  return MWB_OK;
+}
+
 extern "C" int mwb_render_top_view(mwb_handle* h, const double extents[4], int render_agent, uint8_t* obs, void* stream) {
   if (!h || !extents || !obs) return fail(MWB_EINVAL, "null argument");
   if (!(extents[1] > extents[0]) || !(extents[3] > extents[2])) return fail(MWB_EINVAL, "empty extents");
@@ -1190,6 +1206,86 @@ extern "C" int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream) {
   } else if (!stream) {
     if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
   }
+  return MWB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: snapshot / restore
+// Every array that changes while episodes run (entity lists, counters, camera / lighting parameters, RNG
+// streams, pending-reset flags) plus the geometry currently on the device, in one fixed order.
+struct SnapHeader {
+  uint32_t magic, abi;
+  int32_t N, E, R, Q, S, G;
+  uint64_t bytes;
+};
+
+static void snapshot_arrays(mwb_handle* h, std::vector<std::pair<void*, size_t>>& v) {
+  const DevState& S = h->S;
+  const size_t N = S.N, E = S.E, G = S.shared_geom ? 1 : N;
+#define SA(field, count) v.push_back(std::make_pair((void*)S.field, (size_t)(count) * sizeof(*S.field)))
+  SA(ent_proto, E * N); SA(ent_px, E * N); SA(ent_py, E * N); SA(ent_pz, E * N); SA(ent_dir, E * N);
+  SA(ent_col, E * 3 * N); SA(num_slots, N); SA(agent_slot, N); SA(carrying, N); SA(step_count, N);
+  SA(num_picked, N); SA(needs_reset, N); SA(episodes_done, 1); SA(cam, 4 * N); SA(envp, 12 * N);
+  SA(ghost_slot, N); SA(ghost_proto, N); SA(ghost_pose, 4 * N); SA(ghost_col, 3 * N);
+  SA(rng_s_hi, N); SA(rng_s_lo, N); SA(rng_inc_hi, N); SA(rng_inc_lo, N); SA(rng_has32, N); SA(rng_cache, N);
+  SA(num_rooms, G); SA(num_quads, G); SA(num_segs, G);
+  SA(rooms, G * S.R); SA(quads, G * S.Q); SA(segs, G * S.S); SA(room_tex, N * S.R * 3);
+#undef SA
+}
+
+static SnapHeader snapshot_header(mwb_handle* h) {
+  std::vector<std::pair<void*, size_t>> v;
+  snapshot_arrays(h, v);
+  SnapHeader hd;
+  hd.magic = 0x5342574du;   // "MWBS"
+  hd.abi = MWB_ABI_VERSION;
+  hd.N = h->S.N; hd.E = h->S.E; hd.R = h->S.R; hd.Q = h->S.Q; hd.S = h->S.S;
+  hd.G = h->S.shared_geom ? 1 : h->S.N;
+  hd.bytes = sizeof(SnapHeader);
+  for (size_t k = 0; k < v.size(); ++k) hd.bytes += v[k].second;
+  return hd;
+}
+
+extern "C" int mwb_snapshot_size(mwb_handle* h, size_t* bytes) {
+  if (!h || !bytes) return fail(MWB_EINVAL, "null argument");
+  *bytes = (size_t)snapshot_header(h).bytes;
+  return MWB_OK;
+}
+
+extern "C" int mwb_snapshot(mwb_handle* h, void* blob, size_t bytes) {
+  if (!h || !blob) return fail(MWB_EINVAL, "null argument");
+  const SnapHeader hd = snapshot_header(h);
+  if (bytes < hd.bytes) return fail(MWB_ECAPACITY, "snapshot buffer too small");
+  std::vector<std::pair<void*, size_t>> v;
+  snapshot_arrays(h, v);
+  unsigned char* p = (unsigned char*)blob;
+  memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  for (size_t k = 0; k < v.size(); ++k) {
+    if (d2h(p, v[k].first, v[k].second, h->stream) != 0) return fail(MWB_ECUDA, "readback failed");
+    p += v[k].second;
+  }
+  if (sync_stream(h->stream) != 0) return fail(MWB_ECUDA, "sync failed");
+  return MWB_OK;
+}
+
+extern "C" int mwb_restore(mwb_handle* h, const void* blob, size_t bytes) {
+  if (!h || !blob) return fail(MWB_EINVAL, "null argument");
+  const SnapHeader want = snapshot_header(h);
+  SnapHeader hd;
+  if (bytes < sizeof(hd)) return fail(MWB_EINVAL, "not a snapshot");
+  memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != want.magic || hd.abi != want.abi) return fail(MWB_EABI, "snapshot from another ABI version");
+  if (hd.N != want.N || hd.E != want.E || hd.R != want.R || hd.Q != want.Q || hd.S != want.S || hd.G != want.G ||
+      hd.bytes != want.bytes || bytes < hd.bytes)
+    return fail(MWB_EINVAL, "snapshot does not match this handle's configuration");
+  std::vector<std::pair<void*, size_t>> v;
+  snapshot_arrays(h, v);
+  const unsigned char* p = (const unsigned char*)blob + sizeof(hd);
+  for (size_t k = 0; k < v.size(); ++k) {
+    if (h2d(v[k].first, p, v[k].second, h->stream) != 0) return fail(MWB_ECUDA, "upload failed");
+    p += v[k].second;
+  }
+  if (sync_stream(h->stream) != 0) return fail(MWB_ECUDA, "sync failed");
   return MWB_OK;
 }
 

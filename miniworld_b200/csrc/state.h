@@ -77,6 +77,10 @@ struct DevState {
   int32_t max_episode_steps;
   int32_t autoreset;
   double near_extra;            // 1.1 * max_forward_step
+  // StochasticActionWrapper on the device (reference wrappers.py:49-71): per step one uniform() draw from
+  // the env's own stream; below act_prob the chosen action stands, else act_random (< 0: integers(0, 6))
+  int32_t act_noise, act_random;
+  double act_prob;
 };
 
 MWB_DEV int geom_index(const DevState& S, int i) { return S.shared_geom ? 0 : i; }

@@ -119,7 +119,8 @@ EXPORTS = (
     "mwb_reset", "mwb_set_world", "mwb_step", "mwb_render_obs", "mwb_get_state",
     "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read", "mwb_set_maze", "mwb_get_geometry",
     "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
-    "mwb_render_top_view", "mwb_visible_ents",
+    "mwb_render_top_view", "mwb_visible_ents", "mwb_set_action_noise",
+    "mwb_snapshot_size", "mwb_snapshot", "mwb_restore",
 )
 
 _libs = {}
@@ -151,6 +152,10 @@ def load_library(lib_path=None):
     lib.mwb_render_obs.argtypes = [vp, vp, vp, vp]
     lib.mwb_render_top_view.argtypes = [vp, C.POINTER(C.c_double), C.c_int, vp, vp]
     lib.mwb_visible_ents.argtypes = [vp, vp, vp]
+    lib.mwb_set_action_noise.argtypes = [vp, C.c_int, C.c_double, C.c_int]
+    lib.mwb_snapshot_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.mwb_snapshot.argtypes = [vp, vp, C.c_size_t]
+    lib.mwb_restore.argtypes = [vp, vp, C.c_size_t]
     lib.mwb_get_state.argtypes = [vp, C.POINTER(StateView)]
     lib.mwb_launch_count.argtypes = [vp]
     lib.mwb_launch_count.restype = C.c_int64
@@ -434,6 +439,23 @@ class Engine:
 
     def render(self, obs=None, depth=None, stream=None):
         self._check(self.lib.mwb_render_obs(self.h, _dev_or_host_ptr(obs), _dev_or_host_ptr(depth), stream))
+
+    def snapshot(self):
+        """uint8 array holding the restorable state of every env (mwb_snapshot)."""
+        n = C.c_size_t()
+        self._check(self.lib.mwb_snapshot_size(self.h, C.byref(n)))
+        blob = np.zeros(n.value, np.uint8)
+        self._check(self.lib.mwb_snapshot(self.h, C.c_void_p(blob.ctypes.data), n.value))
+        return blob
+
+    def restore(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        self._check(self.lib.mwb_restore(self.h, C.c_void_p(blob.ctypes.data), blob.size))
+
+    def set_action_noise(self, prob=None, random_action=None):
+        """StochasticActionWrapper inside the step kernel; prob=None switches it off."""
+        self._check(self.lib.mwb_set_action_noise(self.h, int(prob is not None), float(prob or 0.0),
+                                                  -1 if random_action is None else int(random_action)))
 
     def render_top_view(self, extents, obs, render_agent=True, stream=None):
         """Map view of every env (reference render_top_view); extents = (min_x, max_x, min_z, max_z)."""

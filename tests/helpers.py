@@ -132,3 +132,76 @@ def run_single_env_trajectory(name, g, lib_path=None, envs=2, steps=120, device=
             obs = obs["obs"]
         assert obs.shape == (60, 80, 3) and 0 < obs.mean() < 255
         env.close()
+
+
+def noise_parity(lib_path, n=4, steps=80, prob=0.6, random_action=None):
+    """Device-side StochasticActionWrapper == the wrapper around the drop-in single env, draw for draw."""
+    from miniworld_b200.batched import BatchedMiniWorld
+    from miniworld_b200.engine import RNG_DTYPE, rng_state_of
+    from miniworld_b200.envs import Hallway
+    from miniworld_b200.wrappers import StochasticActionWrapper
+    env = BatchedMiniWorld("MiniWorld-Hallway-v0", num_envs=n, domain_rand=True, autoreset=False, lib_path=lib_path)
+    ids = np.arange(n, dtype=np.int32)
+    env.engine.seed(ids, np.array([rng_state_of(1000 + i) for i in range(n)], RNG_DTYPE))
+    env.engine.reset(None)
+    env.set_action_noise(prob, random_action)
+    singles = [StochasticActionWrapper(Hallway(domain_rand=True, engine_lib=lib_path), prob=prob, random_action=random_action)
+               for _ in range(n)]
+    for i, s in enumerate(singles):
+        s.reset(seed=1000 + i)
+    acts = np.random.default_rng(7).integers(0, 3, size=(steps, n), dtype=np.int32)
+    alive = np.ones(n, bool)
+    replaced = 0
+    for t in range(steps):
+        out = env.step_host(acts[t], render=False)
+        st = env.get_state()
+        for i, s in enumerate(singles):
+            if not alive[i]:
+                continue
+            _, r, te, tr, _ = s.step(int(acts[t, i]))
+            a = s.env.agent
+            assert np.array_equal(st["agent_pos"][i], a.pos) and st["agent_dir"][i] == a.dir, (t, i)
+            assert out["reward"][i] == r and bool(out["terminated"][i]) == te and bool(out["truncated"][i]) == tr
+            alive[i] = not (te or tr)
+        if not alive.any():
+            break
+    for s in singles:
+        s.close()
+    env.close()
+
+
+def snapshot_roundtrip(level, lib_path, n=6, domain_rand=True, before=25, after=40, **kw):
+    """step -> snapshot -> step (recorded) -> restore -> step again: identical; also into a fresh handle."""
+    def make():
+        e = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=True, lib_path=lib_path, **kw)
+        return e
+    env = make()
+    ids = np.arange(n, dtype=np.int32)
+    env.engine.seed(ids, np.array([rng_state_of(2000 + i) for i in range(n)], RNG_DTYPE))
+    env.engine.reset(None)
+    nact = env.action_space.n
+    acts = np.random.default_rng(3).integers(0, nact, size=(before + after, n), dtype=np.int32)
+    for t in range(before):
+        env.step_host(acts[t], render=False)
+    blob = env.snapshot()
+
+    def run(e):
+        rec = []
+        for t in range(before, before + after):
+            o = e.step_host(acts[t], render=False)
+            st = e.get_state(rng=True)
+            rec.append((o["reward"].copy(), o["terminated"].copy(), o["truncated"].copy(), st["agent_pos"].copy(),
+                        st["agent_dir"].copy(), st["step_count"].copy(), st["rng"].copy()))
+        return rec
+    first = run(env)
+    env.restore(blob)
+    second = run(env)
+    fresh = make()
+    fresh.restore(blob)
+    third = run(fresh)
+    for a, b, c in zip(first, second, third):
+        for x, y, z in zip(a, b, c):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+    assert any(r[1].any() or r[2].any() for r in first) or after < 100   # episodes may end inside the window
+    fresh.close()
+    env.close()

@@ -161,3 +161,17 @@ def test_single_env_frames_match_oracle(libmwb_path, softgl_lib, level, kw):
                 assert diff.max() <= 1, "%s seed %d step %d: %d values off by > 1" % (level, seed, t, (diff > 1).sum())
                 assert np.array_equal(depth, env.render_depth())
     env.close()
+
+
+def test_device_action_noise_follows_wrapper_gpu(libmwb_path):
+    """mwb_set_action_noise (StochasticActionWrapper inside K1) vs the wrapper around the drop-in env."""
+    from helpers import noise_parity
+    noise_parity(libmwb_path, n=6, steps=120)
+    noise_parity(libmwb_path, n=2, steps=40, prob=0.3, random_action=1)
+
+
+@pytest.mark.parametrize("level", ["MiniWorld-FourRooms-v0", "MiniWorld-MazeS3-v0", "MiniWorld-PickupObjects-v0"])
+def test_snapshot_restore_resumes_bit_exact_gpu(libmwb_path, level):
+    """mwb_snapshot / mwb_restore: a restored handle (same or fresh) continues every env bit for bit."""
+    from helpers import snapshot_roundtrip
+    snapshot_roundtrip(level, libmwb_path, n=32, before=60, after=120)

@@ -119,3 +119,15 @@ def test_top_view_and_visible_ents_match_oracle(hostsim_path, softgl_lib, level)
     img, scale = env.render_top_view(return_scale=True)
     assert img.shape == (60, 80, 3) and scale["x_scale"] > 0 and scale["z_scale"] > 0
     env.close()
+
+
+def test_device_action_noise_follows_wrapper(hostsim_path):
+    from helpers import noise_parity
+    noise_parity(hostsim_path)
+    noise_parity(hostsim_path, n=2, steps=40, prob=0.3, random_action=1)
+
+
+@pytest.mark.parametrize("level", ["MiniWorld-FourRooms-v0", "MiniWorld-MazeS3-v0", "MiniWorld-PickupObjects-v0"])
+def test_snapshot_restore_resumes_bit_exact(hostsim_path, level):
+    from helpers import snapshot_roundtrip
+    snapshot_roundtrip(level, hostsim_path, n=4, before=20, after=30)
