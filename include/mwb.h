@@ -293,6 +293,16 @@ int mwb_set_world(mwb_handle* h, const int32_t* env_ids, int n, const mwb_world*
 int mwb_step(mwb_handle* h, const int32_t* actions, const double* step_params, uint8_t* obs,
              float* depth, double* reward, uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* Observation layout written by the render kernel's epilogue (all `obs` arguments of this header):
+ *   MWB_OBS_HWC_U8    uint8 [N][H][W][3]  MiniWorldEnv.render_obs (default)
+ *   MWB_OBS_CWH_U8    uint8 [N][3][W][H]  PyTorchObsWrapper.observation: transpose(2, 1, 0) (wrappers.py:24-25)
+ *   MWB_OBS_GREY_F64  double [N][H][W][1] GreyscaleWrapper.observation: 0.30 R + 0.59 G + 0.11 B in float64,
+ *                                         as numpy evaluates it on the uint8 frame (wrappers.py:43-46)      */
+#define MWB_OBS_HWC_U8 0
+#define MWB_OBS_CWH_U8 1
+#define MWB_OBS_GREY_F64 2
+int mwb_set_obs_format(mwb_handle* h, int format);
+
 /* StochasticActionWrapper (reference wrappers.py:49-71) applied inside mwb_step: before an env steps, one
  * np_random.uniform() is drawn from ITS stream; if it is not below `prob` the action is replaced by
  * `random_action`, or, when that is negative, by np_random.integers(0, 6).  Envs that reset in this

@@ -35,7 +35,7 @@ def _resolve_level(level):
 
 class BatchedMiniWorld:
     def __init__(self, level, num_envs, obs_width=80, obs_height=60, domain_rand=False, autoreset=True,
-                 msaa_samples=8, device=0, lib_path=None, want_depth=False, level_kwargs=None):
+                 msaa_samples=8, device=0, lib_path=None, want_depth=False, level_kwargs=None, obs_format="hwc"):
         self.level_cls = _resolve_level(level)
         self.level_kwargs = dict(level_kwargs or {})
         self.num_envs = int(num_envs)
@@ -106,6 +106,14 @@ class BatchedMiniWorld:
             # host-reset levels: one worker env per slot keeps that env's RNG stream
             self._workers = [None] * self.num_envs
             self._host_done = np.zeros(self.num_envs, bool)
+        # observation layout written by the render kernel: the reference's PyTorchObsWrapper ("cwh") and
+        # GreyscaleWrapper ("grey") are fused into its epilogue instead of running as separate passes
+        self.obs_format = obs_format
+        N, H, W = self.num_envs, self.obs_height, self.obs_width
+        self.obs_shape = {"hwc": (N, H, W, 3), "cwh": (N, 3, W, H), "grey": (N, H, W, 1)}[obs_format]
+        self.obs_dtype = np.float64 if obs_format == "grey" else np.uint8
+        if obs_format != "hwc":
+            eng.set_obs_format(obs_format)
         self._seeded = False
         self._torch = None
         self._bufs = None
@@ -118,7 +126,7 @@ class BatchedMiniWorld:
             dev = torch.device("cuda", self.device)
             N, H, W = self.num_envs, self.obs_height, self.obs_width
             self._bufs = dict(
-                obs=torch.zeros((N, H, W, 3), dtype=torch.uint8, device=dev),
+                obs=torch.zeros(self.obs_shape, dtype=torch.float64 if self.obs_format == "grey" else torch.uint8, device=dev),
                 depth=torch.zeros((N, H, W, 1), dtype=torch.float32, device=dev) if self.want_depth else None,
                 reward=torch.zeros(N, dtype=torch.float64, device=dev),
                 terminated=torch.zeros(N, dtype=torch.uint8, device=dev),
@@ -208,7 +216,7 @@ class BatchedMiniWorld:
         host->device and obs / reward / flags device->host inside the call."""
         N, H, W = self.num_envs, self.obs_height, self.obs_width
         if out is None:
-            out = dict(obs=np.zeros((N, H, W, 3), np.uint8), reward=np.zeros(N), terminated=np.zeros(N, np.uint8),
+            out = dict(obs=np.zeros(self.obs_shape, self.obs_dtype), reward=np.zeros(N), terminated=np.zeros(N, np.uint8),
                        truncated=np.zeros(N, np.uint8),
                        depth=np.zeros((N, H, W, 1), np.float32) if self.want_depth else None)
         acts = np.ascontiguousarray(actions, np.int32)

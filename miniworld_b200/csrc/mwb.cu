@@ -100,6 +100,9 @@ struct mwb_handle {
   uint8_t* d_term;
   uint8_t* d_trunc;
   uint8_t* d_obs;
+  int obs_format;                 // MWB_OBS_*: layout K2 writes observations in
+  size_t obs_px_bytes;            // bytes per pixel of that layout (3, or 8 for float64 greyscale)
+  size_t d_obs_bytes;             // capacity of the d_obs staging buffer
   float* d_depth;
   int32_t* d_ids;
   int* d_overflow;
@@ -367,10 +370,31 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
       }
   }
 }
-static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewSpec& view, uint8_t* obs, float* depth) {
+static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewSpec& view, int fmt, uint8_t* obs_out, float* depth) {
+  // other layouts: render HWC into a scratch frame set, then apply the same per-pixel conversion K2's epilogue does
+  const size_t px = (size_t)S.obs_w * S.obs_h;
+  std::vector<uint8_t> tmp;
+  uint8_t* obs = obs_out;
+  if (obs_out && fmt != MWB_OBS_HWC_U8) {
+    tmp.resize((size_t)S.N * px * 3);
+    obs = tmp.data();
+  }
   if (S.msaa == 1) hostsim_render_t<1>(S, A, view, obs, depth);
   else if (S.msaa == 4) hostsim_render_t<4>(S, A, view, obs, depth);
   else hostsim_render_t<8>(S, A, view, obs, depth);
+  if (obs_out && fmt != MWB_OBS_HWC_U8) {
+    const int W = S.obs_w, H = S.obs_h;
+    for (int i = 0; i < S.N; ++i)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+          const uint8_t* c = obs + (((size_t)i * H + y) * W + x) * 3;
+          if (fmt == MWB_OBS_CWH_U8) {
+            for (int k = 0; k < 3; ++k) obs_out[(((size_t)i * 3 + k) * W + x) * H + y] = c[k];
+          } else {
+            reinterpret_cast<double*>(obs_out)[((size_t)i * H + y) * W + x] = grey_f64(c[0], c[1], c[2]);
+          }
+        }
+  }
 }
 #endif
 
@@ -406,6 +430,8 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->mesh_bbox_buf = nullptr;
   memset(&h->view, 0, sizeof(ViewSpec));
   h->vis_tris = nullptr;
+  h->obs_format = MWB_OBS_HWC_U8;
+  h->obs_px_bytes = 3;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
 #ifndef MWB_HOSTSIM
@@ -453,6 +479,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (!rc) rc = alloc_arr(h, &h->d_term, N);
   if (!rc) rc = alloc_arr(h, &h->d_trunc, N);
   if (!rc) rc = alloc_arr(h, &h->d_obs, N * (size_t)S.obs_w * S.obs_h * 3);
+  h->d_obs_bytes = N * (size_t)S.obs_w * S.obs_h * 3;
   if (!rc) rc = alloc_arr(h, &h->d_depth, N * (size_t)S.obs_w * S.obs_h);
   if (!rc) rc = alloc_arr(h, &h->d_ids, N);
   if (!rc) rc = alloc_arr(h, &h->d_overflow, 1);
@@ -994,7 +1021,7 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
   prof_mark(h, h->ev_k2, s);
-#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, h->d_overflow)
+#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, h->obs_format, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, h->d_overflow)
 #define MWB_LAUNCH_K2_MSAA(T, B, D)                 \
   switch (h->S.msaa) {                              \
     case 1: MWB_LAUNCH_K2(1, T, B, D); break;       \
@@ -1037,7 +1064,8 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, 
       CK(cudaEventRecord(h->chunk_done[c], s));
       CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
       if (host_obs)
-        CK(cudaMemcpyAsync(host_obs + (size_t)e0 * px * 3, obs + (size_t)e0 * px * 3, (size_t)(e1 - e0) * px * 3,
+        CK(cudaMemcpyAsync(host_obs + (size_t)e0 * px * h->obs_px_bytes, obs + (size_t)e0 * px * h->obs_px_bytes,
+                           (size_t)(e1 - e0) * px * h->obs_px_bytes,
                            cudaMemcpyDeviceToHost, h->copy_stream));
       if (host_depth)
         CK(cudaMemcpyAsync(host_depth + (size_t)e0 * px, depth + (size_t)e0 * px, (size_t)(e1 - e0) * px * sizeof(float),
@@ -1050,7 +1078,7 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, 
     CK(cudaStreamWaitEvent(s, h->copies_done, 0));   // later work on s (and its sync) sees the copies
   }
 #else
-  hostsim_render(h->S, h->A, h->view, obs, depth);
+  hostsim_render(h->S, h->A, h->view, h->obs_format, obs, depth);
 #endif
   return MWB_OK;
 }
@@ -1060,7 +1088,7 @@ static int finish_outputs(mwb_handle* h, uint8_t* obs, bool obs_host, float* dep
   const size_t N = h->S.N, px = (size_t)h->S.obs_w * h->S.obs_h;
   int rc = 0;
   bool any_host = false;
-  if (obs && obs_host) { if (!h->frames_copied) rc |= d2h(obs, h->d_obs, N * px * 3, s); any_host = true; }
+  if (obs && obs_host) { if (!h->frames_copied) rc |= d2h(obs, h->d_obs, N * px * h->obs_px_bytes, s); any_host = true; }
   if (depth && depth_host) { if (!h->frames_copied) rc |= d2h(depth, h->d_depth, N * px * sizeof(float), s); any_host = true; }
   h->frames_copied = false;
   if (reward && !is_device_ptr(reward)) { rc |= d2h(reward, h->d_reward, N * sizeof(double), s); any_host = true; }
@@ -1122,6 +1150,22 @@ extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* s
                          obs_host ? obs : nullptr, depth_host ? depth : nullptr);
   if (rc) return rc;
   return finish_outputs(h, obs, obs_host, depth, depth_host, nullptr, nullptr, nullptr, s, stream != nullptr);
+}
+
+extern "C" int mwb_set_obs_format(mwb_handle* h, int format) {
+  if (!h) return fail(MWB_EINVAL, "null handle");
+  if (format != MWB_OBS_HWC_U8 && format != MWB_OBS_CWH_U8 && format != MWB_OBS_GREY_F64) return fail(MWB_EINVAL, "unknown format");
+  const size_t pxb = format == MWB_OBS_GREY_F64 ? 8 : 3;
+  const size_t need = (size_t)h->S.N * h->S.obs_w * h->S.obs_h * pxb;
+  if (need > h->d_obs_bytes) {     // staging for host destinations grows with the pixel size
+    uint8_t* buf = nullptr;
+    if (alloc_arr(h, &buf, need)) return fail(MWB_ECUDA, "staging allocation failed");
+    h->d_obs = buf;
+    h->d_obs_bytes = need;
+  }
+  h->obs_format = format;
+  h->obs_px_bytes = pxb;
+  return MWB_OK;
 }
 
 extern "C" int mwb_set_action_noise(mwb_handle* h, int enabled, double prob, int random_action) {

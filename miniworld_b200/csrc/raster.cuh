@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
 // DYN: warps claim half-tiles from a shared counter instead of striding, which evens out the per-warp work.
 template <int MSAA, int THREADS, int MINB, bool DYN>
 __global__ void __launch_bounds__(THREADS, MINB)
-render_kernel(DevState S, RenderAssets A, ViewSpec view, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0,
+render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0,
               int parts, int tri_cap, int stage_bytes, int* __restrict__ overflow) {
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -446,12 +446,34 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, uint8_t* __restrict__ o
       code0 = P.keys[0] >> 16;
     }
     resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
-    if (obs != nullptr) {
+    if (obs != nullptr && fmt == MWB_OBS_GREY_F64) {
+      // GreyscaleWrapper fused into the epilogue: float64 [N][H][W][1], eight consecutive doubles per tile row
+      if (px < W && py < H) reinterpret_cast<double*>(obs)[((size_t)i * H + py) * W + px] = grey_f64(rgb[0], rgb[1], rgb[2]);
+    } else if (obs != nullptr) {
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 3; ++c) stage[warp][ly][lx * 3 + c] = rgb[c];
       __syncwarp();
-      if (lane < 12) {   // 4 rows x 3 segments of 8 bytes
+      if (fmt == MWB_OBS_CWH_U8) {
+        // PyTorchObsWrapper's transpose(2, 1, 0) fused into the epilogue: [N][3][W][H]; a half-tile is, per channel
+        // and column, four consecutive bytes
+        if (lane < 24) {
+          const int c = lane >> 3, x = tx0 + (lane & 7);
+          if (x < W) {
+            uint8_t* dst = obs + (((size_t)i * 3 + c) * W + x) * H + ty0;
+            const uint8_t b0 = stage[warp][0][(lane & 7) * 3 + c], b1 = stage[warp][1][(lane & 7) * 3 + c];
+            const uint8_t b2 = stage[warp][2][(lane & 7) * 3 + c], b3 = stage[warp][3][(lane & 7) * 3 + c];
+            if (ty0 + 4 <= H && (H & 3) == 0) {
+              *reinterpret_cast<uint32_t*>(dst) = (uint32_t)b0 | ((uint32_t)b1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)b3 << 24);
+            } else {
+              if (ty0 + 0 < H) dst[0] = b0;
+              if (ty0 + 1 < H) dst[1] = b1;
+              if (ty0 + 2 < H) dst[2] = b2;
+              if (ty0 + 3 < H) dst[3] = b3;
+            }
+          }
+        }
+      } else if (lane < 12) {   // 4 rows x 3 segments of 8 bytes
         const int row = lane / 3, seg = lane % 3;
         const int y = ty0 + row;
         if (y < H && tx0 + 8 <= W) {

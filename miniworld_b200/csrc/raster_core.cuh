@@ -615,6 +615,12 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
   out[2] = b;
 }
 
+// GreyscaleWrapper.observation (reference wrappers.py:43-46): 0.30 R + 0.59 G + 0.11 B as numpy evaluates it
+// on the uint8 image -- float64, one rounding per operation, left to right
+MWB_DEV double grey_f64(uint8_t r, uint8_t g, uint8_t b) {
+  return d_add(d_add(d_mul(0.30, (double)r), d_mul(0.59, (double)g)), d_mul(0.11, (double)b));
+}
+
 MWB_DEV uint8_t to_unorm8(float c) {
   c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
   return (uint8_t)(int)(c * 255.0f + 0.5f);

@@ -120,8 +120,9 @@ EXPORTS = (
     "mwb_launch_count", "mwb_abi_sizes", "mwb_profile", "mwb_profile_read", "mwb_set_maze", "mwb_get_geometry",
     "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
     "mwb_render_top_view", "mwb_visible_ents", "mwb_set_action_noise",
-    "mwb_snapshot_size", "mwb_snapshot", "mwb_restore",
+    "mwb_snapshot_size", "mwb_snapshot", "mwb_restore", "mwb_set_obs_format",
 )
+OBS_FORMATS = {"hwc": 0, "cwh": 1, "grey": 2}
 
 _libs = {}
 
@@ -153,6 +154,7 @@ def load_library(lib_path=None):
     lib.mwb_render_top_view.argtypes = [vp, C.POINTER(C.c_double), C.c_int, vp, vp]
     lib.mwb_visible_ents.argtypes = [vp, vp, vp]
     lib.mwb_set_action_noise.argtypes = [vp, C.c_int, C.c_double, C.c_int]
+    lib.mwb_set_obs_format.argtypes = [vp, C.c_int]
     lib.mwb_snapshot_size.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.mwb_snapshot.argtypes = [vp, vp, C.c_size_t]
     lib.mwb_restore.argtypes = [vp, vp, C.c_size_t]
@@ -439,6 +441,11 @@ class Engine:
 
     def render(self, obs=None, depth=None, stream=None):
         self._check(self.lib.mwb_render_obs(self.h, _dev_or_host_ptr(obs), _dev_or_host_ptr(depth), stream))
+
+    def set_obs_format(self, fmt):
+        """"hwc": uint8 [N,H,W,3]; "cwh": uint8 [N,3,W,H] (PyTorchObsWrapper); "grey": float64 [N,H,W,1]
+        (GreyscaleWrapper) -- written in that layout by the render kernel itself."""
+        self._check(self.lib.mwb_set_obs_format(self.h, OBS_FORMATS[fmt]))
 
     def snapshot(self):
         """uint8 array holding the restorable state of every env (mwb_snapshot)."""

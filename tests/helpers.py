@@ -205,3 +205,27 @@ def snapshot_roundtrip(level, lib_path, n=6, domain_rand=True, before=25, after=
     assert any(r[1].any() or r[2].any() for r in first) or after < 100   # episodes may end inside the window
     fresh.close()
     env.close()
+
+
+def obs_format_parity(lib_path, n=5, steps=6, level="MiniWorld-FourRooms-v0"):
+    """K2's fused PyTorchObsWrapper / GreyscaleWrapper epilogues == the wrappers applied to the HWC frames."""
+    frames = {}
+    for fmt in ("hwc", "cwh", "grey"):
+        env = BatchedMiniWorld(level, num_envs=n, autoreset=True, lib_path=lib_path, obs_format=fmt)
+        ids = np.arange(n, dtype=np.int32)
+        env.engine.seed(ids, np.array([rng_state_of(3000 + i) for i in range(n)], RNG_DTYPE))
+        env.engine.reset(None)
+        acts = np.random.default_rng(5).integers(0, 3, size=(steps, n), dtype=np.int32)
+        out = None
+        for t in range(steps):
+            out = env.step_host(acts[t], out=out)
+        frames[fmt] = out["obs"].copy()
+        env.close()
+    hwc = frames["hwc"]
+    assert frames["cwh"].dtype == np.uint8 and frames["grey"].dtype == np.float64
+    for i in range(n):
+        assert np.array_equal(frames["cwh"][i], hwc[i].transpose(2, 1, 0))
+        o = hwc[i]
+        grey = 0.30 * o[:, :, 0] + 0.59 * o[:, :, 1] + 0.11 * o[:, :, 2]
+        assert np.array_equal(frames["grey"][i], np.expand_dims(grey, axis=2))
+    assert 0 < hwc.mean() < 255

@@ -175,3 +175,11 @@ def test_snapshot_restore_resumes_bit_exact_gpu(libmwb_path, level):
     """mwb_snapshot / mwb_restore: a restored handle (same or fresh) continues every env bit for bit."""
     from helpers import snapshot_roundtrip
     snapshot_roundtrip(level, libmwb_path, n=32, before=60, after=120)
+
+
+@pytest.mark.parametrize("level", ["MiniWorld-FourRooms-v0", "MiniWorld-PickupObjects-v0"])
+def test_fused_observation_layouts_gpu(libmwb_path, level):
+    """mwb_set_obs_format: channel-first and float64-greyscale frames written by K2's epilogue are exactly the
+    reference wrappers' outputs on the HWC frames (host destinations: also covers the chunked D2H path)."""
+    from helpers import obs_format_parity
+    obs_format_parity(libmwb_path, n=300, steps=4, level=level)

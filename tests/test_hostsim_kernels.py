@@ -131,3 +131,8 @@ def test_device_action_noise_follows_wrapper(hostsim_path):
 def test_snapshot_restore_resumes_bit_exact(hostsim_path, level):
     from helpers import snapshot_roundtrip
     snapshot_roundtrip(level, hostsim_path, n=4, before=20, after=30)
+
+
+def test_fused_observation_layouts(hostsim_path):
+    from helpers import obs_format_parity
+    obs_format_parity(hostsim_path, n=2, steps=2)
