@@ -354,7 +354,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         const float tile_bound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(pixel_bound(P), 0.0f))));
         const int j = cb + lane;
         int idx = -1;
-        float znear = 0.0f;             // smallest depth code this lane's triangle can reach inside the half-tile
         if (j < sg.count) {
           idx = ord ? (int)ord[j] : j;
           bool hit;
@@ -374,8 +373,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
             for (int k = 0; k < 3; ++k)   // half-tile entirely outside one edge?
               if (t.A[k] * fx0 + t.B[k] * fy0 + t.K[k] < 0.0f) hit = false;
             // nearest depth the triangle can have inside the half-tile vs everything already stored
-            znear = (t.Za * fx0 + t.Zb * fy0 + t.Kz) * 65535.0f - 1.0f;
-            if (znear > tile_bound) hit = false;
+            if ((t.Za * fx0 + t.Zb * fy0 + t.Kz) * 65535.0f - 1.0f > tile_bound) hit = false;
           }
           if (!hit) idx = -1;
         }
@@ -389,10 +387,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         while (mask) {
           const int b = __ffs(mask) - 1;
           mask &= mask - 1;
-          // hi-Z again, now against what the triangles ahead of it in this chunk have installed
-          const float zb = __shfl_sync(0xffffffffu, znear, b);
-          const float now = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(pixel_bound(P), 0.0f))));
-          if (zb > now) continue;
           const int tb = chunk_idx[warp][b];
           const ClassTri ct = load_class(sg.tris + tb);
           const int cls = classify_pixel<MSAA>(ct, sg.base + tb, px, py, P);
