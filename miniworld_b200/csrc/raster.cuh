@@ -314,6 +314,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
 #pragma unroll
     for (int s = 0; s < MSAA; ++s) skeys[s][lane] = MWB_SKY_KEY;
     int qn = 0;                                  // queued exact items (warp-uniform)
+    float tile_occl = 65535.0f;                  // farthest code of the nearest triangle known to cover the whole half-tile
 
     // Exact processing of the queued (pixel, triangle) items, MSAA lanes per item: every lane
     // evaluates one sample and folds it into the pixel's key with an integer atomicMin
@@ -354,6 +355,8 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         const float tile_bound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(pixel_bound(P), 0.0f))));
         const int j = cb + lane;
         int idx = -1;
+        float znear = 0.0f;                         // lower bound of this lane's triangle's depth codes in the half-tile
+        uint32_t occl = 0x7f800000u;                // +inf: upper bound of its codes if it covers the whole half-tile
         if (j < sg.count) {
           idx = ord ? (int)ord[j] : j;
           bool hit;
@@ -369,14 +372,29 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
           if (hit) {
             const TriRec& t = sg.tris[idx];
             const float fx0 = (float)tx0, fy0 = (float)ty0;
+            bool covers = true;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)   // half-tile entirely outside one edge?
-              if (t.A[k] * fx0 + t.B[k] * fy0 + t.K[k] < 0.0f) hit = false;
+            for (int k = 0; k < 3; ++k) {
+              const float e = t.A[k] * fx0 + t.B[k] * fy0;
+              if (e + t.K[k] < 0.0f) hit = false;   // half-tile entirely outside one edge?
+              // ... or certainly inside it everywhere: min of E over [x0, x0 + 8] x [y0, y0 + 4] minus the margin R
+              covers = covers && e + t.C[k] - t.R[k] + 8.0f * fminf(t.A[k], 0.0f) + 4.0f * fminf(t.B[k], 0.0f) > 0.0f;
+            }
             // nearest depth the triangle can have inside the half-tile vs everything already stored
-            if ((t.Za * fx0 + t.Zb * fy0 + t.Kz) * 65535.0f - 1.0f > tile_bound) hit = false;
+            const float zb = t.Za * fx0 + t.Zb * fy0;
+            const float zmin = zb + t.Kz;
+            znear = zmin * 65535.0f - 1.0f;
+            if (znear > tile_bound) hit = false;
+            // a triangle that covers every sample of the half-tile unclipped occludes, whatever the draw order,
+            // every triangle whose nearest code here lies strictly behind its farthest one
+            const float zmax = zb + t.Zc + t.Zr + 8.0f * fmaxf(t.Za, 0.0f) + 4.0f * fmaxf(t.Zb, 0.0f);
+            const float chi = zmax * 65535.0f + 1.5f;
+            if (hit && covers && zmin >= 0.0f && zmax <= 1.0f && chi < 65535.0f) occl = __float_as_uint(chi);
           }
           if (!hit) idx = -1;
         }
+        tile_occl = fminf(tile_occl, __uint_as_float(__reduce_min_sync(0xffffffffu, occl)));
+        if (znear > tile_occl) idx = -1;
         uint32_t mask = __ballot_sync(0xffffffffu, idx >= 0);
         __syncwarp();
         chunk_idx[warp][lane] = idx;
