@@ -290,6 +290,7 @@ __global__ void seed_kernel(DevState S, const WorldUpload* u, int n) {
 #else
 // host simulator: sequential stand-in for mesh_setup_kernel + render_kernel built from the
 // same MWB_DEV functions
+static long long g_tile[6];   // half-tiles, bbox hits, after edge rejection, full covers, culled by an occluder, tiles with one
 struct VecTris {
   const TriRec* t;
   const TriRec& operator()(uint32_t slot) const { return t[slot]; }
@@ -333,6 +334,37 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
       }
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return zmin[a] < zmin[b]; });
     }
+    if (getenv("MWB_HS_TILESTATS")) {   // test-only: how the half-tile level tests of K2 would triage this frame
+      for (int ty0 = 0; ty0 < H; ty0 += 4)
+        for (int tx0 = 0; tx0 < W; tx0 += 8) {
+          g_tile[0]++;
+          float occl = 65535.0f;
+          std::vector<float> zn;
+          for (size_t j = 0; j < tris.size(); ++j) {
+            const TriRec& t = tris[j];
+            const int bx0 = t.bx & 0xFFFF, bx1 = t.bx >> 16, by0 = t.by & 0xFFFF, by1 = t.by >> 16;
+            if (!(bx0 <= tx0 + 7 && bx1 >= tx0 && by0 <= ty0 + 3 && by1 >= ty0)) continue;
+            g_tile[1]++;
+            const float fx0 = (float)tx0, fy0 = (float)ty0;
+            bool hit = true, covers = true;
+            for (int k = 0; k < 3; ++k) {
+              const float e = t.A[k] * fx0 + t.B[k] * fy0;
+              if (e + t.K[k] < 0.0f) hit = false;
+              covers = covers && e + t.C[k] - t.R[k] + 8.0f * fminf(t.A[k], 0.0f) + 4.0f * fminf(t.B[k], 0.0f) > 0.0f;
+            }
+            if (!hit) continue;
+            g_tile[2]++;
+            const float zb = t.Za * fx0 + t.Zb * fy0, zmin = zb + t.Kz;
+            const float zmax = zb + t.Zc + t.Zr + 8.0f * fmaxf(t.Za, 0.0f) + 4.0f * fmaxf(t.Zb, 0.0f);
+            const float chi = zmax * 65535.0f + 1.5f;
+            zn.push_back(zmin * 65535.0f - 1.0f);
+            if (covers) g_tile[3]++;
+            if (covers && zmin >= 0.0f && zmax <= 1.0f && chi < 65535.0f) occl = fminf(occl, chi);
+          }
+          if (occl < 65535.0f) g_tile[5]++;
+          for (size_t k = 0; k < zn.size(); ++k) if (zn[k] > occl) g_tile[4]++;
+        }
+    }
     VecTris fetch{tris.data()};
     for (int py = 0; py < H; ++py)
       for (int px = 0; px < W; ++px) {
@@ -361,7 +393,7 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
         } else {
           if (obs) {
             uint8_t rgb[3];
-            resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
+            resolve_pixel<MSAA>(A, cam, fetch, P.keys, -1, px, py, rgb);
             memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
           }
           code0 = P.keys[0] >> 16;
@@ -586,6 +618,9 @@ extern "C" int64_t mwb_overflow_count(mwb_handle* h) {
 #ifdef MWB_HOSTSIM
 extern "C" void hs_counters(long long* out, int reset) {
   for (int k = 0; k < 6; ++k) { out[k] = g_cnt[k]; if (reset) g_cnt[k] = 0; }
+}
+extern "C" void hs_tile_counters(long long* out, int reset) {
+  for (int k = 0; k < 6; ++k) { out[k] = g_tile[k]; if (reset) g_tile[k] = 0; }
 }
 #endif
 

@@ -152,11 +152,16 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   __shared__ Segment segs[MWB_MAX_SEGS];
   __shared__ int seg_count[MWB_MAX_SEGS];
   __shared__ int warp_tot[WARPS];
-  __shared__ __align__(8) uint8_t stage[WARPS][4][24];
   __shared__ __align__(8) uint64_t quad_bar;
-  __shared__ int chunk_idx[WARPS][32];   // triangle tested by each lane in the current chunk
-  __shared__ uint32_t eq_keys[WARPS][MSAA][32];       // per-sample keys of explicit pixels
-  __shared__ uint32_t eq_items[WARPS][MWB_EQ_CAP];    // queued (pixel, triangle) exact items
+  // everything a warp keeps in shared memory for its current half-tile sits in ONE record, so that a single base
+  // register (+ immediate offsets) addresses all of it
+  struct __align__(16) WarpScratch {
+    uint32_t keys[MSAA][32];          // per-sample keys of explicit pixels: [sample][pixel lane] depth16 << 16 | slot
+    uint32_t items[MWB_EQ_CAP];       // queued (pixel, triangle) exact items
+    int chunk[32];                    // triangle tested by each lane in the current chunk
+    uint8_t stage[4][24];             // RGB of the half-tile, row-major, for the 8-byte row-segment stores
+  };
+  __shared__ WarpScratch wscratch[WARPS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = S.obs_w, H = S.obs_h;
@@ -279,6 +284,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
 
   // ---- C/D. one warp per 8x4 half-tile (lane = one pixel; an 8x8 tile is two of them)
   const int tiles_x = (W + 7) >> 3;
+  const float inv_tiles_x = 1.0f / (float)tiles_x;
   const int lx = lane & 7, ly = lane >> 3;
   const SegLookup fetch{segs, nsegs};
   // exact-phase work is done sample-parallel: lane -> (queued item lane / MSAA, sample lane % MSAA)
@@ -286,8 +292,9 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   const int my_s = lane % MSAA;
   float my_sx, my_sy;
   sample_xy_dyn<MSAA>(my_s, my_sx, my_sy);
-  uint32_t(*skeys)[32] = eq_keys[warp];          // [sample][pixel lane] depth16 << 16 | slot
-  uint32_t* equeue = eq_items[warp];
+  WarpScratch& ws = wscratch[warp];
+  uint32_t(*skeys)[32] = ws.keys;
+  uint32_t* equeue = ws.items;
   // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x
   const int halves_y = (H + 3) >> 2;
   const int n_halves = tiles_x * halves_y, per_part = (n_halves + parts - 1) / parts;
@@ -299,7 +306,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   int half = h_begin + warp;
 #pragma unroll 1
   while (half < h_end) {
-    const int hrow = half / tiles_x, hcol = half - hrow * tiles_x;
+    const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;   // exact: half < 2^20
     const int tx0 = hcol << 3, ty0 = hrow << 2;
     if (DYN) {                 // claim the next half-tile now; the atomic's latency hides behind this one
       int nxt = 0;
@@ -314,7 +321,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
 #pragma unroll
     for (int s = 0; s < MSAA; ++s) skeys[s][lane] = MWB_SKY_KEY;
     int qn = 0;                                  // queued exact items (warp-uniform)
-    float tile_occl = 65535.0f;                  // farthest code of the nearest triangle known to cover the whole half-tile
 
     // Exact processing of the queued (pixel, triangle) items, MSAA lanes per item: every lane
     // evaluates one sample and folds it into the pixel's key with an integer atomicMin
@@ -355,8 +361,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         const float tile_bound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(pixel_bound(P), 0.0f))));
         const int j = cb + lane;
         int idx = -1;
-        float znear = 0.0f;                         // lower bound of this lane's triangle's depth codes in the half-tile
-        uint32_t occl = 0x7f800000u;                // +inf: upper bound of its codes if it covers the whole half-tile
         if (j < sg.count) {
           idx = ord ? (int)ord[j] : j;
           bool hit;
@@ -372,32 +376,17 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
           if (hit) {
             const TriRec& t = sg.tris[idx];
             const float fx0 = (float)tx0, fy0 = (float)ty0;
-            bool covers = true;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const float e = t.A[k] * fx0 + t.B[k] * fy0;
-              if (e + t.K[k] < 0.0f) hit = false;   // half-tile entirely outside one edge?
-              // ... or certainly inside it everywhere: min of E over [x0, x0 + 8] x [y0, y0 + 4] minus the margin R
-              covers = covers && e + t.C[k] - t.R[k] + 8.0f * fminf(t.A[k], 0.0f) + 4.0f * fminf(t.B[k], 0.0f) > 0.0f;
-            }
+            for (int k = 0; k < 3; ++k)   // half-tile entirely outside one edge?
+              if (t.A[k] * fx0 + t.B[k] * fy0 + t.K[k] < 0.0f) hit = false;
             // nearest depth the triangle can have inside the half-tile vs everything already stored
-            const float zb = t.Za * fx0 + t.Zb * fy0;
-            const float zmin = zb + t.Kz;
-            znear = zmin * 65535.0f - 1.0f;
-            if (znear > tile_bound) hit = false;
-            // a triangle that covers every sample of the half-tile unclipped occludes, whatever the draw order,
-            // every triangle whose nearest code here lies strictly behind its farthest one
-            const float zmax = zb + t.Zc + t.Zr + 8.0f * fmaxf(t.Za, 0.0f) + 4.0f * fmaxf(t.Zb, 0.0f);
-            const float chi = zmax * 65535.0f + 1.5f;
-            if (hit && covers && zmin >= 0.0f && zmax <= 1.0f && chi < 65535.0f) occl = __float_as_uint(chi);
+            if ((t.Za * fx0 + t.Zb * fy0 + t.Kz) * 65535.0f - 1.0f > tile_bound) hit = false;
           }
           if (!hit) idx = -1;
         }
-        tile_occl = fminf(tile_occl, __uint_as_float(__reduce_min_sync(0xffffffffu, occl)));
-        if (znear > tile_occl) idx = -1;
         uint32_t mask = __ballot_sync(0xffffffffu, idx >= 0);
         __syncwarp();
-        chunk_idx[warp][lane] = idx;
+        ws.chunk[lane] = idx;
         __syncwarp();
         // phase 1 (warp-uniform): triage every surviving triangle at this lane's pixel
         uint32_t mine = 0, mine_full = 0;
@@ -405,7 +394,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         while (mask) {
           const int b = __ffs(mask) - 1;
           mask &= mask - 1;
-          const int tb = chunk_idx[warp][b];
+          const int tb = ws.chunk[b];
           const ClassTri ct = load_class(sg.tris + tb);
           const int cls = classify_pixel<MSAA>(ct, sg.base + tb, px, py, P);
           if (cls) mine |= 1u << b;
@@ -434,7 +423,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
             } else {
               const int b = __ffs(mine) - 1;
               mine &= mine - 1;
-              item = (((mine_full >> b) & 1u) << 21) | ((uint32_t)lane << 16) | (uint32_t)(sg.base + chunk_idx[warp][b]);
+              item = (((mine_full >> b) & 1u) << 21) | ((uint32_t)lane << 16) | (uint32_t)(sg.base + ws.chunk[b]);
             }
             equeue[pos] = item;
           }
@@ -448,23 +437,23 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     // (expensive) shading code runs once for the whole warp instead of once per mode.
     uint8_t rgb[3];
     uint32_t code0;
+    int lazy_slot = -1;
     if (P.mode == MWB_PX_LAZY) {
+      lazy_slot = P.lazy_slot;
       code0 = sample0_code<MSAA>(fetch(P.lazy_slot), px, py);
-#pragma unroll
-      for (int s = 0; s < MSAA; ++s) P.keys[s] = (uint32_t)P.lazy_slot;
     } else {
 #pragma unroll
       for (int s = 0; s < MSAA; ++s) P.keys[s] = skeys[s][lane];
       code0 = P.keys[0] >> 16;
     }
-    resolve_pixel<MSAA>(A, cam, fetch, P.keys, px, py, rgb);
+    resolve_pixel<MSAA>(A, cam, fetch, P.keys, lazy_slot, px, py, rgb);
     if (obs != nullptr && fmt == MWB_OBS_GREY_F64) {
       // GreyscaleWrapper fused into the epilogue: float64 [N][H][W][1], eight consecutive doubles per tile row
       if (px < W && py < H) reinterpret_cast<double*>(obs)[((size_t)i * H + py) * W + px] = grey_f64(rgb[0], rgb[1], rgb[2]);
     } else if (obs != nullptr) {
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 3; ++c) stage[warp][ly][lx * 3 + c] = rgb[c];
+      for (int c = 0; c < 3; ++c) ws.stage[ly][lx * 3 + c] = rgb[c];
       __syncwarp();
       if (fmt == MWB_OBS_CWH_U8) {
         // PyTorchObsWrapper's transpose(2, 1, 0) fused into the epilogue: [N][3][W][H]; a half-tile is, per channel
@@ -473,8 +462,8 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
           const int c = lane >> 3, x = tx0 + (lane & 7);
           if (x < W) {
             uint8_t* dst = obs + (((size_t)i * 3 + c) * W + x) * H + ty0;
-            const uint8_t b0 = stage[warp][0][(lane & 7) * 3 + c], b1 = stage[warp][1][(lane & 7) * 3 + c];
-            const uint8_t b2 = stage[warp][2][(lane & 7) * 3 + c], b3 = stage[warp][3][(lane & 7) * 3 + c];
+            const uint8_t b0 = ws.stage[0][(lane & 7) * 3 + c], b1 = ws.stage[1][(lane & 7) * 3 + c];
+            const uint8_t b2 = ws.stage[2][(lane & 7) * 3 + c], b3 = ws.stage[3][(lane & 7) * 3 + c];
             if (ty0 + 4 <= H && (H & 3) == 0) {
               *reinterpret_cast<uint32_t*>(dst) = (uint32_t)b0 | ((uint32_t)b1 << 8) | ((uint32_t)b2 << 16) | ((uint32_t)b3 << 24);
             } else {
@@ -489,12 +478,12 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         const int row = lane / 3, seg = lane % 3;
         const int y = ty0 + row;
         if (y < H && tx0 + 8 <= W) {
-          uint2 v = *reinterpret_cast<const uint2*>(&stage[warp][row][seg * 8]);
+          uint2 v = *reinterpret_cast<const uint2*>(&ws.stage[row][seg * 8]);
           *reinterpret_cast<uint2*>(obs + ((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + seg * 8) = v;
         } else if (y < H) {   // ragged right edge (W not a multiple of 8): byte stores
           for (int q = 0; q < 8; ++q) {
             int bcol = seg * 8 + q;
-            if (tx0 + bcol / 3 < W) obs[((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + bcol] = stage[warp][row][bcol];
+            if (tx0 + bcol / 3 < W) obs[((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + bcol] = ws.stage[row][bcol];
           }
         }
       }

@@ -935,22 +935,26 @@ MWB_DEV uint32_t sample0_code(const TriRec& t, int px, int py) {
 
 template <int MSAA, typename TriFetch>
 MWB_DEV void resolve_pixel(const RenderAssets& A, const Camera& cam, const TriFetch& tris, const uint32_t (&keys)[MSAA],
-                           int px, int py, uint8_t rgb[3]) {
+                           int lazy_slot, int px, int py, uint8_t rgb[3]) {
   float acc[3] = {0.0f, 0.0f, 0.0f};
-  uint32_t todo = (1u << MSAA) - 1u;
+  const uint32_t all = (1u << MSAA) - 1u;
+  uint32_t todo = lazy_slot >= 0 ? 1u : all;       // a lazy pixel is one surface on every sample: keys are not looked at
   const float wgt = 1.0f / (float)MSAA;
 #pragma unroll 1
   while (todo) {
-    // id of the first unprocessed sample (select chain: keys stay in registers)
-    const uint32_t first = todo & (0u - todo);
-    uint32_t id = 0;
+    uint32_t id = (uint32_t)lazy_slot, same = all;
+    if (lazy_slot < 0) {
+      // id of the first unprocessed sample (select chain: keys stay in registers)
+      const uint32_t first = todo & (0u - todo);
+      id = 0;
 #pragma unroll
-    for (int s = 0; s < MSAA; ++s)
-      if (first == (1u << s)) id = key_id<MSAA>(keys[s]);
-    uint32_t same = 0;
+      for (int s = 0; s < MSAA; ++s)
+        if (first == (1u << s)) id = key_id<MSAA>(keys[s]);
+      same = 0;
 #pragma unroll
-    for (int s = 0; s < MSAA; ++s)
-      if (key_id<MSAA>(keys[s]) == id) same |= 1u << s;
+      for (int s = 0; s < MSAA; ++s)
+        if (key_id<MSAA>(keys[s]) == id) same |= 1u << s;
+    }
     todo &= ~same;
     float c[3];
     if (id == 0xFFFFu) {

@@ -16,7 +16,7 @@ import tempfile
 
 rep = sys.argv[1]
 so = sys.argv[2] if len(sys.argv) > 2 else "miniworld_b200/libmwb.so"
-kern = sys.argv[3] if len(sys.argv) > 3 else "_Z13render_kernelILi8ELi3E"
+kern = sys.argv[3] if len(sys.argv) > 3 else "_Z13render_kernelILi8ELi320ELi3ELb1E"
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "miniworld_b200", "csrc", "")
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
