@@ -86,6 +86,9 @@ struct WorldUpload {   // AoS image of one env's dynamic state (host <-> device 
   mwb_rng_state rng;
 };
 
+#define MWB_MAX_D2H_CHUNKS 32
+#define MWB_DEFAULT_D2H_CHUNKS 4
+
 struct mwb_handle {
   mwb_config cfg;
   DevState S;
@@ -119,7 +122,8 @@ struct mwb_handle {
   int k2_parts;                   // blocks per env frame (1 at 80x60, 4 at 160x120)
 #ifndef MWB_HOSTSIM
   cudaStream_t copy_stream;
-  cudaEvent_t chunk_done[4], copies_done;
+  cudaEvent_t chunk_done[MWB_MAX_D2H_CHUNKS], copies_done;
+  int d2h_chunks;                 // pieces a host-destination frame batch is rendered + copied in
 #endif
 #ifndef MWB_HOSTSIM
   std::vector<cudaEvent_t> ev_k1, ev_k2;   // start/stop pairs
@@ -472,7 +476,13 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     delete h;
     return fail(MWB_ECUDA, "cudaStreamCreate failed");
   }
-  for (int c = 0; c < 4; ++c) cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming);
+  for (int c = 0; c < MWB_MAX_D2H_CHUNKS; ++c) cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming);
+  {
+    const char* v = getenv("MWB_D2H_CHUNKS");   // tuning knob
+    h->d2h_chunks = v ? atoi(v) : MWB_DEFAULT_D2H_CHUNKS;
+    if (h->d2h_chunks < 1) h->d2h_chunks = 1;
+    if (h->d2h_chunks > MWB_MAX_D2H_CHUNKS) h->d2h_chunks = MWB_MAX_D2H_CHUNKS;
+  }
   cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming);
 #else
   h->stream = nullptr;
@@ -598,7 +608,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
   cudaStreamSynchronize(h->copy_stream);
-  for (int c = 0; c < 4; ++c) cudaEventDestroy(h->chunk_done[c]);
+  for (int c = 0; c < MWB_MAX_D2H_CHUNKS; ++c) cudaEventDestroy(h->chunk_done[c]);
   cudaEventDestroy(h->copies_done);
   cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
@@ -1090,7 +1100,8 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, 
   const int N = h->S.N;
   const size_t px = (size_t)h->S.obs_w * h->S.obs_h;
   const bool pipelined = (host_obs || host_depth) && N >= 256;
-  const int chunks = pipelined ? 4 : 1;
+  int chunks = pipelined ? h->d2h_chunks : 1;
+  while (chunks > 1 && N / chunks < 128) --chunks;   // keep every launch a few hundred blocks wide
   for (int c = 0; c < chunks; ++c) {
     const int e0 = (int)((long long)N * c / chunks), e1 = (int)((long long)N * (c + 1) / chunks);
     int rc = launch_k2(h, obs, depth, e0, e1 - e0, s);
