@@ -125,10 +125,80 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
     atomicMax(&box[2], x1); atomicMax(&box[3], y1);
   }
   __syncthreads();
+  const int count = total < S.mesh_cap ? total : S.mesh_cap;
+  // ---- bin the listed triangles by half-tile (8 x 4 pixels) of the entity's screen box, so that a
+  // rasteriser warp scans only the triangles that can touch its half-tile instead of the whole mesh
+  __shared__ int bin_cnt[MWB_MAX_BINS + 1];
+  __shared__ int scan_tot[8];
+  int binned = 0;
+  const int c0 = box[0] >> 3, c1 = box[2] >> 3, r0 = box[1] >> 2, r1 = box[3] >> 2;
+  const int cols = c1 - c0 + 1, rows = r1 - r0 + 1, nbins = box[2] >= 0 ? cols * rows : 0;
+  int* off = S.mesh_bin_off + ((size_t)i * S.E + e) * (MWB_MAX_BINS + 1);
+  uint16_t* bidx = S.mesh_bin_idx + ((size_t)i * S.E + e) * ((size_t)MWB_BIN_REFS * S.mesh_cap);
+  if (nbins > 0 && nbins <= MWB_MAX_BINS && count > 64) {
+    for (int b = tid; b <= nbins; b += 256) bin_cnt[b] = 0;
+    __syncthreads();
+    // pass 1: count.  A triangle is listed in a bin if its bbox meets the half-tile and no edge excludes it
+    // (the same conservative tests the rasteriser applies per half-tile).
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = tid; t < count; t += 256) {
+        const uint2 bb = out_bbox[t];
+        const int tc0 = max((int)(bb.x & 0xFFFF) >> 3, c0), tc1 = min((int)(bb.x >> 16) >> 3, c1);
+        const int tr0 = max((int)(bb.y & 0xFFFF) >> 2, r0), tr1 = min((int)(bb.y >> 16) >> 2, r1);
+        const TriRec& T = out[t];
+        float A[3], B[3], K[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { A[k] = T.A[k]; B[k] = T.B[k]; K[k] = T.K[k]; }
+        for (int r = tr0; r <= tr1; ++r)
+          for (int c = tc0; c <= tc1; ++c) {
+            const float fx0 = (float)(c << 3), fy0 = (float)(r << 2);
+            if (A[0] * fx0 + B[0] * fy0 + K[0] < 0.0f || A[1] * fx0 + B[1] * fy0 + K[1] < 0.0f ||
+                A[2] * fx0 + B[2] * fy0 + K[2] < 0.0f)
+              continue;
+            const int b = (r - r0) * cols + (c - c0);
+            const int pos = atomicAdd(&bin_cnt[b], 1);
+            if (pass == 1) bidx[pos] = (uint16_t)t;      // bin_cnt holds the running cursor in pass 2
+          }
+      }
+      __syncthreads();
+      if (pass == 0) {
+        // exclusive scan of the counts -> offsets (also the cursors of pass 2)
+        const int per = (nbins + 255) / 256, b0 = tid * per;
+        int sum = 0;
+        for (int k = 0; k < per; ++k)
+          if (b0 + k < nbins) sum += bin_cnt[b0 + k];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        if (lane == 31) scan_tot[warp] = incl;
+        __syncthreads();
+        int base = incl - sum;
+        for (int w = 0; w < warp; ++w) base += scan_tot[w];
+        int refs = 0;
+        for (int w = 0; w < 8; ++w) refs += scan_tot[w];
+        __syncthreads();
+        for (int k = 0; k < per; ++k)
+          if (b0 + k < nbins) {
+            const int cnt = bin_cnt[b0 + k];
+            bin_cnt[b0 + k] = base;
+            off[b0 + k] = base;
+            base += cnt;
+          }
+        if (tid == 0) off[nbins] = refs;
+        binned = refs <= MWB_BIN_REFS * S.mesh_cap ? 1 : 0;    // uniform across the block
+        __syncthreads();
+        if (!binned) break;
+      }
+    }
+  }
   if (tid == 0) {
-    info->count = total < S.mesh_cap ? total : S.mesh_cap;
+    info->count = count;
     info->bx = box[2] >= 0 ? (box[0] | (box[2] << 16)) : 0;
     info->by = box[3] >= 0 ? (box[1] | (box[3] << 16)) : 0;
+    info->binned = binned;
   }
 }
 
@@ -236,6 +306,8 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
       if (k == 0 || k > fmap.n_ents || fmap.ent_kind[k - 1] == MWB_KIND_BOX) {
         sg.tris = tris + smem_pos;
         sg.bbox = nullptr;
+        sg.bin_idx = nullptr;
+        sg.bin_off = nullptr;
         sg.count = seg_count[k];
         smem_pos += sg.count;
         sg.bx = (W - 1) << 16;
@@ -245,6 +317,8 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         const MeshSegInfo mi = S.mesh_seg[(size_t)i * S.E + e];
         sg.tris = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
         sg.bbox = S.mesh_bbox + ((size_t)i * S.E + e) * S.mesh_cap;
+        sg.bin_idx = mi.binned ? S.mesh_bin_idx + ((size_t)i * S.E + e) * ((size_t)MWB_BIN_REFS * S.mesh_cap) : nullptr;
+        sg.bin_off = mi.binned ? S.mesh_bin_off + ((size_t)i * S.E + e) * (MWB_MAX_BINS + 1) : nullptr;
         sg.count = mi.count;
         sg.bx = mi.bx;
         sg.by = mi.by;
@@ -354,14 +428,24 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
       const Segment sg = segs[sgi];
       if (sg.count == 0) continue;
       if ((sg.bx & 0xFFFF) > tx0 + 7 || (sg.bx >> 16) < tx0 || (sg.by & 0xFFFF) > ty0 + 3 || (sg.by >> 16) < ty0) continue;
-      const uint16_t* ord = sgi == 0 ? order : nullptr;      // front-to-back visiting order of segment 0
+      // which triangles to visit: segment 0 in front-to-back order; a binned mesh list only the triangles
+      // filed under this half-tile; else the whole list
+      const uint16_t* ord = sgi == 0 ? order : nullptr;
+      int lo = 0, hi = sg.count;
+      if (sg.bin_off != nullptr) {
+        const int cols = ((sg.bx >> 16) >> 3) - ((sg.bx & 0xFFFF) >> 3) + 1;
+        const int bin = (hrow - ((sg.by & 0xFFFF) >> 2)) * cols + (hcol - ((sg.bx & 0xFFFF) >> 3));
+        lo = sg.bin_off[bin];
+        hi = sg.bin_off[bin + 1];
+        ord = sg.bin_idx;
+      }
 #pragma unroll 1
-      for (int cb = 0; cb < sg.count; cb += 32) {
+      for (int cb = lo; cb < hi; cb += 32) {
         // largest depth code stored anywhere in this half-tile: a triangle that cannot beat it is dropped whole
         const float tile_bound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(pixel_bound(P), 0.0f))));
         const int j = cb + lane;
         int idx = -1;
-        if (j < sg.count) {
+        if (j < hi) {
           idx = ord ? (int)ord[j] : j;
           bool hit;
           if (sg.bbox != nullptr) {          // mesh list: coalesced bbox test first, record only if it passes

@@ -899,6 +899,8 @@ MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camer
 struct Segment {
   const TriRec* tris;
   const uint2* bbox;                 // mesh lists: packed bboxes (coalesced pre-test); null for shared-memory lists
+  const uint16_t* bin_idx;           // binned mesh lists: triangle indices per half-tile of the segment's box, or null
+  const int* bin_off;
   int base, count;                   // slots [base, base + count)
   int bx, by;                        // bbox lo | hi << 16 (pixels)
 };
@@ -916,7 +918,8 @@ struct SegLookup {                   // slot -> record
 
 // per (env, entity slot) result of mesh_setup_kernel
 struct MeshSegInfo {
-  int count, bx, by, pad;
+  int count, bx, by;
+  int binned;                        // 1: mesh_bin_off / mesh_bin_idx of this (env, slot) are valid for this frame
 };
 
 // Resolve one pixel: average the colour of the surface seen by each sample (box filter of

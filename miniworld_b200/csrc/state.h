@@ -9,6 +9,9 @@
 #include "../../include/mwb.h"
 #include "np_rng.cuh"
 
+#define MWB_MAX_BINS 640         // half-tiles of one entity's screen box that can be binned (160x120 frame: 600)
+#define MWB_BIN_REFS 6           // bin references per listed triangle the index buffer has room for
+
 struct TriRec;
 struct MeshSegInfo;
 struct MazeDev;
@@ -60,6 +63,10 @@ struct DevState {
   TriRec* mesh_tris;
   MeshSegInfo* mesh_seg;        // [N][E]
   uint2* mesh_bbox;             // [N][E][mesh_cap] packed (bx, by) of each listed triangle, coalesced for the tile scan
+  // the same lists binned by half-tile of the entity's screen box (mesh_setup_kernel): bin b holds
+  // mesh_bin_idx[mesh_bin_off[b] .. mesh_bin_off[b + 1]) = triangles that can touch that half-tile
+  uint16_t* mesh_bin_idx;       // [N][E][MWB_BIN_REFS * mesh_cap]
+  int32_t* mesh_bin_off;        // [N][E][MWB_MAX_BINS + 1]
   int32_t mesh_cap;             // 0 = the level has no mesh entities
   TriRec* room_tris;            // [N][tri_cap] room + box triangle lists in HBM for levels whose lists do
                                 //   not fit shared memory (Maze); null = lists live in shared memory
