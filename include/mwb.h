@@ -54,6 +54,8 @@ extern "C" {
 #define MWB_RULE_GOAL 1   /* near(box) -> +_reward(), terminated (hallway.py:67-74, oneroom.py */
                           /* :64-71, fourrooms.py:66-73, maze.py:155-162)                      */
 #define MWB_RULE_PICKUP 2 /* carrying -> remove, reward = 1 (pickupobjects.py:83-95)          */
+#define MWB_RULE_SIDEWALK 3 /* agent inside the street room -> terminated (reward 0), then the  */
+                          /* GOAL rule (sidewalk.py:93-104); rule_arg = box slot | room << 8   */
 
 /* surfaces of a room */
 #define MWB_SURF_WALL 0
@@ -65,6 +67,10 @@ extern "C" {
 #define MWB_OP_CHOICE 1   /* ireg[a] = np_random.choice(b)            (== integers(0, b))      */
 #define MWB_OP_UNIFORM 2  /* freg[a] = np_random.uniform(f[0], f[1])                           */
 #define MWB_OP_PLACE 3    /* place_entity(); see mwb_op                                         */
+#define MWB_OP_IFEQ 5     /* run the next op only if ireg[a] == b (a level's `if rng.integers(0, 2) == 0:`)   */
+#define MWB_OP_PUT 6      /* place_entity(ent, pos=f[0..2], dir=f[3]) (miniworld.py:862-869): no search, no    */
+                          /* draw unless f[3] is NaN (then dir = uniform(-pi, pi)); b = 1: a bare               */
+                          /* entities.append(ent), which does not trigger _gen_static_data                      */
 #define MWB_OP_MAZE 4     /* Maze._gen_world() room topology (reference envs/maze.py:73-153): recursive  */
                           /* backtracker on the env's RNG stream, geometry from mwb_set_maze templates   */
 

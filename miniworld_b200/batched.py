@@ -20,7 +20,7 @@ performs the same step with pinned host buffers for callers that want numpy.
 import numpy as np
 
 from . import pack
-from .engine import Engine, RULE_GOAL, RULE_NONE, RULE_PICKUP, generator_from_state, rng_state_of, RNG_DTYPE
+from .engine import Engine, RULE_GOAL, RULE_NONE, RULE_PICKUP, RULE_SIDEWALK, generator_from_state, rng_state_of, RNG_DTYPE
 from .envs import LEVELS
 from .program import ResetProgram
 
@@ -55,8 +55,7 @@ class BatchedMiniWorld:
         if rule is None:
             raise TypeError("%s has no `device_rule`; use world.MiniWorldEnv (single env) for levels whose "
                             "step() rule is not lowered" % self.level_cls.__name__)
-        rule = (RULE_GOAL, rule[1]) if rule[0] == "goal" else (RULE_PICKUP, rule[1]) if rule[0] == "pickup" \
-            else (RULE_NONE, 0)
+        rule = {"goal": RULE_GOAL, "pickup": RULE_PICKUP, "sidewalk": RULE_SIDEWALK, "none": RULE_NONE}[rule[0]], rule[1]
         self.device_reset = getattr(pe, "device_program", None) is not None
 
         rooms, quads, segs = pack.pack_geometry(pe)
@@ -89,7 +88,8 @@ class BatchedMiniWorld:
         self.engine = Engine(self.num_envs, obs_width, obs_height, msaa_samples,
                              shared_geometry=shared, max_rooms=caps[0], max_quads=caps[1],
                              max_segs=caps[2], max_ents=max_ents, rule=rule, domain_rand=self.domain_rand,
-                             max_episode_steps=self.max_episode_steps, autoreset=autoreset and self.device_reset,
+                             max_episode_steps=int(min(self.max_episode_steps, 2 ** 31 - 1)),   # math.inf: never truncates
+                             autoreset=autoreset and self.device_reset,
                              device=device, lib_path=lib_path)
         self.autoreset = bool(autoreset)
         eng = self.engine

@@ -84,6 +84,15 @@ MWB_DEV CarryPos carry_pos(const DevState& S, int i, double apx, double apz, dou
   return o;
 }
 
+// Room.point_inside: all(sum(edge_norms * (p - outline), axis=1) > 0)
+MWB_DEV bool room_contains(const mwb_room& r, double px, double pz) {
+  for (int e = 0; e < r.num_edges; ++e) {
+    double d = d_add(d_mul(r.edge_nx[e], d_sub(px, r.edge_px[e])), d_mul(r.edge_nz[e], d_sub(pz, r.edge_pz[e])));
+    if (!(d > 0.0)) return false;
+  }
+  return true;
+}
+
 struct StepOut {
   double reward;
   int terminated, truncated;
@@ -172,9 +181,17 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
   o.terminated = 0;
   o.truncated = sc >= S.max_episode_steps ? 1 : 0;
 
-  if (S.rule_kind == MWB_RULE_GOAL) {
+  if (S.rule_kind == MWB_RULE_SIDEWALK) {
+    // sidewalk.py:96-99: stepping into the street ends the episode with reward 0, before the goal test
+    const mwb_room& street = S.rooms[(size_t)geom_index(S, i) * S.R + (S.rule_arg >> 8)];
+    if (room_contains(street, px, pz)) {
+      o.reward = 0.0;
+      o.terminated = 1;
+    }
+  }
+  if (S.rule_kind == MWB_RULE_GOAL || S.rule_kind == MWB_RULE_SIDEWALK) {
     // near(box): np.linalg.norm(box.pos - agent.pos) < r_box + r_agent + 1.1 * max_forward_step
-    int b = S.rule_arg;
+    int b = S.rule_arg & 0xFF;
     int bp = S.ent_proto[b * N + i];
     if (bp >= 0) {
       double dx = d_sub(S.ent_px[b * N + i], px);

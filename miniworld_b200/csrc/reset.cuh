@@ -6,20 +6,22 @@
 // numpy PCG64 stream in exactly the reference's call order, so that an episode reset on the
 // GPU lands on the same poses, colours and camera parameters as `env.reset()` in Python.
 // The level's `_gen_world()` is lowered on the host into a short program of
-// CHOICE / UNIFORM / PLACE ops (miniworld_b200/program.py); room layout comes from the
+// CHOICE / UNIFORM / PLACE / PUT / IFEQ ops (miniworld_b200/program.py); room layout comes from the
 // shared static template.  Levels whose topology is random per episode (Maze) reset on the
 // host and arrive through mwb_set_world instead.
 #pragma once
 #include "maze.cuh"
 #include "physics.cuh"
 
-// Room.point_inside: all(sum(edge_norms * (p - outline), axis=1) > 0)
-MWB_DEV bool room_contains(const mwb_room& r, double px, double pz) {
-  for (int e = 0; e < r.num_edges; ++e) {
-    double d = d_add(d_mul(r.edge_nx[e], d_sub(px, r.edge_px[e])), d_mul(r.edge_nz[e], d_sub(pz, r.edge_pz[e])));
-    if (!(d > 0.0)) return false;
-  }
-  return true;
+// the first place_entity triggers _gen_static_data: per room Texture.get(wall / floor / ceil), each one
+// rng.integers(0, n_variants) under domain randomisation (opengl.py:113-145)
+MWB_DEV void draw_room_textures(const DevState& S, int i, const mwb_room* rooms, int n_rooms, NpRng& rng) {
+  for (int r = 0; r < n_rooms; ++r)
+    for (int k = 0; k < 3; ++k) {
+      int v = 0;
+      if (S.domain_rand) v = (int)rng_integers(rng, (uint32_t)rooms[r].tex_count[k]);
+      S.room_tex[((size_t)i * S.R + r) * 3 + k] = rooms[r].tex_first[k] + v;
+    }
 }
 
 MWB_DEV void device_reset(const DevState& S, int i) {
@@ -54,19 +56,35 @@ MWB_DEV void device_reset(const DevState& S, int i) {
       if (S.maze != nullptr && !S.shared_geom && maze_generate(S, *S.maze, S.maze_cdf, i, rng)) n_rooms = S.num_rooms[g];
       continue;
     }
+    if (op.op == MWB_OP_IFEQ) {
+      if (ireg[op.a & 7] != op.b) ++pc;
+      continue;
+    }
+    if (op.op == MWB_OP_PUT) {
+      if (!static_done && op.b == 0) {
+        draw_room_textures(S, i, rooms, n_rooms, rng);
+        static_done = true;
+      }
+      const mwb_proto& pr = S.protos[op.a];
+      const double dir = isnan(op.f[3]) ? rng_uniform(rng, -3.141592653589793, d_sub(3.141592653589793, -3.141592653589793))
+                                        : op.f[3];
+      const int e = slots++;
+      S.ent_proto[e * N + i] = op.a;
+      S.ent_px[e * N + i] = op.f[0];
+      S.ent_py[e * N + i] = op.f[1];
+      S.ent_pz[e * N + i] = op.f[2];
+      S.ent_dir[e * N + i] = dir;
+      for (int k = 0; k < 3; ++k) S.ent_col[((size_t)e * 3 + k) * N + i] = pr.color[k];
+      S.num_slots[i] = slots;
+      continue;
+    }
     if (op.op == MWB_OP_CHOICE) {
       ireg[op.a & 7] = (int)rng_integers(rng, (uint32_t)op.b);
     } else if (op.op == MWB_OP_UNIFORM) {
       freg[op.a & 7] = rng_uniform(rng, op.f[0], d_sub(op.f[1], op.f[0]));
     } else if (op.op == MWB_OP_PLACE) {
       if (!static_done) {
-        // first place_entity triggers _gen_static_data: per room Texture.get(wall/floor/ceil)
-        for (int r = 0; r < n_rooms; ++r)
-          for (int k = 0; k < 3; ++k) {
-            int v = 0;
-            if (S.domain_rand) v = (int)rng_integers(rng, (uint32_t)rooms[r].tex_count[k]);
-            S.room_tex[((size_t)i * S.R + r) * 3 + k] = rooms[r].tex_first[k] + v;
-          }
+        draw_room_textures(S, i, rooms, n_rooms, rng);
         static_done = true;
       }
       int proto = op.a;

@@ -11,9 +11,9 @@ import os
 import numpy as np
 
 ABI_VERSION = 6
-RULE_NONE, RULE_GOAL, RULE_PICKUP = 0, 1, 2
+RULE_NONE, RULE_GOAL, RULE_PICKUP, RULE_SIDEWALK = 0, 1, 2, 3
 SURF_WALL, SURF_FLOOR, SURF_CEIL = 0, 1, 2
-OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE, OP_MAZE = 0, 1, 2, 3, 4
+OP_END, OP_CHOICE, OP_UNIFORM, OP_PLACE, OP_MAZE, OP_IFEQ, OP_PUT = 0, 1, 2, 3, 4, 5, 6
 MAX_EDGES = 8
 MAX_ENTS_CAP = 32
 

@@ -1,11 +1,11 @@
 """Level definitions and id registration (reference miniworld/envs/__init__.py:44-157).
 
-The five levels of BASELINE.json's configs (Hallway, OneRoom, FourRooms, Maze, PickupObjects) run on
-the batched engine with device-side resets and lowered rules; the others listed here use entity
-kinds the engine renders too (Box, Ball, Key, textured meshes, image / text frames) and run through
-the single-environment class -- all 23 ids of the reference are registered.
-`MiniWorld-MazeS8-v0` is the 8x8 maze (the reference's `MiniWorld-Maze-v0` default) under the name
-BASELINE.json uses.
+All 23 ids of the reference are registered (+ `MiniWorld-MazeS8-v0`, the name BASELINE.json uses for the 8x8
+`MiniWorld-Maze-v0` default).  Twenty-one of the 24 run on the batched engine with device-side resets and
+lowered rules (`device_program` / `device_rule`): Hallway, OneRoom (+S6, S6Fast), FourRooms, Maze (+S2, S3,
+S3Fast, S8), PickupObjects, TMaze / YMaze (+Left, Right), WallGap, ThreeRooms, Sidewalk, RoomObjects.
+PutNext (per-episode box sizes), CollectHealth (health counter, respawning kits) and Sign (dict observations)
+run through the single-environment class: GPU physics + render, the level's Python `step()` rule.
 """
 from .._gym import gym
 from .collecthealth import CollectHealth
@@ -35,7 +35,7 @@ LEVELS = {
     "MiniWorld-MazeS3-v0": MazeS3,
     "MiniWorld-MazeS3Fast-v0": MazeS3Fast,
     "MiniWorld-PickupObjects-v0": PickupObjects,
-    # levels outside BASELINE.json's configs: single-env GPU path (world.MiniWorldEnv), Python rule
+    # levels outside BASELINE.json's configs
     "MiniWorld-CollectHealth-v0": CollectHealth,
     "MiniWorld-PutNext-v0": PutNext,
     "MiniWorld-RoomObjects-v0": RoomObjects,

@@ -24,5 +24,14 @@ class RoomObjects(MiniWorldEnv, utils.EzPickle):
         self.place_entity(Key(color=pick()))
         self.place_agent()
 
+    device_rule = ("none", 0)
+
+    def device_program(self, prog):
+        prog.set_agent(self.agent)                           # radius 1.5
+        for make in (lambda c: Box(color=c, size=0.9), lambda c: Ball(color=c, size=0.9), lambda c: Key(color=c)):
+            colour = prog.choice(len(COLOR_NAMES))           # drawn while the entity is constructed, before place_entity
+            prog.place(prog.proto_row([make(c) for c in COLOR_NAMES]), index=colour)
+        prog.place_agent()
+
     def step(self, action):
         return super().step(action)

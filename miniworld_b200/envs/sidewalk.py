@@ -26,6 +26,20 @@ class Sidewalk(MiniWorldEnv, utils.EzPickle):
         self.box = self.place_entity(Box(color="red"), room=walk, min_z=walk.max_z - 2, max_z=walk.max_z)
         self.place_agent(room=walk, min_z=0, max_z=1.5)
 
+    @property
+    def device_rule(self):
+        n_cones = len(range(1, int(self.rooms[0].max_z // 2)))
+        return ("sidewalk", (1 + n_cones) | (1 << 8))     # box slot after the building and the cones; street = room 1
+
+    def device_program(self, prog):
+        walk = self.rooms[0]
+        prog.put(prog.proto(MeshEnt(mesh_name="building", height=30)), pos=[30, 0, 30], dir=-math.pi)
+        cone = prog.proto(MeshEnt(mesh_name="cone", height=0.75))
+        for i in range(1, int(walk.max_z // 2)):
+            prog.put(cone, pos=[1, 0, 2 * i])                  # dir drawn: uniform(-pi, pi)
+        prog.place(prog.proto(Box(color="red")), room=0, min_z=walk.max_z - 2, max_z=walk.max_z)
+        prog.place_agent(room=0, min_z=0, max_z=1.5)
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         if self.street.point_inside(self.agent.pos):

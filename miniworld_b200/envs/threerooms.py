@@ -27,5 +27,17 @@ class ThreeRooms(MiniWorldEnv, utils.EzPickle):
         self.place_entity(Ball(color="green"))
         self.place_agent()
 
+    device_rule = ("none", 0)
+
+    def device_program(self, prog):
+        prog.place(prog.proto(Box(color="red")))
+        prog.place(prog.proto(Box(color="green", size=0.6)))
+        prog.put(prog.proto(ImageFrame(pos=[0, 1.35, 7], dir=math.pi / 2, width=1.8, tex_name="logo_mila")),
+                 pos=[0, 1.35, 7], dir=math.pi / 2, append_only=True)
+        prog.place(prog.proto(MeshEnt(mesh_name="duckie", height=0.25, static=False)))
+        prog.place(prog.proto(Key(color="blue")))
+        prog.place(prog.proto(Ball(color="green")))
+        prog.place_agent()
+
     def step(self, action):
         return super().step(action)

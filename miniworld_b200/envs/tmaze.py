@@ -29,6 +29,21 @@ class TMaze(MiniWorldEnv, utils.EzPickle):
         heading = self.np_random.uniform(-math.pi / 4, math.pi / 4)
         self.place_agent(dir=heading, room=stem)
 
+    device_rule = ("goal", 0)
+
+    def device_program(self, prog):
+        stem, bar = self.rooms[0], self.rooms[1]
+        box = prog.proto(Box(color="red"))
+        if self.goal_pos is not None:
+            gx, _, gz = self.goal_pos
+            prog.place(box, min_x=gx, max_x=gx, min_z=gz, max_z=gz)
+        else:
+            side = prog.choice(2)
+            prog.place(box, room=1, max_z=bar.min_z + 2, when=(side, 0))
+            prog.place(box, room=1, min_z=bar.max_z - 2, when=(side, 1), same_slot=True)
+        heading = prog.uniform(-math.pi / 4, math.pi / 4)
+        prog.place_agent(dir=heading, room=0)
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         if self.near(self.box):

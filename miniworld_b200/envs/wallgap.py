@@ -25,6 +25,13 @@ class WallGap(MiniWorldEnv, utils.EzPickle):
         self.place_entity(MeshEnt(mesh_name="building", height=30), pos=np.array([30, 0, 30]), dir=-math.pi)
         self.place_agent(room=top)
 
+    device_rule = ("goal", 0)
+
+    def device_program(self, prog):
+        prog.place(prog.proto(Box(color="red")), room=1)
+        prog.put(prog.proto(MeshEnt(mesh_name="building", height=30)), pos=[30, 0, 30], dir=-math.pi)
+        prog.place_agent(room=0)
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         if self.near(self.box):

@@ -39,6 +39,21 @@ class YMaze(MiniWorldEnv, utils.EzPickle):
         heading = self.np_random.uniform(-math.pi / 4, math.pi / 4)
         self.place_agent(dir=heading, room=main_arm)
 
+    device_rule = ("goal", 0)
+
+    def device_program(self, prog):
+        left_arm, right_arm = self.rooms[2], self.rooms[3]     # add_room order: main arm, hub, left, right
+        box = prog.proto(Box(color="red"))
+        if self.goal_pos is not None:
+            gx, _, gz = self.goal_pos
+            prog.place(box, min_x=gx, max_x=gx, min_z=gz, max_z=gz)
+        else:
+            side = prog.choice(2)
+            prog.place(box, room=2, max_z=left_arm.min_z + 2.5, when=(side, 0))
+            prog.place(box, room=3, min_z=right_arm.max_z - 2.5, when=(side, 1), same_slot=True)
+        heading = prog.uniform(-math.pi / 4, math.pi / 4)
+        prog.place_agent(dir=heading, room=0)
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         if self.near(self.box):

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from .engine import OP_CHOICE, OP_DTYPE, OP_MAZE, OP_PLACE, OP_UNIFORM, PROTO_DTYPE
+from .engine import OP_CHOICE, OP_DTYPE, OP_IFEQ, OP_MAZE, OP_PLACE, OP_PUT, OP_UNIFORM, PROTO_DTYPE
 from .entity import Agent
 from .pack import proto_record
 
@@ -39,6 +39,17 @@ class ResetProgram:
     def proto(self, ent):
         self.protos.append(proto_record(ent))
         return len(self.protos) - 1
+
+    def set_agent(self, agent):
+        """The level changes the agent's physical constants (RoomObjects: `self.agent.radius = 1.5`)."""
+        self.protos[self.agent_proto] = proto_record(agent)
+
+    def proto_row(self, ents):
+        """1-D table of entities indexed by one CHOICE result."""
+        base = len(self.protos)
+        for ent in ents:
+            self.proto(ent)
+        return ProtoTable(base, (1, 0))
 
     def proto_table(self, nested):
         """2-D table of entities indexed by two CHOICE results."""
@@ -77,16 +88,36 @@ class ResetProgram:
         return _Reg(self._freg - 1)
 
     # ---- placement
+    def put(self, proto, pos, dir=None, append_only=False):
+        """place_entity(ent, pos=pos, dir=dir): no search; dir=None draws uniform(-pi, pi).  append_only: a bare
+        `self.entities.append(ent)` (does not trigger the static-data texture draws)."""
+        op = np.zeros((), OP_DTYPE)
+        op["op"], op["a"], op["b"] = OP_PUT, int(proto), int(append_only)
+        op["f"] = [float(pos[0]), float(pos[1]), float(pos[2]), math.nan if dir is None else float(dir)]
+        self.ops.append(op)
+        self.num_placed += 1
+        return self.num_placed - 1
+
     def place(self, proto, index=None, room=None, dir=None, min_x=None, max_x=None, min_z=None, max_z=None,
-              _agent=False):
+              when=None, same_slot=False, _agent=False):
+        """place_entity(...).  when=(reg, value): the call sits in an `if reg == value:` branch of _gen_world();
+        the other branches are stated with further place(..., when=..., same_slot=True) calls -- exactly one of
+        them runs per reset and fills the one entity slot."""
+        if when is not None:
+            cond = np.zeros((), OP_DTYPE)
+            cond["op"], cond["a"], cond["b"] = OP_IFEQ, when[0].index, int(when[1])
+            self.ops.append(cond)
+        if same_slot:
+            self.num_placed -= 1
         op = np.zeros((), OP_DTYPE)
         op["op"] = OP_PLACE
         op["ireg_a"] = op["ireg_b"] = -1
         if isinstance(proto, ProtoTable):
             op["a"] = proto.base
-            ia, ib = index
+            ia, ib = index if isinstance(index, (tuple, list)) else (index, None)
             op["ireg_a"], op["stride_a"] = ia.index, proto.strides[0]
-            op["ireg_b"], op["stride_b"] = ib.index, proto.strides[1]
+            if ib is not None:
+                op["ireg_b"], op["stride_b"] = ib.index, proto.strides[1]
         else:
             op["a"] = int(proto)
         op["room"] = -1 if room is None else int(room)

@@ -14,6 +14,13 @@ CASES = {
     "pickup_dr": ("MiniWorld-PickupObjects-v0", True),
     "maze_dr": ("MiniWorld-MazeS8-v0", True),
     "mazes3": ("MiniWorld-MazeS3-v0", False),
+    # levels beyond BASELINE.json's configs whose _gen_world() / rule are lowered too
+    "tmaze": ("MiniWorld-TMaze-v0", False),
+    "ymaze_dr": ("MiniWorld-YMaze-v0", True),
+    "wallgap": ("MiniWorld-WallGap-v0", False),
+    "sidewalk_dr": ("MiniWorld-Sidewalk-v0", True),
+    "threerooms_dr": ("MiniWorld-ThreeRooms-v0", True),
+    "roomobjs": ("MiniWorld-RoomObjects-v0", False),
 }
 
 

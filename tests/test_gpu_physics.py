@@ -17,6 +17,12 @@ def test_device_reset_levels_bit_exact(libmwb_path, name):
     assert T >= 300 and N >= 16
 
 
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs"])
+def test_lowered_extra_levels_bit_exact(libmwb_path, name):
+    """Levels beyond BASELINE.json's configs on the batched engine (IFEQ / PUT reset ops, street rule)."""
+    run_trajectory(name, golden(name), libmwb_path, check_every=5)
+
+
 @pytest.mark.parametrize("name", ["mazes3", "maze_dr"])
 def test_host_reset_levels_bit_exact(libmwb_path, name):
     run_trajectory(name, golden(name), libmwb_path, check_every=5)

@@ -136,3 +136,14 @@ def test_snapshot_restore_resumes_bit_exact(hostsim_path, level):
 def test_fused_observation_layouts(hostsim_path):
     from helpers import obs_format_parity
     obs_format_parity(hostsim_path, n=2, steps=2)
+
+
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs"])
+def test_lowered_extra_levels_bit_exact(hostsim_path, name):
+    """TMaze / YMaze (branching placement, polygon rooms), WallGap / ThreeRooms / Sidewalk (fixed-pose entities,
+    meshes, the street rule) through the batched engine with device-side resets vs the reference trajectories."""
+    g = golden(name)
+    env = make_env(name, g, hostsim_path, n=2)
+    assert env.device_reset
+    env.close()
+    run_trajectory(name, g, hostsim_path, steps=150, check_every=10)
