@@ -57,6 +57,15 @@ extern "C" {
 #define MWB_RULE_SIDEWALK 3 /* agent inside the street room -> terminated (reward 0), then the  */
                           /* GOAL rule (sidewalk.py:93-104); rule_arg = box slot | room << 8   */
 
+#define MWB_RULE_SIGN 4   /* action 3 ends the episode; touching one of the six objects (slots 0..5:   */
+                          /* kind = slot / 3, colour = slot % 3) ends it with reward +1 / -1            */
+                          /* (sign.py:158-173); rule_arg = colour index | goal << 8                     */
+
+#define MWB_RULE_HEALTH 5 /* health -= 2 per step; pickup while carrying: the kit is removed from the list, */
+                          /* placed again (place_entity on the env's stream) and health = 100; reward 2, or  */
+                          /* -100 and terminated once health <= 0 (collecthealth.py:62-86).  The per-env     */
+                          /* level counter (num_picked_up in mwb_state_view) holds the health.               */
+
 /* surfaces of a room */
 #define MWB_SURF_WALL 0
 #define MWB_SURF_FLOOR 1

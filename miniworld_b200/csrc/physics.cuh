@@ -93,6 +93,50 @@ MWB_DEV bool room_contains(const mwb_room& r, double px, double pz) {
   return true;
 }
 
+// place_entity's search loop (miniworld.py:871-909): pick a room (fixed, or Generator.choice(n, p=room_probs) =
+// searchsorted(cdf, random(), 'right')), draw a position in its (optionally overridden) extents grown by the
+// entity's radius, retry until it is inside the room and free; then the heading (given, or uniform(-pi, pi)).
+#define MWB_NAN (__builtin_nan(""))
+MWB_DEV void place_search(const DevState& S, int i, NpRng& rng, const mwb_room* rooms, int n_rooms, int room_fixed,
+                          const double bounds[4], const mwb_proto& pr, double dir_given, double& x, double& z, double& dir) {
+  const double rad = pr.radius;
+  for (;;) {
+    int r = room_fixed;
+    if (r < 0) {
+      double u = rng_random(rng);
+      r = 0;
+      while (r < n_rooms - 1 && rooms[r].cdf <= u) ++r;
+    }
+    const mwb_room& rm = rooms[r];
+    double lx = isnan(bounds[0]) ? rm.min_x : bounds[0];
+    double hx = isnan(bounds[1]) ? rm.max_x : bounds[1];
+    double lz = isnan(bounds[2]) ? rm.min_z : bounds[2];
+    double hz = isnan(bounds[3]) ? rm.max_z : bounds[3];
+    double lox = d_sub(lx, rad), loz = d_sub(lz, rad);
+    x = rng_uniform(rng, lox, d_sub(d_add(hx, rad), lox));
+    (void)rng_random(rng);   // the y component: uniform(0, 0) still consumes a draw
+    z = rng_uniform(rng, loz, d_sub(d_add(hz, rad), loz));
+    if (!room_contains(rm, x, z)) continue;
+    if (world_intersect(S, i, -1, x, z, rad, pr.radius_is_f32 != 0) != MWB_HIT_NONE) continue;
+    dir = isnan(dir_given) ? rng_uniform(rng, -3.141592653589793, d_sub(3.141592653589793, -3.141592653589793)) : dir_given;
+    return;
+  }
+}
+
+// MiniWorldEnv.near(ent): np.linalg.norm(ent.pos - agent.pos) < ent.radius + agent.radius + 1.1 * max_forward_step
+// (3-D distance through BLAS ddot, i.e. an FMA chain)
+MWB_DEV bool near_agent(const DevState& S, int i, int b, int as, double ar) {
+  const size_t N = S.N;
+  const int bp = S.ent_proto[b * N + i];
+  if (bp < 0) return false;
+  const double dx = d_sub(S.ent_px[b * N + i], S.ent_px[as * N + i]);
+  const double dy = d_sub(S.ent_py[b * N + i], S.ent_py[as * N + i]);
+  const double dz = d_sub(S.ent_pz[b * N + i], S.ent_pz[as * N + i]);
+  const double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
+  const mwb_proto& pr = S.protos[bp];
+  return d < d_add(sum_radii(pr.radius, pr.radius_is_f32 != 0, ar, false), S.near_extra);
+}
+
 struct StepOut {
   double reward;
   int terminated, truncated;
@@ -190,20 +234,67 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
     }
   }
   if (S.rule_kind == MWB_RULE_GOAL || S.rule_kind == MWB_RULE_SIDEWALK) {
-    // near(box): np.linalg.norm(box.pos - agent.pos) < r_box + r_agent + 1.1 * max_forward_step
-    int b = S.rule_arg & 0xFF;
-    int bp = S.ent_proto[b * N + i];
-    if (bp >= 0) {
-      double dx = d_sub(S.ent_px[b * N + i], px);
-      double dy = d_sub(S.ent_py[b * N + i], S.ent_py[as * N + i]);
-      double dz = d_sub(S.ent_pz[b * N + i], pz);
-      double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
-      const mwb_proto& pr = S.protos[bp];
-      double thr = d_add(sum_radii(pr.radius, pr.radius_is_f32 != 0, ar, false), S.near_extra);
-      if (d < thr) {
-        o.reward = d_add(o.reward, d_sub(1.0, d_mul(0.2, d_div((double)sc, (double)S.max_episode_steps))));
+    if (near_agent(S, i, S.rule_arg & 0xFF, as, ar)) {
+      o.reward = d_add(o.reward, d_sub(1.0, d_mul(0.2, d_div((double)sc, (double)S.max_episode_steps))));
+      o.terminated = 1;
+    }
+  } else if (S.rule_kind == MWB_RULE_SIGN) {
+    // sign.py:158-173: the extra action ends the episode; touching any of the six objects ends it with
+    // reward +1 for the object the sign names (colour index, kind = goal) and -1 otherwise (the last hit wins)
+    if (action == 3) o.terminated = 1;
+    const int colour = S.rule_arg & 0xFF, goal = (S.rule_arg >> 8) & 0xFF;
+    for (int b = 0; b < 6; ++b)
+      if (near_agent(S, i, b, as, ar)) {
         o.terminated = 1;
+        o.reward = (b % 3 == colour && b / 3 == goal) ? 1.0 : -1.0;
       }
+  } else if (S.rule_kind == MWB_RULE_HEALTH) {
+    // collecthealth.py:62-86.  The level counter (num_picked) holds the agent's health.
+    int health = S.num_picked[i] - 2;
+    if (action == 4 && carrying >= 0) {
+      // the kit in hand is consumed and respawned: entities.remove(kit); place_entity(kit).  This step's
+      // observation was rendered before that, so the frame still shows it at its carry pose (ghost).
+      const int k = carrying, n = S.num_slots[i], kp = S.ent_proto[k * N + i];
+      S.ghost_slot[i] = n - 1;
+      S.ghost_proto[i] = kp;
+      S.ghost_pose[0 * N + i] = S.ent_px[k * N + i];
+      S.ghost_pose[1 * N + i] = S.ent_py[k * N + i];
+      S.ghost_pose[2 * N + i] = S.ent_pz[k * N + i];
+      S.ghost_pose[3 * N + i] = S.ent_dir[k * N + i];
+      for (int c = 0; c < 3; ++c) S.ghost_col[c * N + i] = S.ent_col[((size_t)k * 3 + c) * N + i];
+      for (int e = k; e + 1 < n; ++e) {       // list.remove(): later entities move up one place
+        S.ent_proto[e * N + i] = S.ent_proto[(e + 1) * N + i];
+        S.ent_px[e * N + i] = S.ent_px[(e + 1) * N + i];
+        S.ent_py[e * N + i] = S.ent_py[(e + 1) * N + i];
+        S.ent_pz[e * N + i] = S.ent_pz[(e + 1) * N + i];
+        S.ent_dir[e * N + i] = S.ent_dir[(e + 1) * N + i];
+        for (int c = 0; c < 3; ++c) S.ent_col[((size_t)e * 3 + c) * N + i] = S.ent_col[((size_t)(e + 1) * 3 + c) * N + i];
+      }
+      int as2 = as > k ? as - 1 : as;
+      S.agent_slot[i] = as2;
+      S.ent_proto[(n - 1) * N + i] = -1;
+      S.num_slots[i] = n - 1;
+      const int g = geom_index(S, i);
+      const double nob[4] = {MWB_NAN, MWB_NAN, MWB_NAN, MWB_NAN};
+      NpRng rng = load_rng(S, i);
+      double x, z, dir;
+      place_search(S, i, rng, S.rooms + (size_t)g * S.R, S.num_rooms[g], -1, nob, S.protos[kp], MWB_NAN, x, z, dir);
+      store_rng(S, i, rng);
+      S.ent_proto[(n - 1) * N + i] = kp;      // list.append()
+      S.ent_px[(n - 1) * N + i] = x;
+      S.ent_py[(n - 1) * N + i] = 0.0;
+      S.ent_pz[(n - 1) * N + i] = z;
+      S.ent_dir[(n - 1) * N + i] = dir;
+      S.num_slots[i] = n;
+      carrying = -1;
+      health = 100;
+    }
+    S.num_picked[i] = health;
+    if (health > 0) {
+      o.reward = 2.0;
+    } else {
+      o.reward = -100.0;
+      o.terminated = 1;
     }
   } else if (S.rule_kind == MWB_RULE_PICKUP) {
     if (carrying >= 0) {

@@ -34,7 +34,7 @@ MWB_DEV void device_reset(const DevState& S, int i) {
 
   S.step_count[i] = 0;
   S.carrying[i] = -1;
-  S.num_picked[i] = 0;
+  S.num_picked[i] = S.rule_kind == MWB_RULE_HEALTH ? 100 : 0;   // CollectHealth: self.health = 100
   S.ghost_slot[i] = -1;
   S.num_slots[i] = 0;
   for (int e = 0; e < S.E; ++e) S.ent_proto[e * N + i] = -1;
@@ -91,31 +91,10 @@ MWB_DEV void device_reset(const DevState& S, int i) {
       if (op.ireg_a >= 0) proto += ireg[op.ireg_a & 7] * op.stride_a;
       if (op.ireg_b >= 0) proto += ireg[op.ireg_b & 7] * op.stride_b;
       const mwb_proto& pr = S.protos[proto];
-      const double rad = pr.radius;
       double x, z, dir;
-      for (;;) {
-        int r = op.room;
-        if (r < 0) {   // Generator.choice(n, p=room_probs): searchsorted(cdf, random(), 'right')
-          double u = rng_random(rng);
-          r = 0;
-          while (r < n_rooms - 1 && rooms[r].cdf <= u) ++r;
-        }
-        const mwb_room& rm = rooms[r];
-        double lx = isnan(op.f[0]) ? rm.min_x : op.f[0];
-        double hx = isnan(op.f[1]) ? rm.max_x : op.f[1];
-        double lz = isnan(op.f[2]) ? rm.min_z : op.f[2];
-        double hz = isnan(op.f[3]) ? rm.max_z : op.f[3];
-        double lox = d_sub(lx, rad), loz = d_sub(lz, rad);
-        x = rng_uniform(rng, lox, d_sub(d_add(hx, rad), lox));
-        (void)rng_random(rng);   // the y component: uniform(0, 0) still consumes a draw
-        z = rng_uniform(rng, loz, d_sub(d_add(hz, rad), loz));
-        if (!room_contains(rm, x, z)) continue;
-        S.num_slots[i] = slots;   // entities placed so far
-        if (world_intersect(S, i, -1, x, z, rad, pr.radius_is_f32 != 0) != MWB_HIT_NONE) continue;
-        dir = op.dir_freg >= 0 ? freg[op.dir_freg & 7]
-                               : rng_uniform(rng, -3.141592653589793, d_sub(3.141592653589793, -3.141592653589793));
-        break;
-      }
+      S.num_slots[i] = slots;   // entities placed so far
+      place_search(S, i, rng, rooms, n_rooms, op.room, op.f, pr,
+                   op.dir_freg >= 0 ? freg[op.dir_freg & 7] : MWB_NAN, x, z, dir);
       int e = slots++;
       S.ent_proto[e * N + i] = proto;
       S.ent_px[e * N + i] = x;

@@ -19,6 +19,14 @@ class CollectHealth(MiniWorldEnv, utils.EzPickle):
         self.place_agent()
         self.health = 100
 
+    device_rule = ("health", 0)
+
+    def device_program(self, prog):
+        kit = prog.proto(MeshEnt(mesh_name="medkit", height=0.40, static=False))
+        for _ in range(18):
+            prog.place(kit)
+        prog.place_agent()
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         self.health -= 2

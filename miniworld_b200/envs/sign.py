@@ -50,6 +50,22 @@ class Sign(MiniWorldEnv, utils.EzPickle):
         self.entities.append(TextFrame(pos=[s, 1.35, s + gap], dir=math.pi, str=text, height=1))
         self.place_agent(min_x=4, max_x=5, min_z=4, max_z=6)
 
+    @property
+    def device_rule(self):
+        return ("sign", self._color_index | (self._goal << 8))
+
+    def device_program(self, prog):
+        s, gap = self._size, 0.25
+        spots = [(Box(color="blue"), 1, 1), (Box(color="red"), 9, 1), (Box(color="green"), 9, 5),
+                 (BigKey(color="blue"), 5, 1), (BigKey(color="red"), 1, 5), (BigKey(color="green"), 1, 9)]
+        for ent, x, z in spots:
+            prog.put(prog.proto(ent), pos=(x, 0, z))          # place_entity(pos=...): dir = uniform(-pi, pi)
+        text = ["BLUE", "RED", "GREEN"][self._color_index]
+        frame = TextFrame(pos=[s, 1.35, s + gap], dir=math.pi, str=text, height=1)
+        frame.randomize(self.params, None)                    # builds the glyph quads (no draws: domain_rand is off)
+        prog.put(prog.proto(frame), pos=[s, 1.35, s + gap], dir=math.pi, append_only=True)
+        prog.place_agent(min_x=4, max_x=5, min_z=4, max_z=6)
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         if action == self.actions.move_forward + 1:

@@ -45,6 +45,8 @@ CASES = [
     ("collecthealth", "MiniWorld-CollectHealth-v0", {}, 4, 300),
     ("threerooms_dr", "MiniWorld-ThreeRooms-v0", {"domain_rand": True}, 6, 300),
     ("sign", "MiniWorld-Sign-v0", {}, 6, 120),
+    # pickup-heavy action mix (turns, forward, pickup): exercises CollectHealth's kit respawn
+    ("collecthealth_pick", "MiniWorld-CollectHealth-v0", {}, 6, 300, [0.15, 0.15, 0.4, 0.0, 0.3, 0.0, 0.0, 0.0]),
 ]
 
 
@@ -72,10 +74,13 @@ def snapshot(env, out, t, i):
     out["cam"][t, i] = [a.cam_height, a.cam_fwd_disp, a.cam_pitch, a.cam_fov_y]
 
 
-def run_case(name, env_id, kwargs, N, T):
+def run_case(name, env_id, kwargs, N, T, action_probs=None):
     env = make_reference_env(env_id, **kwargs)
     n_act = env.action_space.n
-    actions = np.random.default_rng(12345).integers(0, n_act, size=(T, N), dtype=np.int32)
+    if action_probs is None:
+        actions = np.random.default_rng(12345).integers(0, n_act, size=(T, N), dtype=np.int32)
+    else:
+        actions = np.random.default_rng(12345).choice(n_act, size=(T, N), p=action_probs).astype(np.int32)
     S = T + 1   # row 0 = state after the seeded reset
     out = dict(
         pos=np.zeros((S, N, 3)), dir=np.zeros((S, N)), step_count=np.zeros((S, N), np.int32),

@@ -21,6 +21,9 @@ CASES = {
     "sidewalk_dr": ("MiniWorld-Sidewalk-v0", True),
     "threerooms_dr": ("MiniWorld-ThreeRooms-v0", True),
     "roomobjs": ("MiniWorld-RoomObjects-v0", False),
+    "sign": ("MiniWorld-Sign-v0", False),
+    "collecthealth": ("MiniWorld-CollectHealth-v0", False),
+    "collecthealth_pick": ("MiniWorld-CollectHealth-v0", False),     # pickup-heavy action mix: kit respawns
 }
 
 
@@ -106,6 +109,7 @@ SINGLE_CASES = {
     "wallgap": ("MiniWorld-WallGap-v0", {}),
     "sidewalk_dr": ("MiniWorld-Sidewalk-v0", {"domain_rand": True}),
     "collecthealth": ("MiniWorld-CollectHealth-v0", {}),
+    "collecthealth_pick": ("MiniWorld-CollectHealth-v0", {}),
     "threerooms_dr": ("MiniWorld-ThreeRooms-v0", {"domain_rand": True}),
     "sign": ("MiniWorld-Sign-v0", {}),
     "fourrooms": ("MiniWorld-FourRooms-v0", {}),

@@ -64,7 +64,7 @@ def test_device_maze_long_rollout_with_resets(hostsim_path):
 
 
 @pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "roomobjs", "putnext_dr", "pickup", "wallgap", "sidewalk_dr",
-                                  "collecthealth", "threerooms_dr", "sign"])
+                                  "collecthealth", "collecthealth_pick", "threerooms_dr", "sign"])
 def test_single_env_levels_follow_reference(hostsim_path, name):
     """Levels outside the batched configs (and PickupObjects for the carry path) through the
     N = 1 engine with the level's own Python rule."""
@@ -138,7 +138,7 @@ def test_fused_observation_layouts(hostsim_path):
     obs_format_parity(hostsim_path, n=2, steps=2)
 
 
-@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs"])
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs", "sign", "collecthealth", "collecthealth_pick"])
 def test_lowered_extra_levels_bit_exact(hostsim_path, name):
     """TMaze / YMaze (branching placement, polygon rooms), WallGap / ThreeRooms / Sidewalk (fixed-pose entities,
     meshes, the street rule) through the batched engine with device-side resets vs the reference trajectories."""
@@ -146,4 +146,4 @@ def test_lowered_extra_levels_bit_exact(hostsim_path, name):
     env = make_env(name, g, hostsim_path, n=2)
     assert env.device_reset
     env.close()
-    run_trajectory(name, g, hostsim_path, steps=150, check_every=10)
+    run_trajectory(name, g, hostsim_path, steps=300 if name == "collecthealth_pick" else 150, check_every=10)
