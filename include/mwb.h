@@ -66,6 +66,9 @@ extern "C" {
                           /* -100 and terminated once health <= 0 (collecthealth.py:62-86).  The per-env     */
                           /* level counter (num_picked_up in mwb_state_view) holds the health.               */
 
+#define MWB_RULE_PUTNEXT 6 /* near(ent a, ent b) and not carrying -> +_reward(), terminated (putnext.py:61-66);  */
+                          /* rule_arg = slot a | slot b << 8                                                  */
+
 /* surfaces of a room */
 #define MWB_SURF_WALL 0
 #define MWB_SURF_FLOOR 1
@@ -191,7 +194,9 @@ typedef struct mwb_entity {
 
 typedef struct mwb_op {
   int32_t op;                /* MWB_OP_*                                                         */
-  int32_t a, b;              /* CHOICE: dst ireg, n.  UNIFORM: dst freg.  PLACE: proto base, -   */
+  int32_t a, b;              /* CHOICE: dst ireg, n.  UNIFORM: dst freg.  PLACE: proto base, 1 + freg holding   */
+                             /* this episode's Box edge length (0: the prototype's).  IFEQ: ireg, value.        */
+                             /* PUT: proto, append-only flag                                                    */
   int32_t ireg_a, stride_a;  /* PLACE: proto = a + ireg[ireg_a]*stride_a + ireg[ireg_b]*stride_b */
   int32_t ireg_b, stride_b;  /*        (ireg_* = -1: unused)                                     */
   int32_t room;              /* PLACE: fixed room index or -1 (sample by area)                   */

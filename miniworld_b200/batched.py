@@ -20,7 +20,7 @@ performs the same step with pinned host buffers for callers that want numpy.
 import numpy as np
 
 from . import pack
-from .engine import Engine, RULE_GOAL, RULE_NONE, RULE_HEALTH, RULE_PICKUP, RULE_SIDEWALK, RULE_SIGN, generator_from_state, rng_state_of, RNG_DTYPE
+from .engine import Engine, RULE_GOAL, RULE_NONE, RULE_HEALTH, RULE_PICKUP, RULE_PUTNEXT, RULE_SIDEWALK, RULE_SIGN, generator_from_state, rng_state_of, RNG_DTYPE
 from .envs import LEVELS
 from .program import ResetProgram
 
@@ -56,7 +56,7 @@ class BatchedMiniWorld:
         if rule is None:
             raise TypeError("%s has no `device_rule`; use world.MiniWorldEnv (single env) for levels whose "
                             "step() rule is not lowered" % self.level_cls.__name__)
-        rule = {"goal": RULE_GOAL, "pickup": RULE_PICKUP, "sidewalk": RULE_SIDEWALK, "sign": RULE_SIGN, "health": RULE_HEALTH, "none": RULE_NONE}[rule[0]], rule[1]
+        rule = {"goal": RULE_GOAL, "pickup": RULE_PICKUP, "sidewalk": RULE_SIDEWALK, "sign": RULE_SIGN, "health": RULE_HEALTH, "putnext": RULE_PUTNEXT, "none": RULE_NONE}[rule[0]], rule[1]
         self.device_reset = getattr(pe, "device_program", None) is not None
 
         rooms, quads, segs = pack.pack_geometry(pe)

@@ -213,6 +213,7 @@ MWB_DEV void scatter_one(const DevState& S, const WorldUpload& u) {
   for (int e = 0; e < S.E; ++e) {
     const bool live = e < u.num_slots && e < MWB_MAX_ENTS_CAP;
     S.ent_proto[e * N + i] = live ? u.ents[e].proto : -1;
+    S.ent_size[e * N + i] = 0.0;         // host-generated worlds carry each entity's own prototype
     if (!live) continue;
     S.ent_px[e * N + i] = u.ents[e].pos[0];
     S.ent_py[e * N + i] = u.ents[e].pos[1];
@@ -510,7 +511,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   int rc = 0;
 #define AL(field, count) if (!rc) rc = alloc_arr(h, &S.field, (count))
   AL(ent_proto, E * N); AL(ent_px, E * N); AL(ent_py, E * N); AL(ent_pz, E * N); AL(ent_dir, E * N);
-  AL(ent_col, E * 3 * N); AL(num_slots, N); AL(agent_slot, N); AL(carrying, N); AL(step_count, N);
+  AL(ent_col, E * 3 * N); AL(ent_size, E * N); AL(num_slots, N); AL(agent_slot, N); AL(carrying, N); AL(step_count, N);
   AL(num_picked, N); AL(needs_reset, N); AL(episodes_done, 1); AL(cam, 4 * N); AL(envp, 12 * N); AL(ghost_slot, N);
   AL(ghost_proto, N); AL(ghost_pose, 4 * N); AL(ghost_col, 3 * N);
   AL(rng_s_hi, N); AL(rng_s_lo, N); AL(rng_inc_hi, N); AL(rng_inc_lo, N); AL(rng_has32, N); AL(rng_cache, N);
@@ -1321,7 +1322,7 @@ static void snapshot_arrays(mwb_handle* h, std::vector<std::pair<void*, size_t>>
   const size_t N = S.N, E = S.E, G = S.shared_geom ? 1 : N;
 #define SA(field, count) v.push_back(std::make_pair((void*)S.field, (size_t)(count) * sizeof(*S.field)))
   SA(ent_proto, E * N); SA(ent_px, E * N); SA(ent_py, E * N); SA(ent_pz, E * N); SA(ent_dir, E * N);
-  SA(ent_col, E * 3 * N); SA(num_slots, N); SA(agent_slot, N); SA(carrying, N); SA(step_count, N);
+  SA(ent_col, E * 3 * N); SA(ent_size, E * N); SA(num_slots, N); SA(agent_slot, N); SA(carrying, N); SA(step_count, N);
   SA(num_picked, N); SA(needs_reset, N); SA(episodes_done, 1); SA(cam, 4 * N); SA(envp, 12 * N);
   SA(ghost_slot, N); SA(ghost_proto, N); SA(ghost_pose, 4 * N); SA(ghost_col, 3 * N);
   SA(rng_s_hi, N); SA(rng_s_lo, N); SA(rng_inc_hi, N); SA(rng_inc_lo, N); SA(rng_has32, N); SA(rng_cache, N);

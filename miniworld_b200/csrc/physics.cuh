@@ -43,6 +43,29 @@ MWB_DEV double sum_radii(double r0, bool r0_f32, double r1, bool r1_f32) {
   return d_add(r0, r1);
 }
 
+// Physical size of the entity in slot e: the prototype's, unless the level drew this episode's Box edge
+// length itself (PutNext: Box(size=rng.uniform(0.6, 0.85))); then Box.__init__'s arithmetic applies
+// (entity.py:396-403): radius = math.sqrt(sx * sx + sz * sz) / 2, height = sy.
+struct EntDims {
+  double radius, height, size;   // size = 0: prototype geometry
+  bool f32;
+};
+MWB_DEV EntDims ent_dims(const DevState& S, int i, int e, const mwb_proto& pr) {
+  EntDims d;
+  d.f32 = pr.radius_is_f32 != 0;
+  const double s = S.ent_size[(size_t)e * S.N + i];
+  if (s > 0.0) {
+    d.radius = d_div(d_sqrt(d_add(d_mul(s, s), d_mul(s, s))), 2.0);
+    d.height = s;
+    d.size = s;
+  } else {
+    d.radius = pr.radius;
+    d.height = pr.height;
+    d.size = 0.0;
+  }
+  return d;
+}
+
 // MiniWorldEnv.intersect: walls first, then the entity list in order (skipping `self_slot`).
 // np.linalg.norm of a 1-D vector goes through BLAS ddot, which accumulates with FMA:
 // sqrt(fma(dz, dz, fma(dy, dy, dx*dx))) with dy == 0 here.
@@ -58,8 +81,8 @@ MWB_DEV int world_intersect(const DevState& S, int i, int self_slot, double px, 
     double dx = d_sub(S.ent_px[(size_t)e * S.N + i], px);
     double dz = d_sub(S.ent_pz[(size_t)e * S.N + i], pz);
     double d = d_sqrt(d_fma(dz, dz, d_mul(dx, dx)));
-    const mwb_proto& pr = S.protos[p];
-    if (d < sum_radii(radius, radius_f32, pr.radius, pr.radius_is_f32 != 0)) return e;
+    const EntDims ed = ent_dims(S, i, e, S.protos[p]);
+    if (d < sum_radii(radius, radius_f32, ed.radius, ed.f32)) return e;
   }
   return MWB_HIT_NONE;
 }
@@ -70,9 +93,9 @@ struct CarryPos {
 
 // _get_carry_pos(agent_pos, ent): agent_pos + dir_vec * 1.05 * dist, lifted to stay visible
 MWB_DEV CarryPos carry_pos(const DevState& S, int i, double apx, double apz, double c, double s, int slot, double ar) {
-  const mwb_proto& pr = S.protos[S.ent_proto[(size_t)slot * S.N + i]];
+  const EntDims pr = ent_dims(S, i, slot, S.protos[S.ent_proto[(size_t)slot * S.N + i]]);
   double dist;   // agent.radius + ent.radius + max_forward_step, float32 as soon as ent.radius is
-  if (pr.radius_is_f32)
+  if (pr.f32)
     dist = (double)f_add(f_add((float)ar, (float)pr.radius), (float)S.params.max_forward_step);
   else
     dist = d_add(d_add(ar, pr.radius), S.params.max_forward_step);
@@ -98,8 +121,8 @@ MWB_DEV bool room_contains(const mwb_room& r, double px, double pz) {
 // entity's radius, retry until it is inside the room and free; then the heading (given, or uniform(-pi, pi)).
 #define MWB_NAN (__builtin_nan(""))
 MWB_DEV void place_search(const DevState& S, int i, NpRng& rng, const mwb_room* rooms, int n_rooms, int room_fixed,
-                          const double bounds[4], const mwb_proto& pr, double dir_given, double& x, double& z, double& dir) {
-  const double rad = pr.radius;
+                          const double bounds[4], double rad, bool rad_f32, double dir_given, double& x, double& z,
+                          double& dir) {
   for (;;) {
     int r = room_fixed;
     if (r < 0) {
@@ -117,7 +140,7 @@ MWB_DEV void place_search(const DevState& S, int i, NpRng& rng, const mwb_room* 
     (void)rng_random(rng);   // the y component: uniform(0, 0) still consumes a draw
     z = rng_uniform(rng, loz, d_sub(d_add(hz, rad), loz));
     if (!room_contains(rm, x, z)) continue;
-    if (world_intersect(S, i, -1, x, z, rad, pr.radius_is_f32 != 0) != MWB_HIT_NONE) continue;
+    if (world_intersect(S, i, -1, x, z, rad, rad_f32) != MWB_HIT_NONE) continue;
     dir = isnan(dir_given) ? rng_uniform(rng, -3.141592653589793, d_sub(3.141592653589793, -3.141592653589793)) : dir_given;
     return;
   }
@@ -133,8 +156,21 @@ MWB_DEV bool near_agent(const DevState& S, int i, int b, int as, double ar) {
   const double dy = d_sub(S.ent_py[b * N + i], S.ent_py[as * N + i]);
   const double dz = d_sub(S.ent_pz[b * N + i], S.ent_pz[as * N + i]);
   const double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
-  const mwb_proto& pr = S.protos[bp];
-  return d < d_add(sum_radii(pr.radius, pr.radius_is_f32 != 0, ar, false), S.near_extra);
+  const EntDims pr = ent_dims(S, i, b, S.protos[bp]);
+  return d < d_add(sum_radii(pr.radius, pr.f32, ar, false), S.near_extra);
+}
+
+// MiniWorldEnv.near(ent0, ent1) between two entities of the list
+MWB_DEV bool near_pair(const DevState& S, int i, int a, int b) {
+  const size_t N = S.N;
+  const int pa = S.ent_proto[a * N + i], pb = S.ent_proto[b * N + i];
+  if (pa < 0 || pb < 0) return false;
+  const double dx = d_sub(S.ent_px[a * N + i], S.ent_px[b * N + i]);
+  const double dy = d_sub(S.ent_py[a * N + i], S.ent_py[b * N + i]);
+  const double dz = d_sub(S.ent_pz[a * N + i], S.ent_pz[b * N + i]);
+  const double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
+  const EntDims da = ent_dims(S, i, a, S.protos[pa]), db = ent_dims(S, i, b, S.protos[pb]);
+  return d < d_add(sum_radii(da.radius, da.f32, db.radius, db.f32), S.near_extra);
 }
 
 struct StepOut {
@@ -163,8 +199,8 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
     bool ok = world_intersect(S, i, as, nx, nz, ar, false) == MWB_HIT_NONE;
     if (ok && carrying >= 0) {
       CarryPos cp = carry_pos(S, i, nx, nz, c, s, carrying, ar);
-      const mwb_proto& pr = S.protos[S.ent_proto[carrying * N + i]];
-      ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.radius_is_f32 != 0) == MWB_HIT_NONE;
+      const EntDims pr = ent_dims(S, i, carrying, S.protos[S.ent_proto[carrying * N + i]]);
+      ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.f32) == MWB_HIT_NONE;
       if (ok) {
         S.ent_px[carrying * N + i] = cp.x;
         S.ent_py[carrying * N + i] = cp.y;
@@ -184,9 +220,9 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
     if (carrying >= 0) {
       double c = mwb_libm::cos_glibc(ndir), s = mwb_libm::sin_glibc(ndir);
       CarryPos cp = carry_pos(S, i, px, pz, c, s, carrying, ar);
-      const mwb_proto& pr = S.protos[S.ent_proto[carrying * N + i]];
+      const EntDims pr = ent_dims(S, i, carrying, S.protos[S.ent_proto[carrying * N + i]]);
       // the agent's dir is already updated when the reference tests this; intersect() does not read it
-      ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.radius_is_f32 != 0) == MWB_HIT_NONE;
+      ok = world_intersect(S, i, carrying, cp.x, cp.z, pr.radius, pr.f32) == MWB_HIT_NONE;
       if (ok) {
         S.ent_px[carrying * N + i] = cp.x;
         S.ent_py[carrying * N + i] = cp.y;
@@ -248,6 +284,12 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
         o.terminated = 1;
         o.reward = (b % 3 == colour && b / 3 == goal) ? 1.0 : -1.0;
       }
+  } else if (S.rule_kind == MWB_RULE_PUTNEXT) {
+    // putnext.py:61-66: done once the two boxes are next to each other and the agent has let go
+    if (carrying < 0 && near_pair(S, i, S.rule_arg & 0xFF, (S.rule_arg >> 8) & 0xFF)) {
+      o.reward = d_add(o.reward, d_sub(1.0, d_mul(0.2, d_div((double)sc, (double)S.max_episode_steps))));
+      o.terminated = 1;
+    }
   } else if (S.rule_kind == MWB_RULE_HEALTH) {
     // collecthealth.py:62-86.  The level counter (num_picked) holds the agent's health.
     int health = S.num_picked[i] - 2;
@@ -268,6 +310,7 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
         S.ent_py[e * N + i] = S.ent_py[(e + 1) * N + i];
         S.ent_pz[e * N + i] = S.ent_pz[(e + 1) * N + i];
         S.ent_dir[e * N + i] = S.ent_dir[(e + 1) * N + i];
+        S.ent_size[e * N + i] = S.ent_size[(e + 1) * N + i];
         for (int c = 0; c < 3; ++c) S.ent_col[((size_t)e * 3 + c) * N + i] = S.ent_col[((size_t)(e + 1) * 3 + c) * N + i];
       }
       int as2 = as > k ? as - 1 : as;
@@ -278,13 +321,15 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
       const double nob[4] = {MWB_NAN, MWB_NAN, MWB_NAN, MWB_NAN};
       NpRng rng = load_rng(S, i);
       double x, z, dir;
-      place_search(S, i, rng, S.rooms + (size_t)g * S.R, S.num_rooms[g], -1, nob, S.protos[kp], MWB_NAN, x, z, dir);
+      place_search(S, i, rng, S.rooms + (size_t)g * S.R, S.num_rooms[g], -1, nob, S.protos[kp].radius,
+                   S.protos[kp].radius_is_f32 != 0, MWB_NAN, x, z, dir);
       store_rng(S, i, rng);
       S.ent_proto[(n - 1) * N + i] = kp;      // list.append()
       S.ent_px[(n - 1) * N + i] = x;
       S.ent_py[(n - 1) * N + i] = 0.0;
       S.ent_pz[(n - 1) * N + i] = z;
       S.ent_dir[(n - 1) * N + i] = dir;
+      S.ent_size[(n - 1) * N + i] = 0.0;
       S.num_slots[i] = n;
       carrying = -1;
       health = 100;

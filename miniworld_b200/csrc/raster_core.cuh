@@ -660,11 +660,13 @@ struct FrameMap {
 struct EntPose {
   double x, y, z, dir;
   double col[3];
+  double size;                       // per-episode Box edge length (PutNext), 0 = the prototype's size
 };
 
 MWB_DEV EntPose entity_pose(const DevState& S, int i, int e) {
   const size_t N = S.N;
   EntPose p;
+  p.size = S.ent_size[e * N + i];
   if (e == S.ghost_slot[i]) {
     p.x = S.ghost_pose[0 * N + i];
     p.y = S.ghost_pose[1 * N + i];
@@ -778,7 +780,9 @@ MWB_DEV void box_corner(int f, int v, int& sx, int& top, int& sz) {
 // triangle t (0..11) of a Box: face t / 2 in drawBox order, fan half t % 2
 MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput& in) {
   const int f = t >> 1, half = t & 1;
-  const float hx = (float)(pr.size[0] / 2), sy = (float)pr.size[1], hz = (float)(pr.size[2] / 2);
+  const double ex = P.size > 0.0 ? P.size : pr.size[0], ey = P.size > 0.0 ? P.size : pr.size[1],
+               ez = P.size > 0.0 ? P.size : pr.size[2];
+  const float hx = (float)(ex / 2), sy = (float)ey, hz = (float)(ez / 2);
   const float NX[6] = {0, 0, -1, 1, 0, 0}, NY[6] = {0, 0, 0, 0, 1, -1}, NZ[6] = {1, -1, 0, 0, 0, 0};
   // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = z c - x s
   const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);

@@ -37,7 +37,10 @@ MWB_DEV void device_reset(const DevState& S, int i) {
   S.num_picked[i] = S.rule_kind == MWB_RULE_HEALTH ? 100 : 0;   // CollectHealth: self.health = 100
   S.ghost_slot[i] = -1;
   S.num_slots[i] = 0;
-  for (int e = 0; e < S.E; ++e) S.ent_proto[e * N + i] = -1;
+  for (int e = 0; e < S.E; ++e) {
+    S.ent_proto[e * N + i] = -1;
+    S.ent_size[e * N + i] = 0.0;
+  }
   // Agent() defaults (entity.py:459-474)
   S.cam[0 * N + i] = P.cam_height;
   S.cam[1 * N + i] = P.cam_fwd_disp;
@@ -74,6 +77,7 @@ MWB_DEV void device_reset(const DevState& S, int i) {
       S.ent_py[e * N + i] = op.f[1];
       S.ent_pz[e * N + i] = op.f[2];
       S.ent_dir[e * N + i] = dir;
+      S.ent_size[e * N + i] = 0.0;
       for (int k = 0; k < 3; ++k) S.ent_col[((size_t)e * 3 + k) * N + i] = pr.color[k];
       S.num_slots[i] = slots;
       continue;
@@ -93,9 +97,13 @@ MWB_DEV void device_reset(const DevState& S, int i) {
       const mwb_proto& pr = S.protos[proto];
       double x, z, dir;
       S.num_slots[i] = slots;   // entities placed so far
-      place_search(S, i, rng, rooms, n_rooms, op.room, op.f, pr,
+      // a Box whose edge length the level drew for this episode (op.b = 1 + freg): Box.__init__'s radius
+      const double size = op.b > 0 ? freg[(op.b - 1) & 7] : 0.0;
+      const double rad = size > 0.0 ? d_div(d_sqrt(d_add(d_mul(size, size), d_mul(size, size))), 2.0) : pr.radius;
+      place_search(S, i, rng, rooms, n_rooms, op.room, op.f, rad, pr.radius_is_f32 != 0,
                    op.dir_freg >= 0 ? freg[op.dir_freg & 7] : MWB_NAN, x, z, dir);
       int e = slots++;
+      S.ent_size[e * N + i] = size;
       S.ent_proto[e * N + i] = proto;
       S.ent_px[e * N + i] = x;
       S.ent_py[e * N + i] = 0.0;

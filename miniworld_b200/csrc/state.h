@@ -28,6 +28,7 @@ struct DevState {
   double* ent_pz;
   double* ent_dir;
   double* ent_col;              // [E][3][N]  Box colour after randomize
+  double* ent_size;             // [E][N]  per-episode Box edge length drawn by the level (PutNext); 0 = the prototype's
   int32_t* num_slots;           // [N] entity-list length
   int32_t* agent_slot;          // [N]
   int32_t* carrying;            // [N] slot or -1

@@ -1,11 +1,12 @@
 """Level definitions and id registration (reference miniworld/envs/__init__.py:44-157).
 
 All 23 ids of the reference are registered (+ `MiniWorld-MazeS8-v0`, the name BASELINE.json uses for the 8x8
-`MiniWorld-Maze-v0` default).  Twenty-one of the 24 run on the batched engine with device-side resets and
-lowered rules (`device_program` / `device_rule`): Hallway, OneRoom (+S6, S6Fast), FourRooms, Maze (+S2, S3,
-S3Fast, S8), PickupObjects, TMaze / YMaze (+Left, Right), WallGap, ThreeRooms, Sidewalk, RoomObjects.
-PutNext (per-episode box sizes), CollectHealth (health counter, respawning kits) and Sign (dict observations)
-run through the single-environment class: GPU physics + render, the level's Python `step()` rule.
+`MiniWorld-Maze-v0` default), and every one of them runs on the batched engine with device-side resets and a
+lowered rule: each level class states its `_gen_world()` once more as a `device_program` (CHOICE / UNIFORM /
+PLACE / PUT / IFEQ / MAZE ops interpreted per env on the GPU, on that env's numpy-exact stream) and names its
+`device_rule` (goal, pickup, sidewalk, sign, health, putnext, none).  The same classes are the drop-in
+single-environment API (host world generation, the level's Python `step()`), which is what the reference's
+own tests exercise.
 """
 from .._gym import gym
 from .collecthealth import CollectHealth

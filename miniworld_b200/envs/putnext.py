@@ -21,6 +21,16 @@ class PutNext(MiniWorldEnv, utils.EzPickle):
                 self.yellow_box = box
         self.place_agent()
 
+    @property
+    def device_rule(self):
+        return ("putnext", COLOR_NAMES.index("red") | (COLOR_NAMES.index("yellow") << 8))
+
+    def device_program(self, prog):
+        for color in COLOR_NAMES:
+            size = prog.uniform(0.6, 0.85)                    # drawn while the Box is constructed
+            prog.place(prog.proto(Box(color=color, size=0.8)), size=size)
+        prog.place_agent()
+
     def step(self, action):
         obs, reward, termination, truncation, info = super().step(action)
         if not self.agent.carrying and self.near(self.red_box, self.yellow_box):

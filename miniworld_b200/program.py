@@ -99,7 +99,7 @@ class ResetProgram:
         return self.num_placed - 1
 
     def place(self, proto, index=None, room=None, dir=None, min_x=None, max_x=None, min_z=None, max_z=None,
-              when=None, same_slot=False, _agent=False):
+              when=None, same_slot=False, size=None, _agent=False):
         """place_entity(...).  when=(reg, value): the call sits in an `if reg == value:` branch of _gen_world();
         the other branches are stated with further place(..., when=..., same_slot=True) calls -- exactly one of
         them runs per reset and fills the one entity slot."""
@@ -120,6 +120,8 @@ class ResetProgram:
                 op["ireg_b"], op["stride_b"] = ib.index, proto.strides[1]
         else:
             op["a"] = int(proto)
+        if size is not None:           # Box(size=<a value drawn for this episode>): overrides the prototype's size
+            op["b"] = 1 + size.index
         op["room"] = -1 if room is None else int(room)
         op["dir_freg"] = -1 if dir is None else dir.index
         op["is_agent"] = int(_agent)

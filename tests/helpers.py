@@ -24,6 +24,7 @@ CASES = {
     "sign": ("MiniWorld-Sign-v0", False),
     "collecthealth": ("MiniWorld-CollectHealth-v0", False),
     "collecthealth_pick": ("MiniWorld-CollectHealth-v0", False),     # pickup-heavy action mix: kit respawns
+    "putnext_dr": ("MiniWorld-PutNext-v0", True),
 }
 
 
@@ -239,3 +240,34 @@ def obs_format_parity(lib_path, n=5, steps=6, level="MiniWorld-FourRooms-v0"):
         grey = 0.30 * o[:, :, 0] + 0.59 * o[:, :, 1] + 0.11 * o[:, :, 2]
         assert np.array_equal(frames["grey"][i], np.expand_dims(grey, axis=2))
     assert 0 < hwc.mean() < 255
+
+
+def batched_equals_single_env(level, lib_path, n=3, steps=4, domain_rand=False, **kw):
+    """The batched engine (device-side reset program, lowered rule) and the drop-in single-env class (host world
+    generation, Python rule) produce identical frames, rewards and flags from the same seeds and actions."""
+    from miniworld_b200.envs import LEVELS
+    env = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=False, lib_path=lib_path, **kw)
+    assert env.device_reset
+    ids = np.arange(n, dtype=np.int32)
+    env.engine.seed(ids, np.array([rng_state_of(4000 + i) for i in range(n)], RNG_DTYPE))
+    env.engine.reset(None)
+    first = np.zeros((n, env.obs_height, env.obs_width, 3), np.uint8)
+    env.engine.render(obs=first)
+    dr = {"domain_rand": True} if domain_rand else {}
+    singles = [LEVELS[level](engine_lib=lib_path, **dr, **kw) for _ in range(n)]
+    for i, s in enumerate(singles):
+        o, _ = s.reset(seed=4000 + i)
+        o = o["obs"] if isinstance(o, dict) else o
+        assert np.array_equal(o, first[i]), (level, "reset frame", i)
+    acts = np.random.default_rng(11).integers(0, env.action_space.n, size=(steps, n), dtype=np.int32)
+    out = None
+    for t in range(steps):
+        out = env.step_host(acts[t], out)
+        for i, s in enumerate(singles):
+            o, r, te, tr, _ = s.step(int(acts[t, i]))
+            o = o["obs"] if isinstance(o, dict) else o
+            assert np.array_equal(o, out["obs"][i]), (level, "frame", t, i)
+            assert r == out["reward"][i] and te == bool(out["terminated"][i]) and tr == bool(out["truncated"][i])
+    for s in singles:
+        s.close()
+    env.close()

@@ -17,7 +17,7 @@ def test_device_reset_levels_bit_exact(libmwb_path, name):
     assert T >= 300 and N >= 16
 
 
-@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs", "sign", "collecthealth", "collecthealth_pick"])
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs", "sign", "collecthealth", "collecthealth_pick", "putnext_dr"])
 def test_lowered_extra_levels_bit_exact(libmwb_path, name):
     """Levels beyond BASELINE.json's configs on the batched engine (IFEQ / PUT reset ops, street rule)."""
     run_trajectory(name, golden(name), libmwb_path, check_every=5)

@@ -226,3 +226,14 @@ def test_top_view_and_visible_ents_batched(libmwb_path, softgl_lib):
     assert seen == {True, False}
     ts.close()
     env.close()
+
+
+@pytest.mark.parametrize("level,dr", [("MiniWorld-PutNext-v0", True), ("MiniWorld-Sign-v0", False), ("MiniWorld-TMaze-v0", False),
+                                      ("MiniWorld-YMaze-v0", True), ("MiniWorld-WallGap-v0", False),
+                                      ("MiniWorld-ThreeRooms-v0", True), ("MiniWorld-Sidewalk-v0", True),
+                                      ("MiniWorld-RoomObjects-v0", False), ("MiniWorld-CollectHealth-v0", False)])
+def test_batched_frames_equal_single_env(libmwb_path, level, dr):
+    """Levels lowered beyond BASELINE.json's configs: the batched engine's frames (device reset program, per-episode
+    box sizes, fixed-pose meshes, text / image frames) == the drop-in class's, whose frames the oracle tests pin."""
+    from helpers import batched_equals_single_env
+    batched_equals_single_env(level, libmwb_path, n=6, steps=12, domain_rand=dr)

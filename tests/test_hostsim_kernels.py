@@ -138,7 +138,7 @@ def test_fused_observation_layouts(hostsim_path):
     obs_format_parity(hostsim_path, n=2, steps=2)
 
 
-@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs", "sign", "collecthealth", "collecthealth_pick"])
+@pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "wallgap", "sidewalk_dr", "threerooms_dr", "roomobjs", "sign", "collecthealth", "collecthealth_pick", "putnext_dr"])
 def test_lowered_extra_levels_bit_exact(hostsim_path, name):
     """TMaze / YMaze (branching placement, polygon rooms), WallGap / ThreeRooms / Sidewalk (fixed-pose entities,
     meshes, the street rule) through the batched engine with device-side resets vs the reference trajectories."""
@@ -147,3 +147,10 @@ def test_lowered_extra_levels_bit_exact(hostsim_path, name):
     assert env.device_reset
     env.close()
     run_trajectory(name, g, hostsim_path, steps=300 if name == "collecthealth_pick" else 150, check_every=10)
+
+
+@pytest.mark.parametrize("level,dr", [("MiniWorld-PutNext-v0", True), ("MiniWorld-Sign-v0", False),
+                                      ("MiniWorld-TMaze-v0", False)])
+def test_batched_frames_equal_single_env(hostsim_path, level, dr):
+    from helpers import batched_equals_single_env
+    batched_equals_single_env(level, hostsim_path, n=2, steps=2, domain_rand=dr)

@@ -12,7 +12,7 @@ from helpers import CASES
 def test_reset_matches_reference_golden(name):
     level, dr = CASES[name]
     g = golden(name)
-    env = LEVELS[level](device=None, domain_rand=dr)
+    env = LEVELS[level](device=None, **({"domain_rand": True} if dr else {}))    # (Sign fixes domain_rand itself)
     n = min(g["pos"].shape[1], 4 if "maze_dr" in name else 12)
     for i in range(n):
         env.reset(seed=1000 + i)
