@@ -1,7 +1,7 @@
 """BatchedMiniWorld: N independent MiniWorld environments stepped by one C-ABI call.
 
 This is the hot path of the package: `step(actions)` = K1 (physics / reward / auto-reset,
-one thread per env) + K2 (first-person render, one block per env) through `mwb_step`.
+one warp per env) + K2 (first-person render, one block per env) through `mwb_step`.
 Per-environment semantics are exactly those of the reference's `MiniWorldEnv.reset/step`
 (miniworld.py:544-604, 670-730) plus the level's own `step()` rule, for every env:
 
@@ -262,14 +262,15 @@ class BatchedMiniWorld:
         self.engine.set_action_noise(prob, random_action)
 
     def render_top_view(self, render_agent=True, out=None):
-        """Map view of every env, uint8 [N, H, W, 3] (reference render_top_view, miniworld.py:1088-1175).
+        """Map view of every env in the observation layout -- uint8 [N, H, W, 3] by default (reference
+        render_top_view, miniworld.py:1088-1175).
         Extents come from the level definition (all envs of a level share them).  `out`: optional numpy
         array / CUDA tensor to fill; default a fresh CUDA tensor."""
         ext = self.proto_env.top_view_extents(self.obs_width, self.obs_height)
         if out is None:
             torch = self._ensure_torch()
-            out = torch.zeros((self.num_envs, self.obs_height, self.obs_width, 3), dtype=torch.uint8,
-                              device=torch.device("cuda", self.device))
+            out = torch.zeros(self.obs_shape, dtype=torch.float64 if self.obs_format == "grey" else torch.uint8,
+                              device=torch.device("cuda", self.device))      # same layout as the observations
         self.engine.render_top_view(ext, out, render_agent)
         return out
 

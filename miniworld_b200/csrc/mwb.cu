@@ -1,6 +1,6 @@
 // mwb.cu -- libmwb.so: the C ABI of include/mwb.h on top of the CUDA kernels.
 //
-//   step_kernel   (K1)  physics.cuh + reset.cuh   one thread per env
+//   step_kernel   (K1)  physics.cuh + reset.cuh   one warp per env
 //   render_kernel (K2)  raster.cuh                one block per env, one warp per 8x8 tile
 //   scatter / gather    host <-> SoA state exchange for host-generated worlds
 //
@@ -54,7 +54,7 @@ typedef cudaStream_t stream_t;
   do {                                                                                        \
     cudaError_t e_ = (call);                                                                  \
     if (e_ != cudaSuccess)                                                                    \
-      return fail(MWB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+      return fail(MWB_ECUDA, std::string(#call) + " (mwb.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e_)); \
   } while (0)
 static int dev_alloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
 static void dev_free(void* p) { cudaFree(p); }
@@ -187,7 +187,7 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
     if (o.terminated || o.truncated) {
       if (S.autoreset) S.needs_reset[i] = 1;
 #ifdef __CUDA_ARCH__
-      atomicAdd(S.episodes_done, 1ull);
+      if ((threadIdx.x & 31) == 0) atomicAdd(S.episodes_done, 1ull);
 #else
       *S.episodes_done += 1ull;
 #endif
@@ -265,11 +265,11 @@ MWB_DEV void gather_one(const DevState& S, int i, WorldUpload& u) {
 #ifndef MWB_HOSTSIM
 __global__ void step_kernel(DevState S, const int32_t* actions, const double* step_params, double* reward,
                             uint8_t* term, uint8_t* trunc) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per env (physics.cuh: circle_hits_walls)
   if (i < S.N) step_one(S, i, actions, step_params, reward, term, trunc);
 }
 __global__ void reset_kernel(DevState S, const int32_t* ids, int n) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per env
   if (t >= n) return;
   int i = ids ? ids[t] : t;
   device_reset(S, i);
@@ -437,6 +437,30 @@ static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewS
 }
 #endif
 
+#ifndef MWB_HOSTSIM
+// The opt-in for large dynamic shared memory is an attribute of the kernel FUNCTION (per device), not of a
+// handle: several handles with different triangle capacities share it, so it is only ever raised.
+static int g_k2_smem[16][3] = {};
+static int ensure_k2_smem(mwb_handle* h, int smem) {
+  const int dev = h->cfg.device & 15;
+  if (smem <= g_k2_smem[dev][h->k2_variant]) return 0;
+#define MWB_K2_ATTR(T, B, D)                                                                                               \
+  (cudaFuncSetAttribute(render_kernel<1, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||    \
+   cudaFuncSetAttribute(render_kernel<4, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||    \
+   cudaFuncSetAttribute(render_kernel<8, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  bool bad;
+  switch (h->k2_variant) {
+    case 0: bad = MWB_K2_ATTR(320, 3, false); break;
+    case 1: bad = MWB_K2_ATTR(320, 3, true); break;
+    default: bad = MWB_K2_ATTR(256, 4, true); break;
+  }
+#undef MWB_K2_ATTR
+  if (bad) return -1;
+  g_k2_smem[dev][h->k2_variant] = smem;
+  return 0;
+}
+#endif
+
 // ------------------------------------------------------------------ ABI: lifetime
 extern "C" const char* mwb_last_error(void) { return g_err.c_str(); }
 
@@ -574,16 +598,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
   const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
-#define MWB_K2_ATTR(T, B, D)                                                                                        \
-  CK(cudaFuncSetAttribute(render_kernel<1, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
-  CK(cudaFuncSetAttribute(render_kernel<4, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
-  CK(cudaFuncSetAttribute(render_kernel<8, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
-  switch (h->k2_variant) {
-    case 0: MWB_K2_ATTR(320, 3, false); break;
-    case 1: MWB_K2_ATTR(320, 3, true); break;
-    default: MWB_K2_ATTR(256, 4, true); break;
-  }
-#undef MWB_K2_ATTR
+  if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   if (getenv("MWB_DEBUG")) {
     int nb = 0;
     switch (h->k2_variant) {
@@ -934,7 +949,7 @@ extern "C" int mwb_reset(mwb_handle* h, const int32_t* env_ids, int n, void* str
     }
   }
 #ifndef MWB_HOSTSIM
-  reset_kernel<<<(n + 63) / 64, 64, 0, s>>>(h->S, ids, n);
+  reset_kernel<<<(n + 3) / 4, 128, 0, s>>>(h->S, ids, n);
   h->launches++;
   CK(cudaGetLastError());
   if (!stream) CK(cudaStreamSynchronize(s));
@@ -1181,7 +1196,7 @@ extern "C" int mwb_step(mwb_handle* h, const int32_t* actions, const double* ste
   uint8_t* d_tr = truncated && is_device_ptr(truncated) ? truncated : h->d_trunc;
 #ifndef MWB_HOSTSIM
   prof_mark(h, h->ev_k1, s);
-  step_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(h->S, d_act, d_sp, d_rew, d_te, d_tr);
+  step_kernel<<<(unsigned)((N + 3) / 4), 128, 0, s>>>(h->S, d_act, d_sp, d_rew, d_te, d_tr);
   prof_mark(h, h->ev_k1, s);
   h->launches++;
   CK(cudaGetLastError());

@@ -1,4 +1,5 @@
-// physics.cuh -- K1: one thread per environment, float64, the reference's arithmetic.
+// physics.cuh -- K1: one warp per environment (scalar logic in lockstep, wall tests lane-parallel), float64,
+// the reference's arithmetic.
 //
 // Restates, operation for operation (no FMA contraction except where numpy's BLAS ddot
 // itself fuses), the step path of the reference:
@@ -19,8 +20,18 @@
 
 // intersect_circle_segs: any(dist(point, seg) < radius), strict.  numpy evaluates
 // sum(ap*ab, axis=1) as (x*x' + 0) + z*z' with separate roundings (ufunc reduce, no FMA).
+// On the GPU the K1 kernels run ONE WARP PER ENVIRONMENT: all 32 lanes execute the env's scalar logic in
+// lockstep on identical values (so control flow never diverges and every store writes the same value), and
+// this loop -- the only long one: up to 256 wall segments in an 8x8 maze -- is strided across the lanes and
+// closed with a warp vote.
 MWB_DEV bool circle_hits_walls(const mwb_seg* segs, int n, double px, double pz, double radius) {
-  for (int s = 0; s < n; ++s) {
+#ifdef __CUDA_ARCH__
+  const int first = threadIdx.x & 31, stride = 32;
+#else
+  const int first = 0, stride = 1;
+#endif
+  bool hit = false;
+  for (int s = first; s < n && !hit; s += stride) {
     double ax = segs[s].ax, az = segs[s].az;
     double abx = d_sub(segs[s].bx, ax), abz = d_sub(segs[s].bz, az);
     double apx = d_sub(px, ax), apz = d_sub(pz, az);
@@ -31,9 +42,12 @@ MWB_DEV bool circle_hits_walls(const mwb_seg* segs, int n, double px, double pz,
     double cx = d_add(ax, d_mul(t, abx)), cz = d_add(az, d_mul(t, abz));
     double dx = d_sub(cx, px), dz = d_sub(cz, pz);
     double dist = d_sqrt(d_add(d_mul(dx, dx), d_mul(dz, dz)));
-    if (dist < radius) return true;
+    if (dist < radius) hit = true;
   }
-  return false;
+#ifdef __CUDA_ARCH__
+  hit = __any_sync(0xffffffffu, hit);
+#endif
+  return hit;
 }
 
 // `radius + ent2.radius` as Python/numpy evaluates it: float32 arithmetic as soon as one of
