@@ -218,11 +218,11 @@ def snapshot_roundtrip(level, lib_path, n=6, domain_rand=True, before=25, after=
     env.close()
 
 
-def obs_format_parity(lib_path, n=5, steps=6, level="MiniWorld-FourRooms-v0"):
+def obs_format_parity(lib_path, n=5, steps=6, level="MiniWorld-FourRooms-v0", **kw):
     """K2's fused PyTorchObsWrapper / GreyscaleWrapper epilogues == the wrappers applied to the HWC frames."""
     frames = {}
     for fmt in ("hwc", "cwh", "grey"):
-        env = BatchedMiniWorld(level, num_envs=n, autoreset=True, lib_path=lib_path, obs_format=fmt)
+        env = BatchedMiniWorld(level, num_envs=n, autoreset=True, lib_path=lib_path, obs_format=fmt, **kw)
         ids = np.arange(n, dtype=np.int32)
         env.engine.seed(ids, np.array([rng_state_of(3000 + i) for i in range(n)], RNG_DTYPE))
         env.engine.reset(None)

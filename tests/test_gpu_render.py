@@ -111,6 +111,31 @@ def test_obs_160x120(libmwb_path, softgl_lib):
     env.close()
 
 
+@pytest.mark.parametrize("w,h,level", [(84, 62, "MiniWorld-FourRooms-v0"), (45, 31, "MiniWorld-PickupObjects-v0")])
+def test_ragged_frame_sizes(libmwb_path, softgl_lib, w, h, level):
+    """Frame sizes that are not multiples of the 8x4 half-tile: edge tiles, byte-wise stores, and the fused
+    channel-first / greyscale epilogues on them."""
+    from helpers import obs_format_parity
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.batched import BatchedMiniWorld
+    from miniworld_b200.envs import LEVELS
+    env = BatchedMiniWorld(level, 3, obs_width=w, obs_height=h, want_depth=True)
+    env.reset(seed=1000)
+    obs = env.render().cpu().numpy()
+    depth = env.render_depth().cpu().numpy()
+    assert obs.shape == (3, h, w, 3)
+    ts = softgl_lib.TextureSet([t.texels for t in Texture.registry])
+    for i in range(3):
+        ref = LEVELS[level](device=None, obs_width=w, obs_height=h)
+        ref.reset(seed=1000 + i)
+        rgb, d = softgl_lib.render(ref, ts, lambda tex: tex.tex_id, w, h)
+        assert np.abs(rgb.astype(int) - obs[i].astype(int)).max() <= 1
+        assert np.array_equal(d, depth[i])
+    ts.close()
+    env.close()
+    obs_format_parity(libmwb_path, n=3, steps=2, level=level, obs_width=w, obs_height=h)
+
+
 def test_pickup_objects_meshes_160x120(libmwb_path, softgl_lib):
     """Ball / Key meshes (5192 / 208 triangles, un-normalised normals) and boxes, 160x120,
     at reset and after steps incl. the frame in which a picked-up object is shown carried."""
