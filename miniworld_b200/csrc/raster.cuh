@@ -4,20 +4,23 @@
 // the reference (miniworld.py:1064-1086, 1177-1236; opengl.py:339-435), i.e. the whole
 // OpenGL draw + MSAA resolve + glReadPixels round trip, for N environments per launch.
 //
-// Structure of one block (env i, 10 warps):
-//   A. thread 0 derives the camera (raster_core.cuh: make_camera) and the frame map.
+// Structure of one block (env i, 10 warps; big frames are cut into several blocks per env):
+//   A. a TMA bulk copy stages the env's static quads in shared memory while six threads evaluate the
+//      camera's glibc-exact sin / cos and another lays out the frame's draw list.
 //   B. geometry: one thread per triangle task (half of a static room quad or of a box face)
 //      transforms, lights and sets up its triangle; survivors of frustum / back-face culling
 //      are compacted IN DRAW ORDER into shared memory (shuffle prefix scan) -- the set-up
 //      triangles of rooms and boxes never touch HBM.  Mesh entities (thousands of triangles)
-//      arrive as per-entity lists prepared by mesh_setup_kernel.
-//   C. raster: one warp per 8x8 pixel tile, taken as two 8x4 halves (lane = pixel).  Per chunk of
-//      32 triangles every lane tests one triangle's bbox / edge functions against the tile
-//      and a warp ballot yields the tile's coverage list; hits are applied in order to the
-//      per-sample (depth16, slot) keys held in registers.
+//      arrive as per-entity lists prepared AND binned by half-tile by mesh_setup_kernel.
+//   C. raster: warps claim 8x4 half-tiles from a shared counter (lane = pixel).  Per chunk of 32
+//      triangles every lane tests one triangle's bbox / edge functions / nearest depth against the
+//      half-tile and a warp ballot yields its coverage list; each listed triangle is classified per
+//      pixel (lazy single-surface pixels), undecided (pixel, triangle) pairs go through an exact
+//      sample-parallel phase on (depth16, slot) keys in shared memory.
 //   D. resolve: each pixel shades the distinct triangles its samples see (perspective-
-//      correct Gouraud x trilinear texture), box-filters, converts to unorm8; the tile is
-//      transposed through shared memory and written as 8-byte row segments; depth (sample 0's
+//      correct Gouraud x trilinear texture), box-filters, converts to unorm8; the half-tile is
+//      transposed through shared memory and written as 8-byte row segments (or channel-first /
+//      float64 greyscale: the reference's observation wrappers fused in); depth (sample 0's
 //      16-bit code -> metres) goes out as 32-byte row segments.
 // HBM traffic per env-step is the framebuffer written once (+ L2-resident template reads).
 #pragma once
