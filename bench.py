@@ -282,12 +282,13 @@ def run_ours(args):
             v, n = cpu_port_throughput(1, 1.0, 12.0)
             cpu = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                    "sample": "%d env-steps of 1 env in 12 s (oracle/physics_port.py + oracle/softgl.c)" % n}
-        traffic = None
+        traffic, limiter = None, None
         try:   # DRAM bytes of one K2 launch from the committed ncu --set full capture (profiles/)
             with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
                 tj = json.load(f)
             if N == N_ENVS:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            limiter = tj.get("limiter")      # what ncu says actually bounds the kernel (issue slots, not DRAM)
         except Exception:
             pass
         line = {
@@ -305,7 +306,8 @@ def run_ours(args):
                          "frac": achieved / peak if achieved else None, "traffic": traffic,
                          "kernel": "render_kernel<8>", "kernel_avg_ms": k2_avg_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "k1_avg_ms": k1_ms / max(1, n1), "kernel_share_of_step": k2_ms / ms if ms else None},
+                         "k1_avg_ms": k1_ms / max(1, n1), "kernel_share_of_step": k2_ms / ms if ms else None,
+                         "limiter": limiter},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
                     "d2h_bytes_per_step": N * (BYTES_RGB + BYTES_DEPTH + 8 + 1 + 1), "ms_per_step": e2e_s * 1e3 / K},

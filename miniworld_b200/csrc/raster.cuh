@@ -527,7 +527,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     int lazy_slot = -1;
     if (P.mode == MWB_PX_LAZY) {
       lazy_slot = P.lazy_slot;
-      code0 = sample0_code<MSAA>(fetch(P.lazy_slot), px, py);
+      code0 = depth != nullptr ? sample0_code<MSAA>(fetch(P.lazy_slot), px, py) : 0u;   // only the depth map needs it
     } else {
 #pragma unroll
       for (int s = 0; s < MSAA; ++s) P.keys[s] = skeys[s][lane];
