@@ -438,6 +438,20 @@ static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewS
 #endif
 
 #ifndef MWB_HOSTSIM
+// K2's dynamic shared memory: [triangle records] [staged static quads] [visit order + depth keys] [frame stage].
+// The frame stage holds one env's whole RGB frame (80x60: 14.4 KB) so that it leaves the SM as full 16-byte
+// row-contiguous stores -- what makes the peer-memory observation path efficient over NVLink (8-byte
+// scattered segments reach ~190 GB/s into one GPU, 128-byte lines several times that).
+static int k2_frame_stage_bytes(const mwb_handle* h) {
+  const size_t bytes = (size_t)h->S.obs_w * h->S.obs_h * 3;
+  if (h->k2_parts != 1 || h->obs_format == MWB_OBS_GREY_F64 || bytes > 16384 || (bytes & 15) != 0) return 0;
+  return (int)bytes;      // a multiple of 16: every env's frame starts 16-byte aligned
+}
+static int k2_smem_bytes(const mwb_handle* h) {
+  const int lists = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
+  return ((lists + 15) & ~15) + k2_frame_stage_bytes(h);
+}
+
 // The opt-in for large dynamic shared memory is an attribute of the kernel FUNCTION (per device), not of a
 // handle: several handles with different triangle capacities share it, so it is only ever raised.
 static int g_k2_smem[16][3] = {};
@@ -597,7 +611,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
+  const int smem = k2_smem_bytes(h) + 16384;     // room for a frame stage whatever observation layout is chosen later
   if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   if (getenv("MWB_DEBUG")) {
     int nb = 0;
@@ -1088,9 +1102,10 @@ extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int
 // Launch K2 for envs [env0, env0 + count) (obs / depth point at env 0 of the full buffers).
 static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int count, stream_t s) {
 #ifndef MWB_HOSTSIM
-  const int smem = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
+  const int smem = k2_smem_bytes(h), fstage = k2_frame_stage_bytes(h);
+  if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   prof_mark(h, h->ev_k2, s);
-#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, h->obs_format, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, h->d_overflow)
+#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, h->obs_format, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, fstage, h->d_overflow)
 #define MWB_LAUNCH_K2_MSAA(T, B, D)                 \
   switch (h->S.msaa) {                              \
     case 1: MWB_LAUNCH_K2(1, T, B, D); break;       \

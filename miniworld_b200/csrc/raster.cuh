@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
 template <int MSAA, int THREADS, int MINB, bool DYN>
 __global__ void __launch_bounds__(THREADS, MINB)
 render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0,
-              int parts, int tri_cap, int stage_bytes, int* __restrict__ overflow) {
+              int parts, int tri_cap, int stage_bytes, int frame_stage_bytes, int* __restrict__ overflow) {
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // large frames are cut into `parts` blocks per env (each redoes the cheap geometry phase and
@@ -248,6 +248,9 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + tri_bytes);
   uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + tri_bytes + stage_bytes);
   float* zkey = reinterpret_cast<float*>(order + ((tri_cap + 1) & ~1));
+  // whole-frame RGB stage (frame_stage_bytes > 0): warps drop their pixels here and the block writes the frame
+  // out at the end with 16-byte stores in address order
+  uint8_t* fstage = smem_raw + ((tri_bytes + stage_bytes + (size_t)tri_cap * 6 + 8 + 15) & ~(size_t)15);
   __shared__ double trig[6];
   __shared__ int next_half;
   if (tid == 0) mbar_init(&quad_bar, 1);
@@ -537,6 +540,16 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     if (obs != nullptr && fmt == MWB_OBS_GREY_F64) {
       // GreyscaleWrapper fused into the epilogue: float64 [N][H][W][1], eight consecutive doubles per tile row
       if (px < W && py < H) reinterpret_cast<double*>(obs)[((size_t)i * H + py) * W + px] = grey_f64(rgb[0], rgb[1], rgb[2]);
+    } else if (obs != nullptr && frame_stage_bytes > 0) {
+      if (px < W && py < H) {
+        if (fmt == MWB_OBS_CWH_U8) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) fstage[((size_t)c * W + px) * H + py] = rgb[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) fstage[((size_t)py * W + px) * 3 + c] = rgb[c];
+        }
+      }
     } else if (obs != nullptr) {
       __syncwarp();
 #pragma unroll
@@ -576,6 +589,14 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
       }
     }
     if (depth != nullptr && px < W && py < H) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(code0);
+  }
+  if (obs != nullptr && frame_stage_bytes > 0) {
+    __syncthreads();
+    const size_t frame = (size_t)W * H * 3;
+    uint8_t* dst = obs + (size_t)i * frame;
+    const int vec = (int)(frame >> 4);
+    for (int o = tid; o < vec; o += THREADS) reinterpret_cast<uint4*>(dst)[o] = reinterpret_cast<const uint4*>(fstage)[o];
+    for (int o = (vec << 4) + tid; o < (int)frame; o += THREADS) dst[o] = fstage[o];
   }
 }
 
