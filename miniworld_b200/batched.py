@@ -76,7 +76,7 @@ class BatchedMiniWorld:
                     self.device_reset = False
         if self.device_reset:
             protos = self.program.proto_array()
-            max_ents = max(8, self.program.num_placed)
+            max_ents = max(2, self.program.num_placed)     # exact: K2's shared-memory triangle capacity scales with it
             caps = (len(rooms), len(quads), len(segs))
             if self.maze_template is not None:
                 caps = (len(rooms), len(quads) + 8, len(segs) + 8)

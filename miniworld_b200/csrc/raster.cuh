@@ -577,10 +577,10 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
       } else if (lane < 12) {   // 4 rows x 3 segments of 8 bytes
         const int row = lane / 3, seg = lane % 3;
         const int y = ty0 + row;
-        if (y < H && tx0 + 8 <= W) {
+        if (y < H && (W & 7) == 0) {    // rows start 8-byte aligned only when W is a multiple of 8
           uint2 v = *reinterpret_cast<const uint2*>(&ws.stage[row][seg * 8]);
           *reinterpret_cast<uint2*>(obs + ((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + seg * 8) = v;
-        } else if (y < H) {   // ragged right edge (W not a multiple of 8): byte stores
+        } else if (y < H) {   // W not a multiple of 8 (ragged right edge, unaligned rows): byte stores
           for (int q = 0; q < 8; ++q) {
             int bcol = seg * 8 + q;
             if (tx0 + bcol / 3 < W) obs[((size_t)i * H + y) * W * 3 + (size_t)tx0 * 3 + bcol] = ws.stage[row][bcol];
