@@ -262,3 +262,25 @@ def test_batched_frames_equal_single_env(libmwb_path, level, dr):
     box sizes, fixed-pose meshes, text / image frames) == the drop-in class's, whose frames the oracle tests pin."""
     from helpers import batched_equals_single_env
     batched_equals_single_env(level, libmwb_path, n=6, steps=12, domain_rand=dr)
+
+
+def test_large_batch_frames_equal_small_batch(libmwb_path):
+    """At N >= 1776 a frame is rendered by ONE block and leaves the SM through the whole-frame shared-memory
+    stage (16-byte stores); small batches split a frame over several blocks and store row segments directly.
+    Same seeds => same worlds => the two routes must give identical frames, in both uint8 layouts."""
+    import torch
+    from miniworld_b200.batched import BatchedMiniWorld
+    small_n, big_n, steps = 48, 2048, 3
+    acts = np.random.default_rng(9).integers(0, 3, size=(steps, big_n), dtype=np.int32)
+    for fmt in ("hwc", "cwh"):
+        frames = {}
+        for n in (small_n, big_n):
+            env = BatchedMiniWorld("MiniWorld-FourRooms-v0", n, obs_format=fmt, want_depth=True)
+            env.reset(seed=1000)
+            for t in range(steps):
+                obs, _, _, _, info = env.step(torch.as_tensor(acts[t, :n], device="cuda"))
+            frames[n] = (obs[:small_n].cpu().numpy().copy(), info["depth"][:small_n].cpu().numpy().copy())
+            env.close()
+        assert np.array_equal(frames[small_n][0], frames[big_n][0]), fmt
+        assert np.array_equal(frames[small_n][1], frames[big_n][1]), fmt
+        assert 0 < frames[big_n][0].mean() < 255
