@@ -15,7 +15,8 @@
  *   - every buffer is caller-owned.  Output / action pointers may be host or device
  *     memory (detected with cudaPointerGetAttributes); host pointers make the call
  *     synchronous, device pointers enqueue on `stream` and return.
- *   - a handle is bound to one CUDA device and is not thread-safe.
+ *   - a handle is bound to one CUDA device and is not thread-safe; that device must be the calling
+ *     thread's current device for every call on the handle (one process per GPU is the intended use).
  *   - there is no CPU execution path: mwb_create fails with MWB_ENOCUDA without a GPU.
  */
 #ifndef MWB_H_
