@@ -612,7 +612,10 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
   const int smem = k2_smem_bytes(h) + 16384;     // room for a frame stage whatever observation layout is chosen later
-  if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+  if (ensure_k2_smem(h, smem)) {
+    mwb_destroy(h);
+    return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+  }
   if (getenv("MWB_DEBUG")) {
     int nb = 0;
     switch (h->k2_variant) {
@@ -642,6 +645,8 @@ extern "C" int mwb_destroy(mwb_handle* h) {
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
   cudaStreamSynchronize(h->copy_stream);
+  for (cudaEvent_t e : h->ev_k1) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
   for (int c = 0; c < MWB_MAX_D2H_CHUNKS; ++c) cudaEventDestroy(h->chunk_done[c]);
   cudaEventDestroy(h->copies_done);
   cudaStreamDestroy(h->copy_stream);
