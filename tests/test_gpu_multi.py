@@ -43,12 +43,14 @@ def _worker(rank, world, port, total, steps, q):
     dist.destroy_process_group()
 
 
-def test_peer_observation_buffer_equals_gather(libmwb_path):
+@pytest.mark.parametrize("total,steps", [(64, 5), (4096, 2)])
+def test_peer_observation_buffer_equals_gather(libmwb_path, total, steps):
+    """total = 64: frames split over several blocks, 8-byte row-segment peer stores; total = 4096 (2048 per
+    rank): one block per frame, whole-frame shared-memory stage written to the peer as 16-byte stores."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    total, steps = 64, 5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 2000
