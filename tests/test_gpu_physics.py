@@ -45,3 +45,15 @@ def test_rng_stream_position_after_rollout(libmwb_path):
             mirror.reset()
         assert env.np_random(i).random() == mirror.np_random.random()
     env.close()
+
+
+@pytest.mark.parametrize("level,dr", [("MiniWorld-TMaze-v0", True), ("MiniWorld-YMaze-v0", False), ("MiniWorld-WallGap-v0", True),
+                                      ("MiniWorld-Sidewalk-v0", False), ("MiniWorld-ThreeRooms-v0", False),
+                                      ("MiniWorld-RoomObjects-v0", True), ("MiniWorld-Sign-v0", False),
+                                      ("MiniWorld-CollectHealth-v0", True), ("MiniWorld-PutNext-v0", False),
+                                      ("MiniWorld-PickupObjects-v0", True), ("MiniWorld-MazeS3Fast-v0", True)])
+def test_device_programs_equal_python_levels(libmwb_path, level, dr):
+    """Batched engine (device reset program + lowered rule) vs the level's Python `_gen_world()` / `step()` on the
+    drop-in class over many episodes, for seeds / domain_rand settings the golden files do not contain."""
+    from helpers import batched_equals_python_levels
+    batched_equals_python_levels(level, libmwb_path, dr, n=4, steps=400)

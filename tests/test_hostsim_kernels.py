@@ -183,3 +183,12 @@ def test_every_level_views_match_oracle(hostsim_path, softgl_lib):
         assert env.get_visible_ents() == softgl_lib.visible_ents(env, ts, tex_index), lvl
         ts.close()
         env.close()
+
+
+@pytest.mark.parametrize("level,dr", [("MiniWorld-TMaze-v0", True), ("MiniWorld-Sidewalk-v0", False), ("MiniWorld-Sign-v0", False),
+                                      ("MiniWorld-CollectHealth-v0", True), ("MiniWorld-PutNext-v0", False),
+                                      ("MiniWorld-RoomObjects-v0", True)])
+def test_device_programs_equal_python_levels(hostsim_path, level, dr):
+    """Seeds and domain_rand settings the golden files do not contain."""
+    from helpers import batched_equals_python_levels
+    batched_equals_python_levels(level, hostsim_path, dr, n=2, steps=150)
