@@ -49,7 +49,8 @@ class BatchedMiniWorld:
         self.proto_env = self.level_cls(device=None, obs_width=obs_width, obs_height=obs_height, **dr,
                                         **self.level_kwargs)
         pe = self.proto_env
-        self.action_space = pe.action_space
+        self.action_space = pe.action_space                  # per-env space: `step` takes one action per env
+        self.single_action_space = pe.action_space           # (gymnasium.vector naming)
         self.single_observation_space = pe.observation_space
         self.max_episode_steps = pe.max_episode_steps
         rule = getattr(pe, "device_rule", None)
