@@ -369,6 +369,41 @@ class MiniWorldEnv(gym.Env):
         y_pos = max(self.agent.cam_height - ent.height - 0.3, 0)
         return pos + Y_VEC * y_pos
 
+    def move_agent(self, fwd_dist, fwd_drift):
+        """Host-side move along the heading plus a sideways drift, refused (False) if the agent or the object it
+        carries would touch a wall or another entity (reference miniworld.py:620-645).  `step()` performs the same
+        move on the GPU (csrc/physics.cuh); this method is for level code and scripts that move the agent directly."""
+        agent = self.agent
+        target = agent.pos + agent.dir_vec * fwd_dist + agent.right_vec * fwd_drift
+        if self.intersect(agent, target, agent.radius):
+            return False
+        held = agent.carrying
+        if held:
+            held_target = self._get_carry_pos(target, held)
+            if self.intersect(held, held_target, held.radius):
+                return False
+            held.pos = held_target
+        agent.pos = target
+        self._world_dirty = True
+        return True
+
+    def turn_agent(self, turn_angle):
+        """Host-side turn by `turn_angle` degrees; undone (False) if the carried object would collide at its new
+        place in front of the agent (reference miniworld.py:647-668)."""
+        agent = self.agent
+        before = agent.dir
+        agent.dir += turn_angle * (math.pi / 180)
+        held = agent.carrying
+        if held:
+            held_target = self._get_carry_pos(agent.pos, held)
+            if self.intersect(held, held_target, held.radius):
+                agent.dir = before
+                return False
+            held.pos = held_target
+            held.dir = agent.dir
+        self._world_dirty = True
+        return True
+
     # ------------------------------------------------------------------ GPU execution
 
     def _require_engine(self):

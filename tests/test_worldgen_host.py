@@ -89,3 +89,30 @@ def test_reference_level_file_runs_on_this_engine_api():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.parametrize("name", ["fourrooms", "hallway", "mazes3"])
+def test_host_move_and_turn_follow_reference(name):
+    """MiniWorldEnv.move_agent / turn_agent (host-side mirrors of miniworld.py:620-668, for level code and scripts)
+    reproduce the reference trajectory bit for bit up to the first episode end."""
+    level, dr = CASES[name]
+    g = golden(name)
+    env = LEVELS[level](device=None)
+    fwd = env.params.sample(None, "forward_step")
+    drift = env.params.sample(None, "forward_drift")
+    turn = env.params.sample(None, "turn_step")
+    for i in range(4):
+        env.reset(seed=1000 + i)
+        moved = 0
+        for t in range(g["actions"].shape[0]):
+            if g["terminated"][t, i] or g["truncated"][t, i]:
+                break
+            a = int(g["actions"][t, i])
+            if a == 0:
+                env.turn_agent(turn)
+            elif a == 1:
+                env.turn_agent(-turn)
+            elif a == 2:
+                moved += bool(env.move_agent(fwd, drift))
+            assert np.array_equal(env.agent.pos, g["pos"][t + 1, i]) and env.agent.dir == g["dir"][t + 1, i], (name, i, t)
+        assert moved > 0
