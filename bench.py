@@ -161,7 +161,7 @@ def run_reference_arm(args):
     warm_s, budget = slice_s * args.warmup, slice_s * args.steps
     value, vals = cpu_port_throughput(cores, warm_s, budget)
     line = {
-        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+        "impl": "reference", "metric": "env steps/sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
         "config": {"workload": "%s 80x60 RGB+depth, random actions, auto-reset" % LEVEL, "n_envs": cores,
@@ -294,7 +294,7 @@ def run_ours(args):
         except Exception:
             pass
         line = {
-            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "metric": "env steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64+f32", "data": "synthetic",
             "config": {"workload": "%s N_envs=%d per GPU, 80x60 RGB+depth, 8x MSAA, random actions, next-step "
