@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
   const int cols = c1 - c0 + 1, rows = r1 - r0 + 1, nbins = box[2] >= 0 ? cols * rows : 0;
   int* off = S.mesh_bin_off + ((size_t)i * S.E + e) * (MWB_MAX_BINS + 1);
   uint16_t* bidx = S.mesh_bin_idx + ((size_t)i * S.E + e) * ((size_t)MWB_BIN_REFS * S.mesh_cap);
-  if (nbins > 0 && nbins <= MWB_MAX_BINS && count > 64) {
+  if (nbins > 0 && nbins <= MWB_MAX_BINS && count > 64 && count <= 65535) {   // bin entries are 16-bit triangle indices
     for (int b = tid; b <= nbins; b += 256) bin_cnt[b] = 0;
     __syncthreads();
     // pass 1: count.  A triangle is listed in a bin if its bbox meets the half-tile and no edge excludes it
