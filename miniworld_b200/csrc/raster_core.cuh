@@ -644,7 +644,7 @@ MWB_DEV float depth_code_to_metres(uint32_t code) {
 // "slots" number the surviving triangles consecutively across segments, so slot order ==
 // draw order and the per-sample key (depth16 << 16 | slot) implements GL_LESS exactly.
 
-#define MWB_MAX_DRAWN 24
+#define MWB_MAX_DRAWN 32               // = the entity-slot cap (MWB_MAX_ENTS_CAP): every non-agent entity can be drawn
 
 struct FrameMap {
   int n_quads;                       // room quads of this env
