@@ -117,6 +117,7 @@ struct mwb_handle {
   bool profiling;
   bool frames_copied;
   int k2_variant;
+  int k2_static_smem;             // static shared memory of the K2 instantiation in use (cudaFuncGetAttributes)
   TriRec* vis_tris;              // scratch of mwb_visible_ents, allocated on first use
   ViewSpec view;                 // what the next render launch draws (agent camera unless mwb_render_top_view)
   int k2_parts;                   // blocks per env frame (1 at 80x60, 4 at 160x120)
@@ -442,15 +443,19 @@ static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewS
 // The frame stage holds one env's whole RGB frame (80x60: 14.4 KB) so that it leaves the SM as full 16-byte
 // row-contiguous stores -- what makes the peer-memory observation path efficient over NVLink (8-byte
 // scattered segments reach ~190 GB/s into one GPU, 128-byte lines several times that).
+static int k2_list_bytes(const mwb_handle* h) {
+  const int lists = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
+  return (lists + 15) & ~15;
+}
 static int k2_frame_stage_bytes(const mwb_handle* h) {
   const size_t bytes = (size_t)h->S.obs_w * h->S.obs_h * 3;
   if (h->k2_parts != 1 || h->obs_format == MWB_OBS_GREY_F64 || bytes > 16384 || (bytes & 15) != 0) return 0;
+  // not at the price of a resident block: three blocks per SM (+ 1 KB each for the system) must still fit in 227 KB
+  const size_t per_block = (size_t)k2_list_bytes(h) + bytes + (size_t)h->k2_static_smem + 1024;
+  if (3 * per_block > 232448) return 0;
   return (int)bytes;      // a multiple of 16: every env's frame starts 16-byte aligned
 }
-static int k2_smem_bytes(const mwb_handle* h) {
-  const int lists = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
-  return ((lists + 15) & ~15) + k2_frame_stage_bytes(h);
-}
+static int k2_smem_bytes(const mwb_handle* h) { return k2_list_bytes(h) + k2_frame_stage_bytes(h); }
 
 // The opt-in for large dynamic shared memory is an attribute of the kernel FUNCTION (per device), not of a
 // handle: several handles with different triangle capacities share it, so it is only ever raised.
@@ -510,6 +515,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->vis_tris = nullptr;
   h->obs_format = MWB_OBS_HWC_U8;
   h->obs_px_bytes = 3;
+  h->k2_static_smem = 19456;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
 #ifndef MWB_HOSTSIM
@@ -611,6 +617,27 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
 #ifndef MWB_HOSTSIM
+  {
+    cudaFuncAttributes fa;
+    cudaError_t e;
+    switch (h->k2_variant) {
+      case 0: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, false>)
+                : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 320, 3, false>)
+                                         : cudaFuncGetAttributes(&fa, render_kernel<1, 320, 3, false>); break;
+      case 1: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, true>)
+                : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 320, 3, true>)
+                                         : cudaFuncGetAttributes(&fa, render_kernel<1, 320, 3, true>); break;
+      default: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 256, 4, true>)
+                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 256, 4, true>)
+                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 256, 4, true>); break;
+    }
+    if (e == cudaSuccess) {
+      h->k2_static_smem = (int)fa.sharedSizeBytes;
+    } else {
+      cudaGetLastError();
+      h->k2_static_smem = 19456;
+    }
+  }
   const int smem = k2_smem_bytes(h) + 16384;     // room for a frame stage whatever observation layout is chosen later
   if (ensure_k2_smem(h, smem)) {
     mwb_destroy(h);
