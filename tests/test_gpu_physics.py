@@ -57,3 +57,26 @@ def test_device_programs_equal_python_levels(libmwb_path, level, dr):
     drop-in class over many episodes, for seeds / domain_rand settings the golden files do not contain."""
     from helpers import batched_equals_python_levels
     batched_equals_python_levels(level, libmwb_path, dr, n=4, steps=400)
+
+
+@pytest.mark.parametrize("name", ["hallway", "fourrooms_dr"])
+def test_host_reset_fallback_for_levels_without_a_device_program(libmwb_path, name):
+    """Levels that only name their rule (user-defined ones): host `_gen_world()` + mwb_set_world, RNG stream handed
+    back and forth around every host reset; same reference trajectory bit for bit."""
+    from helpers import state_mismatches
+    from miniworld_b200.batched import BatchedMiniWorld
+    from miniworld_b200.envs import LEVELS
+    level, dr = CASES[name]
+    host_only = type("HostOnly" + LEVELS[level].__name__, (LEVELS[level],), {"device_program": None})
+    g = golden(name)
+    n = 8
+    env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True, lib_path=libmwb_path)
+    assert not env.device_reset
+    env._host_reset(np.arange(n, dtype=np.int32), [1000 + i for i in range(n)])
+    env._seeded = True
+    out = None
+    for t in range(300):
+        out = env.step_host(g["actions"][t, :n], out, render=False)
+        bad = state_mismatches(env, g, t + 1, n, out)
+        assert not bad, "step %d: %s" % (t + 1, "; ".join(bad))
+    env.close()

@@ -192,3 +192,29 @@ def test_device_programs_equal_python_levels(hostsim_path, level, dr):
     """Seeds and domain_rand settings the golden files do not contain."""
     from helpers import batched_equals_python_levels
     batched_equals_python_levels(level, hostsim_path, dr, n=2, steps=150)
+
+
+@pytest.mark.parametrize("name,steps", [("hallway", 300), ("fourrooms_dr", 300)])
+def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, name, steps):
+    """A level class that only names its rule (no `device_program`) still runs batched: worlds are generated by its
+    Python `_gen_world()` on the host and uploaded (`mwb_set_world`), the env's numpy stream is handed back and forth
+    around every host reset (device-side per-step domain-rand draws).  Same reference trajectory, bit for bit."""
+    from helpers import state_mismatches
+    from miniworld_b200.batched import BatchedMiniWorld
+    from miniworld_b200.envs import LEVELS
+    level, dr = CASES[name]
+    host_only = type("HostOnly" + LEVELS[level].__name__, (LEVELS[level],), {"device_program": None})
+    g = golden(name)
+    n = 4
+    env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True, lib_path=hostsim_path)
+    assert not env.device_reset
+    env._host_reset(np.arange(n, dtype=np.int32), [1000 + i for i in range(n)])
+    env._seeded = True
+    assert not state_mismatches(env, g, 0, n)
+    out = None
+    for t in range(steps):
+        out = env.step_host(g["actions"][t, :n], out, render=False)
+        bad = state_mismatches(env, g, t + 1, n, out)
+        assert not bad, "step %d: %s" % (t + 1, "; ".join(bad))
+    assert g["was_reset"][1:steps + 1, :n].any()
+    env.close()
