@@ -218,3 +218,28 @@ def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, n
         assert not bad, "step %d: %s" % (t + 1, "; ".join(bad))
     assert g["was_reset"][1:steps + 1, :n].any()
     env.close()
+
+
+def test_text_frame_with_arbitrary_text(hostsim_path, softgl_lib):
+    """reference tests/test_miniworld.py:67-79 (a level that appends a TextFrame with free text), plus the frame
+    against the oracle from a pose that looks at the text."""
+    import math
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.entity import TextFrame
+    from miniworld_b200.envs import ThreeRooms
+
+    class TestText(ThreeRooms):
+        def _gen_world(self):
+            super()._gen_world()
+            self.entities.append(TextFrame(pos=[0, 1.35, 7], dir=math.pi / 2, str="this is a test"))
+
+    env = TestText(engine_lib=hostsim_path)
+    env.reset(seed=2)
+    env.agent.pos = np.array([0.0, 0.0, 4.0])
+    env.agent.dir = -math.pi / 2          # facing +z, towards the wall that carries the text
+    obs = env.render_obs()
+    ts = softgl_lib.TextureSet([t.texels for t in Texture.registry])
+    rgb, _ = softgl_lib.render(env, ts, lambda tex: tex.tex_id)
+    assert np.abs(rgb.astype(int) - obs.astype(int)).max() <= 1 and 0 < obs.mean() < 255
+    ts.close()
+    env.close()

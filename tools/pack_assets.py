@@ -18,7 +18,8 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 TEXTURES = ["concrete", "floor_tiles_bw", "concrete_tiles", "brick_wall", "asphalt", "cinder_blocks", "slime",
-            "logo_mila"] + ["chars/ch_0x%d" % ord(c) for c in "BLUERDGN"]
+            "logo_mila"] + ["chars/ch_0x%d" % ord(c) for c in
+                            "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"]   # every TextFrame glyph
 MESHES = ["ball_%s" % c for c in ("blue", "green", "grey", "purple", "red", "yellow")] + \
          ["key_%s" % c for c in ("blue", "green", "grey", "purple", "red", "yellow")] + \
          ["building", "cone", "medkit", "duckie"]
