@@ -116,3 +116,19 @@ def test_host_move_and_turn_follow_reference(name):
                 moved += bool(env.move_agent(fwd, drift))
             assert np.array_equal(env.agent.pos, g["pos"][t + 1, i]) and env.agent.dir == g["dir"][t + 1, i], (name, i, t)
         assert moved > 0
+
+
+def test_levels_pickle_like_the_reference():
+    """reference tests/test_miniworld.py:157-171: every level survives pickle (EzPickle: constructor arguments) and
+    the copy generates the same world from the same seed."""
+    import pickle
+    for eid, cls in LEVELS.items():
+        if "Maze-v0" in eid or "MazeS8" in eid:
+            continue
+        env = cls(device=None)
+        twin = pickle.loads(pickle.dumps(env))
+        assert type(twin) is type(env) and twin.max_episode_steps == env.max_episode_steps
+        env.reset(seed=5)
+        twin.reset(seed=5)
+        assert np.array_equal(env.agent.pos, twin.agent.pos) and env.agent.dir == twin.agent.dir, eid
+        assert len(env.entities) == len(twin.entities)
