@@ -243,3 +243,29 @@ def test_text_frame_with_arbitrary_text(hostsim_path, softgl_lib):
     assert np.abs(rgb.astype(int) - obs.astype(int)).max() <= 1 and 0 < obs.mean() < 255
     ts.close()
     env.close()
+
+
+def test_env_checker_invariants(hostsim_path):
+    """What gymnasium's check_env verifies for the reference (tests/test_miniworld.py:138-154), restated: seeded
+    resets are deterministic, observations live in the declared space, step() returns the five-tuple with the
+    documented types."""
+    from miniworld_b200.envs import LEVELS
+    for eid, cls in LEVELS.items():
+        if "Maze-v0" in eid or "MazeS8" in eid:
+            continue
+        env = cls(engine_lib=hostsim_path)
+        o1, info1 = env.reset(seed=123)
+        p1 = env.agent.pos.copy()
+        o2, _ = env.reset(seed=123)
+        img = lambda o: o["obs"] if isinstance(o, dict) else o
+        assert np.array_equal(img(o1), img(o2)) and np.array_equal(p1, env.agent.pos), eid
+        assert isinstance(info1, dict)
+        space = env.observation_space
+        if isinstance(o1, dict):
+            assert set(o1) == {"obs", "goal"} and o1["obs"].shape == (60, 80, 3) and o1["obs"].dtype == np.uint8
+        else:
+            assert o1.shape == space.shape and o1.dtype == space.dtype, eid
+        o, r, te, tr, info = env.step(env.action_space.sample())
+        assert isinstance(te, (bool, np.bool_)) and isinstance(tr, (bool, np.bool_)) and isinstance(info, dict), eid
+        assert np.isscalar(r) or isinstance(r, (int, float)), eid
+        env.close()
