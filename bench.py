@@ -171,7 +171,7 @@ def run_reference_arm(args):
                          "sample": "%d env-steps total in %.0f s on %d processes (one env each)" % (vals, budget, cores)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -316,9 +316,30 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: whatever else a library writes to file descriptor 1
+    (NCCL's "NCCL version ..." banner, for one) is sent to stderr for the rest of the run."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -333,6 +354,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
