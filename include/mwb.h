@@ -181,7 +181,8 @@ typedef struct mwb_proto {
   double size[3];            /* Box size                                                         */
   double color[3];           /* COLORS[color] (entity.py:30-40)                                  */
   float scale;               /* MeshEnt.scale (entity.py:144)                                    */
-  int32_t reserved;
+  int32_t deg_form;          /* how render() forms glRotatef's angle: 1 = dir * 180 / pi (MeshEnt, entity.py:158), */
+                             /* 0 = dir * (180 / pi) (Box, ImageFrame, TextFrame: entity.py:206, 316, 421)          */
 } mwb_proto;
 
 /* Per-env entity instance (host-generated worlds / state exchange). */

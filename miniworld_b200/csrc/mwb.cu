@@ -321,7 +321,8 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
       } else {
         const mwb_proto& pr = S.protos[fm.ent_proto[k]];
         const EntPose P = entity_pose(S, i, fm.ent_slot[k]);
-        const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
+        float c, s;
+        model_rotation(P.dir, pr.deg_form, c, s);
         for (int t = 0; t < A.meshes[pr.mesh_id].count; ++t) {
           TriInput in;
           mesh_triangle(A, pr, P, c, s, t, in);

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
   __syncthreads();
   const mwb_proto& pr = S.protos[p];
   const EntPose P = entity_pose(S, i, e);
-  const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
+  float c, s;
+  model_rotation(P.dir, pr.deg_form, c, s);
   const int ntris = A.meshes[pr.mesh_id].count;
   TriRec* out = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
   uint2* out_bbox = S.mesh_bbox + ((size_t)i * S.E + e) * S.mesh_cap;

@@ -90,7 +90,8 @@ struct Camera {
   float px, py;                  // projection scales cot/aspect, cot
   float za, zb;                  // z_clip = za * w_clip - zb
   float halfw, halfh;
-  float light[3], lamb[3], ldif[3], sky[3];
+  float light[3], lamb[3], ldif[3], sky[3];   // light = DIRECTION towards LIGHT0 (see camera_common)
+  float linv;                    // 1 / |light|
   int ortho;                     // 1: render_top_view's orthographic map projection
   float osx, otx, osy, oty;      // x_clip = osx x + otx, y_clip = osy (-z) + oty, z_clip = -0.01 y, w = 1
 };
@@ -113,17 +114,22 @@ MWB_DEV void camera_angles(const DevState& S, int i, double ang[3]) {
   ang[2] = d_div(d_mul(S.cam[3 * N + i], 3.141592653589793), 360.0);
 }
 
-// view-independent part: viewport scale, sky colour, light
+// view-independent part: viewport scale, sky colour, light.
+// LIGHT0 is DIRECTIONAL: the reference issues glLightfv(GL_LIGHT0, GL_POSITION, (GLfloat * 4)(*self.light_pos + [1]))
+// (miniworld.py:1031) with light_pos a numpy array (params.py:45-46 turns every default into one, rng.uniform returns
+// one), so `+ [1]` adds 1 to each component, three GLfloats are passed and w stays 0: a light at infinity in the
+// direction float32(light_pos + 1).  Pinned by the recorded GL stream (oracle/gl_record.py, tests/test_stream_oracle.py).
 MWB_DEV void camera_common(const DevState& S, int i, Camera& c) {
   const size_t N = S.N;
   c.halfw = 0.5f * (float)S.obs_w;
   c.halfh = 0.5f * (float)S.obs_h;
   for (int k = 0; k < 3; ++k) {
     c.sky[k] = (float)S.envp[(0 + k) * N + i];
-    c.light[k] = (float)S.envp[(3 + k) * N + i];
+    c.light[k] = (float)d_add(S.envp[(3 + k) * N + i], 1.0);
     c.ldif[k] = (float)S.envp[(6 + k) * N + i];
     c.lamb[k] = (float)S.envp[(9 + k) * N + i];
   }
+  c.linv = 1.0f / sqrtf(c.light[0] * c.light[0] + c.light[1] * c.light[1] + c.light[2] * c.light[2]);
 }
 
 // Camera of env i from trig = {cos, sin} of those angles.  Angles go through the glibc-exact
@@ -220,14 +226,11 @@ MWB_DEV HVert transform_vertex(const Camera& c, float x, float y, float z) {
   return v;
 }
 
-// Fixed-function vertex lighting (one positional light, no attenuation, no specular):
-// clamp01(m * (0.2 + L_amb + L_diff * max(N . norm(P_light - P), 0))); N is NOT renormalised
+// Fixed-function vertex lighting (one directional light, no specular):
+// clamp01(m * (0.2 + L_amb + L_diff * max(N . norm(L), 0))); N is NOT renormalised
 // (neither GL_NORMALIZE nor GL_RESCALE_NORMAL is enabled by the reference).
-MWB_DEV void light_vertex(const Camera& c, float x, float y, float z, float nx, float ny, float nz,
-                          const float m[3], float out[3]) {
-  float lx = c.light[0] - x, ly = c.light[1] - y, lz = c.light[2] - z;
-  float inv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
-  float ndl = (nx * lx + ny * ly + nz * lz) * inv;
+MWB_DEV void light_vertex(const Camera& c, float nx, float ny, float nz, const float m[3], float out[3]) {
+  float ndl = (nx * c.light[0] + ny * c.light[1] + nz * c.light[2]) * c.linv;
   ndl = ndl > 0.0f ? ndl : 0.0f;
   for (int k = 0; k < 3; ++k) {
     float v = m[k] * (0.2f + c.lamb[k] + c.ldif[k] * ndl);
@@ -730,7 +733,7 @@ MWB_DEV bool finish_triangle(const Camera& cam, const TriInput& in, int W, int H
   for (int k = 0; k < 3; ++k) {
     hv[k] = transform_vertex(cam, in.pos[k][0], in.pos[k][1], in.pos[k][2]);
     float col[3];
-    light_vertex(cam, in.pos[k][0], in.pos[k][1], in.pos[k][2], in.nrm[k][0], in.nrm[k][1], in.nrm[k][2], in.mat[k], col);
+    light_vertex(cam, in.nrm[k][0], in.nrm[k][1], in.nrm[k][2], in.mat[k], col);
     at[k].u = in.uv[k][0];
     at[k].v = in.uv[k][1];
     at[k].r = col[0];
@@ -766,6 +769,16 @@ MWB_DEV bool room_triangle(const DevState& S, const RenderAssets& A, const mwb_q
   return true;
 }
 
+// cos / sin of an entity's model rotation.  glRotatef takes a GLfloat: the angle in degrees the reference forms in
+// float64 -- `dir * (180 / math.pi)` for Box / ImageFrame / TextFrame (entity.py:206, 316, 421), `dir * 180 / math.pi`
+// for MeshEnt (entity.py:158) -- reaches GL rounded to float32.  Spec: c, s = float32(cos / sin(float64(a32) * pi / 180)).
+MWB_DEV void model_rotation(double dir, int mesh_form, float& c, float& s) {
+  const double deg = mesh_form ? d_div(d_mul(dir, 180.0), 3.141592653589793) : d_mul(dir, 57.29577951308232);
+  const double rad = d_div(d_mul((double)(float)deg, 3.141592653589793), 180.0);
+  c = (float)mwb_libm::cos_glibc(rad);
+  s = (float)mwb_libm::sin_glibc(rad);
+}
+
 // corner v (0..3) of face f of drawBox (opengl.py:460-503; faces +z, -z, -x, +x, +y, -y): which end of
 // the box's x / z range (sign) and of its y range (top?) the vertex takes
 MWB_DEV void box_corner(int f, int v, int& sx, int& top, int& sz) {
@@ -785,7 +798,8 @@ MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput
   const float hx = (float)(ex / 2), sy = (float)ey, hz = (float)(ez / 2);
   const float NX[6] = {0, 0, -1, 1, 0, 0}, NY[6] = {0, 0, 0, 0, 1, -1}, NZ[6] = {1, -1, 0, 0, 0, 0};
   // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = z c - x s
-  const float c = (float)mwb_libm::cos_glibc(P.dir), s = (float)mwb_libm::sin_glibc(P.dir);
+  float c, s;
+  model_rotation(P.dir, 0, c, s);
   const float tx = (float)P.x, ty = (float)P.y, tz = (float)P.z;
   const float nx = f_add(f_mul(NX[f], c), f_mul(NZ[f], s)), ny = NY[f], nz = f_sub(f_mul(NZ[f], c), f_mul(NX[f], s));
 #pragma unroll

@@ -66,7 +66,7 @@ SEG_DTYPE = np.dtype([("ax", "f8"), ("az", "f8"), ("bx", "f8"), ("bz", "f8")], a
 PROTO_DTYPE = np.dtype([
     ("kind", "i4"), ("is_static", "i4"), ("mesh_id", "i4"), ("radius_is_f32", "i4"),
     ("radius", "f8"), ("height", "f8"), ("size", "f8", 3), ("color", "f8", 3),
-    ("scale", "f4"), ("reserved", "i4")], align=True)
+    ("scale", "f4"), ("deg_form", "i4")], align=True)
 ENTITY_DTYPE = np.dtype([
     ("proto", "i4"), ("reserved", "i4"), ("pos", "f8", 3), ("dir", "f8"), ("color", "f8", 3)], align=True)
 OP_DTYPE = np.dtype([

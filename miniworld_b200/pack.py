@@ -89,6 +89,7 @@ def proto_record(ent):
         p["kind"] = KIND_MESH
         p["mesh_id"] = ent.mesh.mesh_id
         p["scale"] = np.float32(ent.scale)
+        p["deg_form"] = int(isinstance(ent, MeshEnt))     # glRotatef angle: dir * 180 / pi vs dir * (180 / pi)
     else:
         raise TypeError("entity type %s is not supported by the CUDA engine yet" % type(ent).__name__)
     return p

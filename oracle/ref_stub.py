@@ -5,14 +5,14 @@ Headless import shim for the *unmodified* reference at /root/reference.
 The reference (Farama-Foundation/Miniworld) needs pyglet<2 + libGL + gymnasium, none of
 which exist in this image.  Every GL entry point it touches is a ctypes call into a
 third-party driver; physics / reward / world generation (SURVEY.md section 8a rows R1-R8,
-R15, R16) never read anything back from GL.  So we inject fake `pyglet` / `gymnasium`
-modules whose GL calls are no-ops and let the reference's own Python execute:
-miniworld/miniworld.py, entity.py, math.py, params.py, objmesh.py, opengl.py and envs/*.py
-run unmodified from /root/reference (read-only, via sys.path).
+R15, R16) never read anything back from GL.  So we inject a fake `gymnasium` and a fake
+`pyglet` whose GL is the RECORDING fixed-function GL of oracle/gl_record.py, and let the
+reference's own Python execute: miniworld/miniworld.py, entity.py, math.py, params.py,
+objmesh.py, opengl.py and envs/*.py run unmodified from /root/reference (read-only, via sys.path).
 
 This makes the reference itself the oracle of record for pose / dir / reward /
-terminated / truncated / RNG order.  Pixels are NOT produced here (render_obs returns
-zeros) -- the pixel oracle is oracle/softgl.c.
+terminated / truncated / RNG order, and -- with the recorder active -- for every argument of
+every GL call that defines a frame; oracle/softgl.c rasterises that recorded stream.
 
 Only usable where /root/reference exists (the build container); the GPU box uses the
 committed fixtures under tests/golden/ produced by oracle/gen_golden.py.
@@ -27,101 +27,6 @@ REFERENCE_ROOT = os.environ.get("MWB_REFERENCE_ROOT", "/root/reference")
 
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "miniworld"))
-
-
-class _Noop:
-    """Callable that swallows anything (stands in for a gl* function or GL object)."""
-
-    def __init__(self, name="noop"):
-        self._name = name
-        self.value = 0
-        self.target = 0
-        self.id = 0
-
-    def __call__(self, *a, **k):
-        return None
-
-    def __getattr__(self, item):
-        return _Noop(item)
-
-
-def _make_gl_module(name):
-    mod = types.ModuleType(name)
-    ctypes_types = {
-        "GLfloat": ctypes.c_float, "GLdouble": ctypes.c_double, "GLubyte": ctypes.c_ubyte,
-        "GLuint": ctypes.c_uint, "GLint": ctypes.c_int, "GLushort": ctypes.c_ushort,
-        "GLenum": ctypes.c_uint, "GLsizei": ctypes.c_int,
-    }
-    counter = [0x1000]
-
-    def _getattr(attr):
-        if attr.startswith("__"):
-            raise AttributeError(attr)
-        if attr in ctypes_types:
-            return ctypes_types[attr]
-        if attr.startswith("GL_"):
-            counter[0] += 1
-            val = counter[0]
-            setattr(mod, attr, val)
-            return val
-        if attr == "gl_info":
-            info = types.SimpleNamespace(have_extension=lambda *_: True)
-            return info
-        if attr == "glCheckFramebufferStatus":
-            fn = lambda *a, **k: getattr(mod, "GL_FRAMEBUFFER_COMPLETE")
-        else:
-            fn = _Noop(attr)
-        setattr(mod, attr, fn)
-        return fn
-
-    mod.__getattr__ = _getattr
-    return mod
-
-
-class _FakeImage:
-    def __init__(self, path):
-        from PIL import Image
-        with Image.open(path) as im:
-            self.width, self.height = im.size
-
-    def get_texture(self):
-        return types.SimpleNamespace(width=self.width, height=self.height, target=0, id=0)
-
-    def get_image_data(self):
-        return types.SimpleNamespace(get_data=lambda *_: b"")
-
-
-def _install_pyglet():
-    pyglet = types.ModuleType("pyglet")
-    pyglet.options = {}
-    gl = _make_gl_module("pyglet.gl")
-    pyglet.gl = gl
-    image = types.ModuleType("pyglet.image")
-    image.load = lambda path, *a, **k: _FakeImage(path)
-    image.ImageData = _Noop
-    pyglet.image = image
-    graphics = types.ModuleType("pyglet.graphics")
-    def _vertex_list(count, *attrs):
-        """Capture what the reference hands to pyglet (objmesh.py:198-204) so the oracle
-        harness can read the mesh arrays back: .attrs['v3f'] etc. are flat float arrays."""
-        vl = _Noop("vlist")
-        vl.count = count
-        vl.attrs = {fmt: data for fmt, data in attrs}
-        return vl
-
-    graphics.vertex_list = _vertex_list
-    pyglet.graphics = graphics
-    window = types.ModuleType("pyglet.window")
-    window.Window = lambda *a, **k: _Noop("window")
-    window.key = _Noop("key")
-    pyglet.window = window
-    text = types.ModuleType("pyglet.text")
-    text.Label = lambda *a, **k: _Noop("label")
-    pyglet.text = text
-    pyglet.app = _Noop("app")
-    pyglet.clock = _Noop("clock")
-    for m in (pyglet, gl, image, graphics, window, text):
-        sys.modules[m.__name__] = m
 
 
 def _install_gymnasium():
@@ -213,11 +118,15 @@ def _install_gymnasium():
 
 
 _installed = False
+recorder = None      # the recording GL context (oracle/gl_record.RecGL) the reference's GL calls go to
 
 
 def install():
-    """Make `import miniworld` resolve to the unmodified reference with GL stubbed out."""
-    global _installed
+    """Make `import miniworld` resolve to the unmodified reference with `pyglet.gl` replaced by the recording
+    fixed-function GL of oracle/gl_record.py.  `recorder.active` decides whether draw calls are recorded and
+    rasterised (the reference's render_* then return the rasterised GL stream) or ignored (physics-only: render_obs
+    returns zeros, as with a no-op GL)."""
+    global _installed, recorder
     if _installed:
         return
     if not reference_available():
@@ -226,16 +135,20 @@ def install():
         if name == "miniworld" or name.startswith("miniworld."):
             raise RuntimeError("a module named `miniworld` is already imported")
     if "pyglet" not in sys.modules:
-        _install_pyglet()
+        from oracle import gl_record
+        recorder = gl_record.install()
     if "gymnasium" not in sys.modules:
         _install_gymnasium()
     sys.path.insert(0, REFERENCE_ROOT)
     _installed = True
 
 
-def make_reference_env(env_id, **kwargs):
-    """Instantiate a reference env class by gym id (e.g. 'MiniWorld-FourRooms-v0')."""
+def make_reference_env(env_id, record=False, **kwargs):
+    """Instantiate a reference env class by gym id (e.g. 'MiniWorld-FourRooms-v0').  `record` switches the
+    process-wide GL recorder on (frames are rasterised from the reference's GL stream) or off (physics only)."""
     install()
+    if recorder is not None:
+        recorder.active = bool(record)
     import contextlib
     import io
     import gymnasium

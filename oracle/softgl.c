@@ -127,6 +127,17 @@ typedef struct {
    * query_out[q] is set to 1 when any sample of a triangle of query q passes the depth test */
   const int* tri_query;
   uint8_t* query_out;
+  /* cam_mode 1 = the camera as the reference's GL stream states it (oracle/gl_record.py): gluLookAt(eye, center,
+   * up) and gluPerspective(fovy, aspect, znear, zfar) arguments instead of the agent's pose and angles.  The basis
+   * follows GLU's algorithm (f = normalise(center - eye), s = normalise(f x up), u = s x f) in float64 and is
+   * rounded once to float32, like the angle-derived basis of cam_mode 0. */
+  int cam_mode;
+  double eye[3], center[3], up[3], fovy, aspect, znear, zfar;
+  /* LIGHT0's GL_POSITION w component: 1 = positional light at light_pos, 0 = DIRECTIONAL light whose direction
+   * (towards the light) is light_pos.  The reference issues (GLfloat * 4)(*self.light_pos + [1]) with light_pos a
+   * numpy array (params.py:45-46 turns the defaults into arrays): the `+ [1]` broadcasts, three components are
+   * passed and w stays 0 -- a directional light along light_pos + 1 (miniworld.py:1031). */
+  double light_w;
 } Scene;
 
 /* D3D standard sample patterns in image space (x right, y down), offsets from the pixel's
@@ -180,6 +191,27 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
   double cot = cos(half) / sin(half);
   float Py = (float)cot, Px = (float)(cot / ((double)W / (double)H));
   float Za = (float)((ZFAR + ZNEAR) / (ZFAR - ZNEAR)), Zb = (float)(2.0 * ZFAR * ZNEAR / (ZFAR - ZNEAR));
+  if (sc->cam_mode == 1) {
+    double f[3] = {sc->center[0] - sc->eye[0], sc->center[1] - sc->eye[1], sc->center[2] - sc->eye[2]};
+    double fl = sqrt((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
+    for (int c = 0; c < 3; ++c) f[c] /= fl;
+    double s[3] = {f[1] * sc->up[2] - f[2] * sc->up[1], f[2] * sc->up[0] - f[0] * sc->up[2], f[0] * sc->up[1] - f[1] * sc->up[0]};
+    double sl = sqrt((s[0] * s[0] + s[1] * s[1]) + s[2] * s[2]);
+    for (int c = 0; c < 3; ++c) s[c] /= sl;
+    double u[3] = {s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]};
+    for (int c = 0; c < 3; ++c) {
+      eye[c] = (float)sc->eye[c];
+      Sv[c] = (float)s[c];
+      Uv[c] = (float)u[c];
+      Fv[c] = (float)f[c];
+    }
+    double radians = sc->fovy / 2 * 3.141592653589793 / 180; /* gluPerspective */
+    double cotg = cos(radians) / sin(radians);
+    Py = (float)cotg;
+    Px = (float)(cotg / sc->aspect);
+    Za = (float)((sc->zfar + sc->znear) / (sc->zfar - sc->znear));
+    Zb = (float)(2.0 * sc->zfar * sc->znear / (sc->zfar - sc->znear));
+  }
   float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
   /* glOrtho's matrix entries: formed in double, stored as float32 */
   float Osx = 0.0f, Otx = 0.0f, Osy = 0.0f, Oty = 0.0f, Osz = (float)(-2.0 / (100.0 - (-100.0)));
@@ -237,7 +269,8 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
       g[k].Y = (we - g[k].cy) * hh; /* ((1 - y_ndc) H / 2) w : row 0 at the top */
       g[k].Z = 0.5f * (g[k].cz + we);
       /* fixed-function lighting, per vertex, normal not renormalised */
-      float lx = lpos[0] - p[0], ly = lpos[1] - p[1], lz = lpos[2] - p[2];
+      float lx = lpos[0], ly = lpos[1], lz = lpos[2];
+      if (sc->light_w != 0.0) { lx -= p[0]; ly -= p[1]; lz -= p[2]; }
       float ll = sqrtf(lx * lx + ly * ly + lz * lz);
       float ndl = (n[0] * lx + n[1] * ly + n[2] * lz) / ll;
       if (ndl < 0.0f) ndl = 0.0f;

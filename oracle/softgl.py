@@ -33,7 +33,10 @@ class _Scene(C.Structure):
                 ("light_ambient", C.c_double * 3), ("width", C.c_int), ("height", C.c_int), ("samples", C.c_int),
                 ("num_tris", C.c_int), ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("tri_uv", C.c_void_p),
                 ("tri_rgb", C.c_void_p), ("tri_tex", C.c_void_p),
-                ("view", C.c_int), ("ortho", C.c_double * 4), ("tri_query", C.c_void_p), ("query_out", C.c_void_p)]
+                ("view", C.c_int), ("ortho", C.c_double * 4), ("tri_query", C.c_void_p), ("query_out", C.c_void_p),
+                ("cam_mode", C.c_int), ("eye", C.c_double * 3), ("center", C.c_double * 3), ("up", C.c_double * 3),
+                ("fovy", C.c_double), ("aspect", C.c_double), ("znear", C.c_double), ("zfar", C.c_double),
+                ("light_w", C.c_double)]
 
 
 _lib = None
@@ -87,6 +90,13 @@ def _box_faces(sx, sy, sz):
     ]
 
 
+def _rot_cs(deg):
+    """glRotatef's angle is a GLfloat: the degrees the reference computes in float64 reach GL rounded to float32.
+    Spec: c, s = float32(cos / sin(float64(angle_f32) * pi / 180))."""
+    rad = float(f32(deg)) * math.pi / 180
+    return f32(math.cos(rad)), f32(math.sin(rad))
+
+
 def _rot_y(v, c, s):
     """glRotatef(theta, 0, 1, 0) on a float32 vector, one rounding per op: x' = x c + z s,
     z' = z c - x s."""
@@ -126,7 +136,7 @@ def draw_list(env, tex_index, agent_marker=False, rooms_only=False):
     def draw_entity(ent):
         kind = type(ent).__name__
         if kind == "Box":
-            c, s = f32(math.cos(ent.dir)), f32(math.sin(ent.dir))
+            c, s = _rot_cs(ent.dir * (180 / math.pi))             # entity.py:421
             t = [f32(v) for v in ent.pos]
             sx, sy, sz = ent.size
             col = tuple(float(v) for v in ent.color_vec)
@@ -142,7 +152,9 @@ def draw_list(env, tex_index, agent_marker=False, rooms_only=False):
             # glTranslatef(pos) glScalef(s, s, s) glRotatef(dir): v' = pos + s * (R v); the normal
             # goes through the inverse transpose, R n / s, and is NOT renormalised
             m = ent.mesh
-            c, s = f32(math.cos(ent.dir)), f32(math.sin(ent.dir))
+            # MeshEnt.render: dir * 180 / pi (entity.py:158); ImageFrame / TextFrame: dir * (180 / pi) (:206, :316)
+            c, s = _rot_cs(ent.dir * 180 / math.pi if hasattr(ent, "mesh_name") or hasattr(m, "vlists")
+                           else ent.dir * (180 / math.pi))
             t = np.asarray(ent.pos, dtype=np.float32)
             sc = f32(ent.scale)
             inv = f32(f32(1.0) / sc)
@@ -281,9 +293,16 @@ def _run(env, texset, lst, width, height, samples, want_codes=False, ortho=None,
     for k in range(3):
         sc.pos[k] = float(a.pos[k])
         sc.sky[k] = float(env.sky_color[k])
-        sc.light_pos[k] = float(env.light_pos[k])
         sc.light_color[k] = float(env.light_color[k])
         sc.light_ambient[k] = float(env.light_ambient[k])
+    # glLightfv(GL_LIGHT0, GL_POSITION, (GLfloat * 4)(*self.light_pos + [1])) (miniworld.py:1031), restated
+    # literally: light_pos is an ndarray (params.py:45-46), so `+ [1]` adds 1 to each component, three GLfloats are
+    # passed and w stays 0 -- a DIRECTIONAL light along light_pos + 1.  (A plain list would give a positional light.)
+    lp = list(env.light_pos + [1])
+    lp = [float(f32(v)) for v in lp] + [0.0] * (4 - len(lp))
+    for k in range(3):
+        sc.light_pos[k] = lp[k]
+    sc.light_w = lp[3]
     sc.dir = float(a.dir)
     sc.cam_height, sc.cam_fwd_disp = float(a.cam_height), float(getattr(a, "cam_fwd_disp", 0.0))
     sc.cam_pitch, sc.cam_fov_y = float(a.cam_pitch), float(a.cam_fov_y)
@@ -297,3 +316,50 @@ def _run(env, texset, lst, width, height, samples, want_codes=False, ortho=None,
     rc = lib().softgl_render(C.byref(sc), texset.h, out.ctypes.data, depth.ctypes.data, codes.ctypes.data)
     assert rc == 0
     return (out, depth, codes) if want_codes else (out, depth)
+
+
+_TOP_VIEW_MATRIX = (1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+
+
+def run_stream(cam, texset, lst, width, height, samples, query=None, query_out=None):
+    """Rasterise one frame recorded from the reference's GL stream (oracle/gl_record.py): `cam` carries the
+    glClearColor / glLightfv / gluPerspective|glOrtho / gluLookAt|glLoadMatrixf arguments, `lst` the world-space
+    triangles.  Returns (rgb u8[H,W,3], depth f32[H,W,1] for near / far = 0.04 / 100, codes u16[H,W])."""
+    pos, nrm, uv, rgb, tx = (np.ascontiguousarray(a) for a in lst)
+    sc = _Scene()
+    proj, view = cam["proj"], cam["view"]
+    if proj is None:                       # nothing was drawn: only the clear colour matters
+        proj, view = ("perspective", 60.0, width / height, 0.04, 100.0), ("lookat", 0, 0, 0, 1, 0, 0, 0, 1, 0)
+    if proj[0] == "perspective" and view[0] == "lookat":
+        sc.cam_mode = 1
+        sc.fovy, sc.aspect, sc.znear, sc.zfar = proj[1:5]
+        for k in range(3):
+            sc.eye[k], sc.center[k], sc.up[k] = view[1 + k], view[4 + k], view[7 + k]
+    elif proj[0] == "ortho" and view[0] == "loadmatrix":
+        if tuple(view[1:]) != _TOP_VIEW_MATRIX or proj[5:] != (-100.0, 100.0):
+            raise NotImplementedError("ortho view other than render_top_view's")
+        sc.view = 1
+        for k in range(4):
+            sc.ortho[k] = proj[1 + k]
+    else:
+        raise NotImplementedError("camera %r / %r" % (proj[0], view[0]))
+    light = cam["light"]
+    for k in range(3):
+        sc.sky[k] = float(cam["clear"][k])
+        if light is not None:
+            sc.light_pos[k] = float(light["position"][k])
+            sc.light_color[k] = float(light["diffuse"][k])
+            sc.light_ambient[k] = float(light["ambient"][k])
+    sc.light_w = 1.0 if light is None else float(light["position"][3])
+    if query is not None:
+        sc.tri_query, sc.query_out = query.ctypes.data, query_out.ctypes.data
+    sc.width, sc.height, sc.samples = width, height, samples
+    sc.num_tris = len(tx)
+    sc.tri_pos, sc.tri_nrm, sc.tri_uv = pos.ctypes.data, nrm.ctypes.data, uv.ctypes.data
+    sc.tri_rgb, sc.tri_tex = rgb.ctypes.data, tx.ctypes.data
+    out = np.zeros((height, width, 3), np.uint8)
+    depth = np.zeros((height, width, 1), np.float32)
+    codes = np.zeros((height, width), np.uint16)
+    rc = lib().softgl_render(C.byref(sc), texset.h, out.ctypes.data, depth.ctypes.data, codes.ctypes.data)
+    assert rc == 0
+    return out, depth, codes

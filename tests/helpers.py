@@ -318,3 +318,78 @@ def batched_equals_python_levels(level, lib_path, domain_rand, n=3, steps=200, s
         s.close()
     env.close()
     return episodes
+
+
+def stream_cases():
+    import glob
+    import os
+    from conftest import GOLDEN
+    return sorted(os.path.basename(p)[len("stream_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN, "stream_*.npz")))
+
+
+def stream_parity(name, lib_path=None, max_rows=None, check_views=True):
+    """Frames the UNMODIFIED reference returned while its GL stream was recorded and rasterised
+    (tests/golden/stream_*.npz, oracle/gen_stream_golden.py) vs the engine replaying the same trajectory:
+    RGB within 1 LSB, depth bit-identical, map view within 1 LSB, occlusion-query sets equal.  Includes the frames in
+    which the picked-up object is still drawn although the level's step() already removed it from the entity list."""
+    import os
+    from conftest import GOLDEN, golden
+    s = np.load(os.path.join(GOLDEN, "stream_%s.npz" % name))
+    traj = str(s["meta"][2])
+    g = golden(traj)
+    H, W = s["rgb"].shape[1:3]
+    sel = s["sel"]
+    if max_rows is not None:
+        sel = sel[sel[:, 0] <= max_rows]
+    N = int(sel[:, 1].max()) + 1
+    env = make_env(traj, g, lib_path, n=N, want_depth=True, obs_width=W, obs_height=H)
+    rows = {}
+    for k, (t, i) in enumerate(s["sel"]):
+        if max_rows is None or t <= max_rows:
+            rows.setdefault(int(t), []).append((k, int(i)))
+    stats = dict(frames=0, worst=0, same=0, total=0, events=0, tops=0, vis=0)
+    out = dict(obs=np.zeros((N, H, W, 3), np.uint8), reward=np.zeros(N), terminated=np.zeros(N, np.uint8),
+               truncated=np.zeros(N, np.uint8), depth=np.zeros((N, H, W, 1), np.float32))
+    top = np.zeros((N, H, W, 3), np.uint8)
+    vis = np.zeros(N, np.int32)
+
+    def check(t):
+        top_done = False
+        for k, i in rows[t]:
+            d = np.abs(out["obs"][i].astype(int) - s["rgb"][k].astype(int))
+            stats["frames"] += 1
+            stats["worst"] = max(stats["worst"], int(d.max()))
+            stats["same"] += int((d == 0).sum())
+            stats["total"] += d.size
+            assert d.max() <= 1, "%s row %d env %d: %d channel values differ by > 1 LSB (max %d)" % (
+                name, t, i, int((d > 1).sum()), int(d.max()))
+            if s["event"][k]:
+                stats["events"] += 1
+                continue
+            assert np.array_equal(out["depth"][i], s["depth"][k]), "%s row %d env %d: depth differs" % (name, t, i)
+            if not check_views:
+                continue
+            if not top_done:
+                env.render_top_view(out=top)
+                env.visible_ents(out=vis)
+                top_done = True
+            dt = np.abs(top[i].astype(int) - s["top"][k].astype(int))
+            assert dt.max() <= 1, "%s row %d env %d: top view differs by %d" % (name, t, i, int(dt.max()))
+            stats["tops"] += 1
+            # device bits are per entity-list SLOT; the golden's are per list index
+            st = env.get_state()["ents"][i]
+            live = [e for e in range(len(st)) if st[e]["proto"] >= 0]
+            got = sum(1 << j for j, e in enumerate(live) if (int(vis[i]) >> e) & 1)
+            assert got == int(s["vis"][k]), "%s row %d env %d: visible set %s != %s" % (name, t, i, bin(got), bin(int(s["vis"][k])))
+            stats["vis"] += 1
+
+    if 0 in rows:
+        env.engine.render(obs=out["obs"], depth=out["depth"])
+        check(0)
+    for t in range(1, max(rows) + 1):
+        need = t in rows
+        env.step_host(g["actions"][t - 1, :N], out, render=need)
+        if need:
+            check(t)
+    env.close()
+    return stats

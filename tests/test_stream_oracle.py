@@ -1,0 +1,73 @@
+"""Pixel parity pinned to the reference's own GL stream.
+
+(1) Where /root/reference exists: the UNMODIFIED reference runs under the recording fixed-function GL
+    (oracle/gl_record.py); the frames its render_obs() / render_depth() / render_top_view() / get_visible_ents()
+    return -- the rasterised stream of the GL calls it made -- must equal, bit for bit, oracle/softgl.py's rendering
+    of the package's mirror objects in the same state.  All 23 reference ids (+ the MazeS8 alias), with and without
+    domain randomisation.
+(2) Everywhere (no reference needed): the kernels' arithmetic compiled for the CPU (tests/hostsim) replays the
+    golden trajectories and is compared with the committed frames the reference returned (tests/golden/stream_*.npz).
+The same comparison through libmwb.so on a B200 is tests/test_gpu_stream.py.
+"""
+import numpy as np
+import pytest
+
+from helpers import stream_cases, stream_parity
+from oracle import ref_stub
+
+needs_reference = pytest.mark.skipif(not ref_stub.reference_available(), reason="needs /root/reference")
+
+
+def _levels():
+    from oracle.stream_check import level_ids
+    return level_ids()
+
+
+@needs_reference
+@pytest.mark.parametrize("level", _levels())
+def test_reference_gl_stream_equals_mirror(softgl_lib, level):
+    from oracle.stream_check import compare
+    for dr in (False, True):
+        if dr and level == "MiniWorld-Sign-v0":
+            continue                                  # Sign fixes domain_rand=False itself (sign.py:88-93)
+        n, bad, worst, dbad = compare(level, dr, steps=12)
+        assert n == 13 and bad == 0 and dbad == 0, "%s dr=%d: %d / %d frames differ (worst %d LSB), %d depth maps differ" % (
+            level, dr, bad, n, worst, dbad)
+
+
+@needs_reference
+@pytest.mark.parametrize("level", ["MiniWorld-Hallway-v0", "MiniWorld-PickupObjects-v0", "MiniWorld-ThreeRooms-v0",
+                                   "MiniWorld-Sidewalk-v0", "MiniWorld-Sign-v0"])
+def test_reference_other_views_equal_mirror(softgl_lib, level):
+    """render_top_view (with the agent marker and its leaked normal), get_visible_ents, a 160 x 120 observation."""
+    from oracle.stream_check import Pair
+    p = Pair(level, False, obs_width=160, obs_height=120)
+    rng = np.random.default_rng(7)
+    p.reset(11)
+    for t in range(6):
+        obs, _, term, trunc, _ = p.step(int(rng.integers(0, p.ref.action_space.n)))
+        if term or trunc:
+            p.reset(12 + t)
+            continue
+        obs = obs["obs"] if isinstance(obs, dict) else obs
+        assert np.array_equal(obs, p.mirror_frame(160, 120)[0])
+        assert np.array_equal(p.ref.render_top_view(), p.mirror_top_view(160, 120))
+        assert p.ref_visible() == p.mirror_visible(160, 120)
+
+
+@needs_reference
+def test_reference_light_is_directional():
+    """(GLfloat * 4)(*self.light_pos + [1]) with an ndarray light_pos passes THREE values, each + 1, and leaves w = 0
+    (miniworld.py:1031, params.py:45-46): LIGHT0 is a directional light along light_pos + 1."""
+    env = ref_stub.make_reference_env("MiniWorld-OneRoom-v0", record=True)
+    env.reset(seed=3)
+    fr = ref_stub.recorder.frames[-1]
+    assert isinstance(env.light_pos, np.ndarray)
+    assert np.array_equal(fr.light["position"], np.array([1.0, 3.5, 1.0, 0.0], np.float32))
+
+
+@pytest.mark.parametrize("name", stream_cases())
+def test_hostsim_matches_reference_stream_frames(hostsim_path, name):
+    big = name in ("maze_dr", "pickup_160")
+    st = stream_parity(name, hostsim_path, max_rows=21 if big else 89)
+    assert st["frames"] >= 4 and st["same"] / st["total"] > 0.995
