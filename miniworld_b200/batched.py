@@ -33,6 +33,13 @@ def _resolve_level(level):
     return level
 
 
+def _torch_stream(torch, device):
+    """Handle of torch's current stream for mwb_step / mwb_render_obs.  torch's default stream is the legacy default
+    stream (handle 0); a NULL stream argument means "the handle's own stream" to the C ABI, which would not be ordered
+    after the torch kernels that produced the actions -- so the default stream is passed as cudaStreamLegacy (0x1)."""
+    return torch.cuda.current_stream(device).cuda_stream or 1
+
+
 class BatchedMiniWorld:
     def __init__(self, level, num_envs, obs_width=80, obs_height=60, domain_rand=False, autoreset=True,
                  msaa_samples=8, device=0, lib_path=None, want_depth=False, level_kwargs=None, obs_format="hwc"):
@@ -203,7 +210,7 @@ class BatchedMiniWorld:
         else:
             b["actions"].copy_(torch.as_tensor(np.asarray(actions, np.int32)), non_blocking=True)
             acts = b["actions"]
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = _torch_stream(torch, self.device)
         if not self.device_reset and self.autoreset and self._host_done.any():
             self._host_reset(np.nonzero(self._host_done)[0].astype(np.int32), None, hold=True)
             self._host_done[:] = False
@@ -234,7 +241,7 @@ class BatchedMiniWorld:
     def render(self):
         torch = self._ensure_torch()
         b = self._bufs
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = _torch_stream(torch, self.device)
         self.engine.render(obs=b["obs"], depth=b["depth"], stream=stream)
         return b["obs"]
 
@@ -242,7 +249,7 @@ class BatchedMiniWorld:
         torch = self._ensure_torch()
         dev = torch.device("cuda", self.device)
         d = torch.zeros((self.num_envs, self.obs_height, self.obs_width, 1), dtype=torch.float32, device=dev)
-        self.engine.render(depth=d, stream=torch.cuda.current_stream(self.device).cuda_stream)
+        self.engine.render(depth=d, stream=_torch_stream(torch, self.device))
         return d
 
     def snapshot(self):

@@ -128,6 +128,10 @@ struct mwb_handle {
 #endif
 #ifndef MWB_HOSTSIM
   std::vector<cudaEvent_t> ev_k1, ev_k2;   // start/stop pairs
+  // stream discipline: the last stream work on this handle's state was enqueued on, and an event recorded behind it
+  cudaEvent_t last_done;
+  cudaStream_t last_stream;
+  bool last_valid;
 #endif
   std::vector<int> mesh_counts;   // triangles per uploaded mesh (host copy)
   void* mesh_tris_buf;
@@ -147,6 +151,27 @@ static int alloc_arr(mwb_handle* h, T** p, size_t count) {
   *p = (T*)q;
   return 0;
 }
+
+// Stream discipline.  A handle's state arrays are touched by work on its own stream (set-up, state exchange,
+// snapshots, resets without a stream argument) and on caller streams (step / render).  Every entry point that
+// enqueues work calls stream_enter() first -- the new work waits for whatever was enqueued last on a DIFFERENT
+// stream -- and stream_leave() when it is done enqueueing, so that e.g. a snapshot() after an asynchronous step() on a
+// torch stream sees the finished step, and a step on another stream sees the finished reset.
+#ifndef MWB_HOSTSIM
+static int stream_enter(mwb_handle* h, stream_t s) {
+  if (h->last_valid && h->last_stream != s) CK(cudaStreamWaitEvent(s, h->last_done, 0));
+  return 0;
+}
+static int stream_leave(mwb_handle* h, stream_t s) {
+  CK(cudaEventRecord(h->last_done, s));
+  h->last_stream = s;
+  h->last_valid = true;
+  return 0;
+}
+#else
+static int stream_enter(mwb_handle*, stream_t) { return 0; }
+static int stream_leave(mwb_handle*, stream_t) { return 0; }
+#endif
 
 // ------------------------------------------------------------------ kernels / loops
 MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const double* step_params, double* reward,
@@ -533,6 +558,9 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     if (h->d2h_chunks > MWB_MAX_D2H_CHUNKS) h->d2h_chunks = MWB_MAX_D2H_CHUNKS;
   }
   cudaEventCreateWithFlags(&h->copies_done, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
+  h->last_stream = h->stream;
+  h->last_valid = false;
 #else
   h->stream = nullptr;
 #endif
@@ -663,6 +691,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
   if (!h) return MWB_OK;
 #ifndef MWB_HOSTSIM
   cudaSetDevice(h->cfg.device);
+  if (h->last_valid) cudaStreamSynchronize(h->last_stream);   // work still running on a caller stream uses these buffers
   cudaStreamSynchronize(h->stream);
 #endif
   for (void* p : h->allocs) dev_free(p);
@@ -677,6 +706,7 @@ extern "C" int mwb_destroy(mwb_handle* h) {
   for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
   for (int c = 0; c < MWB_MAX_D2H_CHUNKS; ++c) cudaEventDestroy(h->chunk_done[c]);
   cudaEventDestroy(h->copies_done);
+  cudaEventDestroy(h->last_done);
   cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
 #endif
@@ -689,6 +719,7 @@ extern "C" int64_t mwb_launch_count(mwb_handle* h) { return h ? h->launches : 0;
 extern "C" int64_t mwb_overflow_count(mwb_handle* h) {
   if (!h) return 0;
   int v = 0;
+  if (stream_enter(h, h->stream)) return -1;
   if (d2h(&v, h->d_overflow, sizeof(int), h->stream) != 0 || sync_stream(h->stream) != 0) return -1;
   return v;
 }
@@ -868,6 +899,7 @@ static int upload_geometry(mwb_handle* h, size_t g, const mwb_geometry* geo) {
     if (geo->rooms[r].num_edges > MWB_MAX_EDGES) return fail(MWB_ECAPACITY, "room outline too long");
   int32_t counts[3] = {geo->num_rooms, geo->num_quads, geo->num_segs};
   int rc = 0;
+  rc |= stream_enter(h, h->stream);
   rc |= h2d(S.num_rooms + g, &counts[0], sizeof(int32_t), h->stream);
   rc |= h2d(S.num_quads + g, &counts[1], sizeof(int32_t), h->stream);
   rc |= h2d(S.num_segs + g, &counts[2], sizeof(int32_t), h->stream);
@@ -927,6 +959,7 @@ extern "C" int mwb_get_geometry(mwb_handle* h, int env, int32_t counts[3], mwb_r
   if (env < 0 || env >= h->S.N) return fail(MWB_EINVAL, "env out of range");
   const size_t g = h->S.shared_geom ? 0 : (size_t)env;
   int rc = 0;
+  rc |= stream_enter(h, h->stream);
   rc |= d2h(&counts[0], h->S.num_rooms + g, sizeof(int32_t), h->stream);
   rc |= d2h(&counts[1], h->S.num_quads + g, sizeof(int32_t), h->stream);
   rc |= d2h(&counts[2], h->S.num_segs + g, sizeof(int32_t), h->stream);
@@ -940,6 +973,7 @@ extern "C" int mwb_get_geometry(mwb_handle* h, int env, int32_t counts[3], mwb_r
 // ------------------------------------------------------------------ ABI: reset
 static int launch_upload(mwb_handle* h, const std::vector<WorldUpload>& up, bool seed_only) {
   const int n = (int)up.size();
+  if (stream_enter(h, h->stream)) return MWB_ECUDA;
   if (h2d(h->d_upload, up.data(), n * sizeof(WorldUpload), h->stream) != 0) return fail(MWB_ECUDA, "upload failed");
 #ifndef MWB_HOSTSIM
   if (seed_only)
@@ -986,6 +1020,7 @@ extern "C" int mwb_reset(mwb_handle* h, const int32_t* env_ids, int n, void* str
   stream_t s = stream ? (stream_t)stream : h->stream;
   if (!env_ids) n = h->S.N;
   if (n <= 0 || n > h->S.N) return fail(MWB_EINVAL, "bad count");
+  if (stream_enter(h, s)) return MWB_ECUDA;
   const int32_t* ids = nullptr;
   if (env_ids) {
     if (is_device_ptr(env_ids)) {
@@ -999,6 +1034,7 @@ extern "C" int mwb_reset(mwb_handle* h, const int32_t* env_ids, int n, void* str
   reset_kernel<<<(n + 3) / 4, 128, 0, s>>>(h->S, ids, n);
   h->launches++;
   CK(cudaGetLastError());
+  if (stream_leave(h, s)) return MWB_ECUDA;
   if (!stream) CK(cudaStreamSynchronize(s));
 #else
   for (int t = 0; t < n; ++t) {
@@ -1213,6 +1249,7 @@ static int finish_outputs(mwb_handle* h, uint8_t* obs, bool obs_host, float* dep
   if (term && !is_device_ptr(term)) { rc |= d2h(term, h->d_term, N, s); any_host = true; }
   if (trunc && !is_device_ptr(trunc)) { rc |= d2h(trunc, h->d_trunc, N, s); any_host = true; }
   if (rc) return fail(MWB_ECUDA, "readback failed");
+  if (stream_leave(h, s)) return MWB_ECUDA;
   if (any_host || !user_stream)
     if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
   return MWB_OK;
@@ -1223,6 +1260,7 @@ extern "C" int mwb_step(mwb_handle* h, const int32_t* actions, const double* ste
   if (!h || !actions) return fail(MWB_EINVAL, "null argument");
   if (!h->have_params || !h->have_protos) return fail(MWB_ESTATE, "params / protos not set");
   stream_t s = stream ? (stream_t)stream : h->stream;
+  if (stream_enter(h, s)) return MWB_ECUDA;
   const size_t N = h->S.N;
   const int32_t* d_act = actions;
   if (!is_device_ptr(actions)) {
@@ -1263,6 +1301,7 @@ extern "C" int mwb_step(mwb_handle* h, const int32_t* actions, const double* ste
 extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* stream) {
   if (!h || (!obs && !depth)) return fail(MWB_EINVAL, "null argument");
   stream_t s = stream ? (stream_t)stream : h->stream;
+  if (stream_enter(h, s)) return MWB_ECUDA;
   const bool obs_host = obs && !is_device_ptr(obs), depth_host = depth && !is_device_ptr(depth);
   int rc = launch_render(h, obs ? (obs_host ? h->d_obs : obs) : nullptr, depth ? (depth_host ? h->d_depth : depth) : nullptr, s,
                          obs_host ? obs : nullptr, depth_host ? depth : nullptr);
@@ -1300,6 +1339,7 @@ extern "C" int mwb_render_top_view(mwb_handle* h, const double extents[4], int r
   if (!h || !extents || !obs) return fail(MWB_EINVAL, "null argument");
   if (!(extents[1] > extents[0]) || !(extents[3] > extents[2])) return fail(MWB_EINVAL, "empty extents");
   stream_t s = stream ? (stream_t)stream : h->stream;
+  if (stream_enter(h, s)) return MWB_ECUDA;
   const bool obs_host = !is_device_ptr(obs);
   // glOrtho(min_x, max_x, -max_z, -min_z, -100, 100) (miniworld.py:1137)
   h->view.mode = 1;
@@ -1318,6 +1358,7 @@ extern "C" int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream) {
   if (!h || !mask) return fail(MWB_EINVAL, "null argument");
   if (!h->have_protos) return fail(MWB_ESTATE, "protos not set");
   stream_t s = stream ? (stream_t)stream : h->stream;
+  if (stream_enter(h, s)) return MWB_ECUDA;
   const int N = h->S.N, box0 = 2 * h->cfg.max_quads, cap = box0 + 12 * h->cfg.max_ents;
   if (!h->vis_tris && alloc_arr(h, &h->vis_tris, (size_t)N * cap)) return fail(MWB_ECUDA, "scratch allocation failed");
   const bool host = !is_device_ptr(mask);
@@ -1362,8 +1403,9 @@ extern "C" int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream) {
     d_mask[i] = vis;
   }
 #endif
+  if (host && d2h(mask, d_mask, (size_t)N * sizeof(uint32_t), s) != 0) return fail(MWB_ECUDA, "readback failed");
+  if (stream_leave(h, s)) return MWB_ECUDA;
   if (host) {
-    if (d2h(mask, d_mask, (size_t)N * sizeof(uint32_t), s) != 0) return fail(MWB_ECUDA, "readback failed");
     if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
   } else if (!stream) {
     if (sync_stream(s) != 0) return fail(MWB_ECUDA, "stream sync failed");
@@ -1422,6 +1464,7 @@ extern "C" int mwb_snapshot(mwb_handle* h, void* blob, size_t bytes) {
   unsigned char* p = (unsigned char*)blob;
   memcpy(p, &hd, sizeof(hd));
   p += sizeof(hd);
+  if (stream_enter(h, h->stream)) return MWB_ECUDA;
   for (size_t k = 0; k < v.size(); ++k) {
     if (d2h(p, v[k].first, v[k].second, h->stream) != 0) return fail(MWB_ECUDA, "readback failed");
     p += v[k].second;
@@ -1443,6 +1486,7 @@ extern "C" int mwb_restore(mwb_handle* h, const void* blob, size_t bytes) {
   std::vector<std::pair<void*, size_t>> v;
   snapshot_arrays(h, v);
   const unsigned char* p = (const unsigned char*)blob + sizeof(hd);
+  if (stream_enter(h, h->stream)) return MWB_ECUDA;
   for (size_t k = 0; k < v.size(); ++k) {
     if (h2d(v[k].first, p, v[k].second, h->stream) != 0) return fail(MWB_ECUDA, "upload failed");
     p += v[k].second;
@@ -1456,6 +1500,7 @@ extern "C" int mwb_get_state(mwb_handle* h, const mwb_state_view* out) {
   if (!h || !out) return fail(MWB_EINVAL, "null argument");
   const int N = h->S.N;
   std::vector<WorldUpload> up(N);
+  if (stream_enter(h, h->stream)) return MWB_ECUDA;
 #ifndef MWB_HOSTSIM
   gather_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(h->S, h->d_upload);
   h->launches++;

@@ -160,6 +160,15 @@ MWB_DEV void place_search(const DevState& S, int i, NpRng& rng, const mwb_room* 
   }
 }
 
+// Threshold of MiniWorldEnv.near (miniworld.py:965-975): `ent0.radius + ent1.radius + 1.1 * self.max_forward_step`,
+// evaluated left to right.  Once one radius is an np.float32 (MeshEnt under numpy >= 2) the first sum is float32 and
+// stays float32 when the Python float 1.1 * max_forward_step is added (NEP 50: Python scalars are weak), so the
+// threshold is float32(float32(r0 + r1) + float32(extra)); with two float64 radii everything is float64.
+MWB_DEV double near_threshold(double r0, bool r0_f32, double r1, bool r1_f32, double extra) {
+  if (r0_f32 || r1_f32) return (double)f_add(f_add((float)r0, (float)r1), (float)extra);
+  return d_add(d_add(r0, r1), extra);
+}
+
 // MiniWorldEnv.near(ent): np.linalg.norm(ent.pos - agent.pos) < ent.radius + agent.radius + 1.1 * max_forward_step
 // (3-D distance through BLAS ddot, i.e. an FMA chain)
 MWB_DEV bool near_agent(const DevState& S, int i, int b, int as, double ar) {
@@ -171,7 +180,7 @@ MWB_DEV bool near_agent(const DevState& S, int i, int b, int as, double ar) {
   const double dz = d_sub(S.ent_pz[b * N + i], S.ent_pz[as * N + i]);
   const double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
   const EntDims pr = ent_dims(S, i, b, S.protos[bp]);
-  return d < d_add(sum_radii(pr.radius, pr.f32, ar, false), S.near_extra);
+  return d < near_threshold(pr.radius, pr.f32, ar, false, S.near_extra);
 }
 
 // MiniWorldEnv.near(ent0, ent1) between two entities of the list
@@ -184,7 +193,7 @@ MWB_DEV bool near_pair(const DevState& S, int i, int a, int b) {
   const double dz = d_sub(S.ent_pz[a * N + i], S.ent_pz[b * N + i]);
   const double d = d_sqrt(d_fma(dz, dz, d_fma(dy, dy, d_mul(dx, dx))));
   const EntDims da = ent_dims(S, i, a, S.protos[pa]), db = ent_dims(S, i, b, S.protos[pb]);
-  return d < d_add(sum_radii(da.radius, da.f32, db.radius, db.f32), S.near_extra);
+  return d < near_threshold(da.radius, da.f32, db.radius, db.f32, S.near_extra);
 }
 
 struct StepOut {
