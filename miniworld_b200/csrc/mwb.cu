@@ -117,6 +117,7 @@ struct mwb_handle {
   bool profiling;
   bool frames_copied;
   int k2_variant;
+  int k2_flags;                   // MWB_K2_* measurement switches (env MWB_K2_FLAGS)
   int k2_static_smem;             // static shared memory of the K2 instantiation in use (cudaFuncGetAttributes)
   TriRec* vis_tris;              // scratch of mwb_visible_ents, allocated on first use
   ViewSpec view;                 // what the next render launch draws (agent camera unless mwb_render_top_view)
@@ -470,8 +471,8 @@ static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewS
 // row-contiguous stores -- what makes the peer-memory observation path efficient over NVLink (8-byte
 // scattered segments reach ~190 GB/s into one GPU, 128-byte lines several times that).
 static int k2_list_bytes(const mwb_handle* h) {
-  const int lists = h->tri_cap * ((h->smem_tris ? (int)sizeof(TriRec) : 0) + 6) + 8 + h->stage_bytes;
-  return (lists + 15) & ~15;
+  const K2Layout L = k2_layout(h->smem_tris, h->tri_cap, h->stage_bytes, k2_halves_per_part(h->S.obs_w, h->S.obs_h, h->k2_parts), 0);
+  return (int)L.stage_off;
 }
 static int k2_frame_stage_bytes(const mwb_handle* h) {
   const size_t bytes = (size_t)h->S.obs_w * h->S.obs_h * 3;
@@ -495,7 +496,7 @@ static int ensure_k2_smem(mwb_handle* h, int smem) {
    cudaFuncSetAttribute(render_kernel<8, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
   bool bad;
   switch (h->k2_variant) {
-    case 0: bad = MWB_K2_ATTR(320, 3, false); break;
+    case 0: bad = MWB_K2_ATTR(256, 3, true); break;
     case 1: bad = MWB_K2_ATTR(320, 3, true); break;
     default: bad = MWB_K2_ATTR(256, 4, true); break;
   }
@@ -607,6 +608,18 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     mwb_destroy(h);
     return rc;
   }
+#ifndef MWB_HOSTSIM
+  {
+    float* lut = nullptr;
+    if (alloc_arr(h, &lut, 65536)) {
+      mwb_destroy(h);
+      return fail(MWB_ECUDA, "depth table allocation failed");
+    }
+    depth_lut_kernel<<<256, 256, 0, h->stream>>>(lut);
+    h->launches++;
+    S.depth_lut = lut;
+  }
+#endif
   // -1 in every entity slot / ghost
   dev_memset(S.ent_proto, 0xFF, E * N * sizeof(int32_t));
   dev_memset(S.ghost_slot, 0xFF, N * sizeof(int32_t));
@@ -642,6 +655,8 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     const char* v = getenv("MWB_K2_VARIANT");
     h->k2_variant = v ? atoi(v) : MWB_K2_DEFAULT_VARIANT;
     if (h->k2_variant < 0 || h->k2_variant > 2) h->k2_variant = MWB_K2_DEFAULT_VARIANT;
+    const char* f = getenv("MWB_K2_FLAGS");
+    h->k2_flags = f ? atoi(f) : (MWB_K2_LISTS | MWB_K2_PAIRS);
   }
   h->stage_bytes = (int)(((size_t)cfg->max_quads * sizeof(mwb_quad) + 15) & ~(size_t)15);
   if (h->stage_bytes > MWB_STAGE_QUAD_BYTES_HOST) h->stage_bytes = 0;
@@ -650,9 +665,9 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     cudaFuncAttributes fa;
     cudaError_t e;
     switch (h->k2_variant) {
-      case 0: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, false>)
-                : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 320, 3, false>)
-                                         : cudaFuncGetAttributes(&fa, render_kernel<1, 320, 3, false>); break;
+      case 0: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 256, 3, true>)
+                : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 256, 3, true>)
+                                         : cudaFuncGetAttributes(&fa, render_kernel<1, 256, 3, true>); break;
       case 1: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, true>)
                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 320, 3, true>)
                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 320, 3, true>); break;
@@ -675,7 +690,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (getenv("MWB_DEBUG")) {
     int nb = 0;
     switch (h->k2_variant) {
-      case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, false>, 320, smem); break;
+      case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 3, true>, 320, smem); break;
       case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, true>, 320, smem); break;
       default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 4, true>, 256, smem); break;
     }
@@ -1172,9 +1187,10 @@ extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int
 static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int count, stream_t s) {
 #ifndef MWB_HOSTSIM
   const int smem = k2_smem_bytes(h), fstage = k2_frame_stage_bytes(h);
+  const K2Layout lay = k2_layout(h->smem_tris, h->tri_cap, h->stage_bytes, k2_halves_per_part(h->S.obs_w, h->S.obs_h, h->k2_parts), fstage);
   if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   prof_mark(h, h->ev_k2, s);
-#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, h->obs_format, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, fstage, h->d_overflow)
+#define MWB_LAUNCH_K2(M, T, B, D) render_kernel<M, T, B, D><<<count * h->k2_parts, T, smem, s>>>(h->S, h->A, h->view, h->obs_format, obs, depth, env0, h->k2_parts, h->tri_cap, h->stage_bytes, fstage, h->k2_flags, lay, h->d_overflow)
 #define MWB_LAUNCH_K2_MSAA(T, B, D)                 \
   switch (h->S.msaa) {                              \
     case 1: MWB_LAUNCH_K2(1, T, B, D); break;       \
@@ -1182,7 +1198,7 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
     default: MWB_LAUNCH_K2(8, T, B, D); break;      \
   }
   switch (h->k2_variant) {
-    case 0: MWB_LAUNCH_K2_MSAA(320, 3, false); break;
+    case 0: MWB_LAUNCH_K2_MSAA(256, 3, true); break;
     case 1: MWB_LAUNCH_K2_MSAA(320, 3, true); break;
     default: MWB_LAUNCH_K2_MSAA(256, 4, true); break;
   }

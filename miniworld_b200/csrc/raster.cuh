@@ -28,6 +28,42 @@
 
 #define MWB_K2_DEFAULT_VARIANT 1
 
+#define MWB_TILE_CAP 16              // candidate triangles listed per half-tile; fuller half-tiles scan the lists
+#define MWB_K2_LISTS 1               // kernel flags (env MWB_K2_FLAGS, default all on): per-half-tile candidate lists,
+#define MWB_K2_PAIRS 2               // quad-pair lazy pixels
+
+// K2's dynamic shared memory, in this order (host and kernel share the arithmetic):
+//   [triangle records (small levels)] [staged static quads] [visit order u16 + depth keys f32]
+//   [slot of every record u16] [per-half-tile candidate counts u16 + lists u16 x MWB_TILE_CAP] [frame stage]
+struct K2Layout {
+  int order_off, zkey_off, slot_off, cnt_off, list_off, stage_off, end;
+};
+static inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+K2Layout k2_layout(bool smem_tris, int tri_cap, int stage_bytes, int halves_per_part, int frame_stage_bytes) {
+  K2Layout L;
+  const int tri_bytes = smem_tris ? tri_cap * (int)sizeof(TriRec) : 0;
+  const int cap2 = (tri_cap + 1) & ~1;
+  L.order_off = tri_bytes + stage_bytes;
+  L.zkey_off = L.order_off + cap2 * 2;
+  L.slot_off = L.zkey_off + tri_cap * 4;
+  L.cnt_off = L.slot_off + cap2 * 2;
+  L.list_off = L.cnt_off + ((halves_per_part + 1) & ~1) * 2;
+  L.stage_off = (L.list_off + halves_per_part * MWB_TILE_CAP * 2 + 15) & ~15;
+  L.end = L.stage_off + frame_stage_bytes;
+  return L;
+}
+static inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int k2_halves_per_part(int W, int H, int parts) {
+  const int n_halves = ((W + 7) >> 3) * ((H + 3) >> 2);
+  return (n_halves + parts - 1) / parts;
+}
+
 #ifdef __CUDACC__
 
 #define MWB_MAX_SEGS (2 + MWB_MAX_DRAWN)   // rooms, drawn entities, the top view's agent marker
@@ -206,13 +242,19 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
   }
 }
 
+// ---- depth16 code -> metres table (65536 floats, built once per handle by the very function it replaces)
+__global__ void depth_lut_kernel(float* __restrict__ lut) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < 65536u) lut[c] = depth_code_to_metres(c);
+}
+
 // ---- K2 --------------------------------------------------------------------------------
 // THREADS x MINB: block size and resident blocks per SM the kernel is compiled for (64 registers per thread);
 // DYN: warps claim half-tiles from a shared counter instead of striding, which evens out the per-warp work.
 template <int MSAA, int THREADS, int MINB, bool DYN>
 __global__ void __launch_bounds__(THREADS, MINB)
 render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __restrict__ obs, float* __restrict__ depth, int env0,
-              int parts, int tri_cap, int stage_bytes, int frame_stage_bytes, int* __restrict__ overflow) {
+              int parts, int tri_cap, int stage_bytes, int frame_stage_bytes, int flags, K2Layout lay, int* __restrict__ overflow) {
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // large frames are cut into `parts` blocks per env (each redoes the cheap geometry phase and
@@ -239,6 +281,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = S.obs_w, H = S.obs_h;
+  const bool use_lists = (flags & MWB_K2_LISTS) != 0, pairs = (flags & MWB_K2_PAIRS) != 0;   // measurement switches
 
   // static room quads of this env: staged into shared memory by one TMA bulk copy that overlaps
   // the camera set-up (fixed-layout levels: 56 quads = 7.6 KB); larger templates are read from L2
@@ -247,11 +290,14 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   const uint32_t quad_bytes = ((uint32_t)nq * (uint32_t)sizeof(mwb_quad) + 15u) & ~15u;
   const bool staged = quad_bytes > 0 && quad_bytes <= (uint32_t)stage_bytes;
   mwb_quad* squads = reinterpret_cast<mwb_quad*>(smem_raw + tri_bytes);
-  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + tri_bytes + stage_bytes);
-  float* zkey = reinterpret_cast<float*>(order + ((tri_cap + 1) & ~1));
+  uint16_t* order = reinterpret_cast<uint16_t*>(smem_raw + lay.order_off);
+  float* zkey = reinterpret_cast<float*>(smem_raw + lay.zkey_off);
+  uint16_t* tri_slot = reinterpret_cast<uint16_t*>(smem_raw + lay.slot_off);     // record position -> slot (draw order)
+  uint16_t* tile_cnt = reinterpret_cast<uint16_t*>(smem_raw + lay.cnt_off);      // candidates per half-tile of this part
+  uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem_raw + lay.list_off);    // [half-tile][MWB_TILE_CAP] record positions
   // whole-frame RGB stage (frame_stage_bytes > 0): warps drop their pixels here and the block writes the frame
   // out at the end with 16-byte stores in address order
-  uint8_t* fstage = smem_raw + ((tri_bytes + stage_bytes + (size_t)tri_cap * 6 + 8 + 15) & ~(size_t)15);
+  uint8_t* fstage = smem_raw + lay.stage_off;
   __shared__ double trig[6];
   __shared__ int next_half;
   if (tid == 0) mbar_init(&quad_bar, 1);
@@ -278,6 +324,16 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     TriRec rec;
     int keep = 0, seg = 0;
     if (task < fmap.n_tasks) keep = task_triangle(S, A, cam, fmap, quads, i, task, W, H, rec, seg) ? 1 : 0;
+    // quads stay PAIRS: tasks (2k, 2k + 1) are the fan halves of one planar quad (room quad, box face; the map
+    // view's marker pairs with nothing).  If either half survives both keep a record -- the culled one an empty record
+    // -- so that records / slots (2k, 2k + 1) always belong together (classify_pixel's pair logic relies on it).
+    const int keep_other = __shfl_xor_sync(0xffffffffu, keep, 1);
+    const int seg_other = __shfl_xor_sync(0xffffffffu, seg, 1);
+    if (!keep && keep_other) {
+      empty_record(rec);
+      seg = seg_other;
+      keep = 1;
+    }
     int incl = keep;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -331,41 +387,80 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         sg.by = mi.by;
       }
       sg.base = slot;
-      slot += sg.count;
+      slot += (sg.count + 1) & ~1;       // even bases: slot parity == record parity inside every list (quad pairs)
     }
   }
   __syncthreads();
   const int nsegs = 1 + fmap.n_ents + (fmap.agent_task >= 0 ? 1 : 0);
 
-  // ---- visiting order of the room triangles: front to back by their nearest possible depth, so
-  // that the conservative occlusion tests fire early (the result does not depend on the order)
+  // ---- visiting order of the block-resident triangles (rooms, boxes, the map view's marker): front to back by
+  // their nearest possible depth, so that the conservative occlusion tests fire early (the image does not depend
+  // on the order: per sample the result is the minimum over (depth code, slot))
+  const int n_res = ntris < tri_cap ? ntris : tri_cap;
   {
-    const int n0 = segs[0].count;
-    for (int t = tid; t < n0; t += THREADS) {
+    for (int t = tid; t < n_res; t += THREADS) {
       const TriRec& T = tris[t];
       const float x0 = (float)(T.bx & 0xFFFF), x1 = (float)((T.bx >> 16) + 1), y0 = (float)(T.by & 0xFFFF), y1 = (float)((T.by >> 16) + 1);
       zkey[t] = T.Zc + fminf(T.Za * x0, T.Za * x1) + fminf(T.Zb * y0, T.Zb * y1);
+      // slot of record t: the records of one list are contiguous, in draw order
+      int slot = t;
+      for (int k = 0; k < nsegs; ++k) {
+        const Segment& sg = segs[k];
+        if (sg.bbox != nullptr) continue;
+        const int start = (int)(sg.tris - tris);
+        if (t >= start && t < start + sg.count) slot = sg.base + (t - start);
+      }
+      tri_slot[t] = (uint16_t)slot;
     }
     __syncthreads();
-    if (n0 <= MWB_SORT_LIMIT) {
-      for (int t = tid; t < n0; t += THREADS) {
+    if (n_res <= MWB_SORT_LIMIT) {
+      for (int t = tid; t < n_res; t += THREADS) {
         const float z = zkey[t];
         int rank = 0;
-        for (int q = 0; q < n0; ++q) {
+        for (int q = 0; q < n_res; ++q) {
           const float zq = zkey[q];
           rank += (zq < z || (zq == z && q < t)) ? 1 : 0;
         }
         order[rank] = (uint16_t)t;
       }
     } else {
-      for (int t = tid; t < n0; t += THREADS) order[t] = (uint16_t)t;
+      for (int t = tid; t < n_res; t += THREADS) order[t] = (uint16_t)t;
     }
     __syncthreads();
   }
 
-  // ---- C/D. one warp per 8x4 half-tile (lane = one pixel; an 8x8 tile is two of them)
+  // ---- candidate lists: one THREAD per half-tile walks the block-resident triangles in visiting order and files
+  // those that can touch its half-tile (bbox + the three conservative edge bounds) -- the test every rasteriser warp
+  // used to repeat per 32-triangle chunk is done once per (triangle, half-tile) pair here, lanes = half-tiles, the
+  // triangle fields broadcast from shared memory.  A half-tile with more than MWB_TILE_CAP candidates keeps only
+  // the count; its warp then scans the lists the old way.
   const int tiles_x = (W + 7) >> 3;
   const float inv_tiles_x = 1.0f / (float)tiles_x;
+  const int halves_y = (H + 3) >> 2;
+  const int n_halves = tiles_x * halves_y, per_part = (n_halves + parts - 1) / parts;
+  const int h_begin = part * per_part, h_end = min(n_halves, h_begin + per_part);
+  for (int hl = tid; hl < h_end - h_begin; hl += THREADS) {
+    const int half = h_begin + hl;
+    const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;
+    const int tx0 = hcol << 3, ty0 = hrow << 2;
+    const float fx0 = (float)tx0, fy0 = (float)ty0;
+    int cnt = 0;
+    for (int q = 0; q < n_res; ++q) {
+      const int p = order[q];
+      const TriRec& t = tris[p];
+      const int bx = t.bx, by = t.by;
+      if ((bx & 0xFFFF) > tx0 + 7 || (bx >> 16) < tx0 || (by & 0xFFFF) > ty0 + 3 || (by >> 16) < ty0) continue;
+      if (t.A[0] * fx0 + t.B[0] * fy0 + t.K[0] < 0.0f || t.A[1] * fx0 + t.B[1] * fy0 + t.K[1] < 0.0f ||
+          t.A[2] * fx0 + t.B[2] * fy0 + t.K[2] < 0.0f)
+        continue;
+      if (cnt < MWB_TILE_CAP) tile_list[hl * MWB_TILE_CAP + cnt] = (uint16_t)p;
+      ++cnt;
+    }
+    tile_cnt[hl] = (uint16_t)min(cnt, 0xFFFF);
+  }
+  __syncthreads();
+
+  // ---- C/D. one warp per 8x4 half-tile (lane = one pixel; an 8x8 tile is two of them)
   const int lx = lane & 7, ly = lane >> 3;
   const SegLookup fetch{segs, nsegs};
   // exact-phase work is done sample-parallel: lane -> (queued item lane / MSAA, sample lane % MSAA)
@@ -377,9 +472,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   uint32_t(*skeys)[32] = ws.keys;
   uint32_t* equeue = ws.items;
   // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x
-  const int halves_y = (H + 3) >> 2;
-  const int n_halves = tiles_x * halves_y, per_part = (n_halves + parts - 1) / parts;
-  const int h_begin = part * per_part, h_end = min(n_halves, h_begin + per_part);
   if (DYN) {
     if (tid == 0) next_half = h_begin + WARPS;
     __syncthreads();
@@ -389,6 +481,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   while (half < h_end) {
     const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;   // exact: half < 2^20
     const int tx0 = hcol << 3, ty0 = hrow << 2;
+    const int hl = half - h_begin;
     if (DYN) {                 // claim the next half-tile now; the atomic's latency hides behind this one
       int nxt = 0;
       if (lane == 0) nxt = atomicAdd(&next_half, 1);
@@ -430,14 +523,69 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
       qn = 0;
     };
 
+    // Queue what this lane's pixel could not decide for the candidates flagged in `mine` (first the lazily held
+    // triangle -- or both halves of a lazily held quad pair -- which must now be materialised); the queue is drained
+    // sample-parallel by flush().  slot_of(b) = slot of candidate b.
+    auto enqueue = [&](uint32_t mine, uint32_t mine_full, auto slot_of) {
+      int need_mat = (mine != 0 && P.mode == MWB_PX_LAZY) ? (lazy_is_pair(P) ? 2 : 1) : 0;
+      if (mine != 0 && P.mode != MWB_PX_EXPLICIT) {
+        P.bound = P.mode == MWB_PX_LAZY ? P.lazy_chi : 65535.0f;   // still an upper bound after materialisation
+        P.mode = MWB_PX_EXPLICIT;
+      }
+#pragma unroll 1
+      for (;;) {
+        const bool has = need_mat != 0 || mine != 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, has);
+        if (!bal) break;
+        const int cnt = __popc(bal);
+        if (qn + cnt > MWB_EQ_CAP) flush();
+        if (has) {
+          const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+          uint32_t item;
+          if (need_mat == 2) {          // a pair: both halves, each with its edge tests (the diagonal decides)
+            item = ((uint32_t)lane << 16) | (uint32_t)(P.lazy_slot ^ 1);
+            need_mat = 3;
+          } else if (need_mat) {
+            item = (need_mat == 1 ? (1u << 21) : 0u) | ((uint32_t)lane << 16) | (uint32_t)P.lazy_slot;
+            need_mat = 0;
+          } else {
+            const int b = __ffs(mine) - 1;
+            mine &= mine - 1;
+            item = (((mine_full >> b) & 1u) << 21) | ((uint32_t)lane << 16) | (uint32_t)slot_of(b);
+          }
+          equeue[pos] = item;
+        }
+        qn += cnt;
+      }
+    };
+
+    // ---- hot path: this half-tile's list of block-resident triangles (already tested against the half-tile, in
+    // front-to-back order); every listed triangle is triaged at each lane's pixel (warp-uniform loop)
+    const int n_cand = tile_cnt[hl];
+    const bool listed = use_lists && n_cand <= MWB_TILE_CAP;
+    if (listed) {
+      const uint16_t* list = tile_list + hl * MWB_TILE_CAP;
+      uint32_t mine = 0, mine_full = 0;
+#pragma unroll 1
+      for (int q = 0; q < n_cand; ++q) {
+        const int p = list[q];
+        const ClassTri ct = load_class(tris + p);
+        const int cls = classify_pixel<MSAA>(ct, (int)tri_slot[p], px, py, P, pairs ? tris + (p ^ 1) : nullptr, (p & 1) ? 1 : 2);
+        if (cls) mine |= 1u << q;
+        if (cls == 2) mine_full |= 1u << q;
+      }
+      enqueue(mine, mine_full, [&](int b) { return (int)tri_slot[list[b]]; });
+    }
+
+    // ---- generic path: the mesh lists in HBM (and, for a half-tile whose candidate list overflowed, the resident lists)
 #pragma unroll 1
     for (int sgi = 0; sgi < nsegs; ++sgi) {
       const Segment sg = segs[sgi];
-      if (sg.count == 0) continue;
+      if (sg.count == 0 || (listed && sg.bbox == nullptr)) continue;
       if ((sg.bx & 0xFFFF) > tx0 + 7 || (sg.bx >> 16) < tx0 || (sg.by & 0xFFFF) > ty0 + 3 || (sg.by >> 16) < ty0) continue;
-      // which triangles to visit: segment 0 in front-to-back order; a binned mesh list only the triangles
-      // filed under this half-tile; else the whole list
-      const uint16_t* ord = sgi == 0 ? order : nullptr;
+      const bool pairable = pairs && sg.bbox == nullptr;   // resident lists hold quad pairs in adjacent records
+      // which triangles to visit: a binned mesh list only the triangles filed under this half-tile; else the whole list
+      const uint16_t* ord = nullptr;
       int lo = 0, hi = sg.count;
       if (sg.bin_off != nullptr) {
         const int cols = ((sg.bx >> 16) >> 3) - ((sg.bx & 0xFFFF) >> 3) + 1;
@@ -487,39 +635,12 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
           mask &= mask - 1;
           const int tb = ws.chunk[b];
           const ClassTri ct = load_class(sg.tris + tb);
-          const int cls = classify_pixel<MSAA>(ct, sg.base + tb, px, py, P);
+          const int cls = classify_pixel<MSAA>(ct, sg.base + tb, px, py, P, pairable ? sg.tris + (tb ^ 1) : nullptr, (tb & 1) ? 1 : 2);
           if (cls) mine |= 1u << b;
           if (cls == 2) mine_full |= 1u << b;
         }
-        // phase 2: queue what this pixel could not decide (first the lazily held triangle, which
-        // must now be materialised); the queue is drained sample-parallel by flush()
-        bool need_mat = mine != 0 && P.mode == MWB_PX_LAZY;
-        if (mine != 0 && P.mode != MWB_PX_EXPLICIT) {
-          P.bound = P.mode == MWB_PX_LAZY ? P.lazy_chi : 65535.0f;   // still an upper bound after materialisation
-          P.mode = MWB_PX_EXPLICIT;
-        }
-#pragma unroll 1
-        for (;;) {
-          const bool has = need_mat || mine != 0;
-          const uint32_t bal = __ballot_sync(0xffffffffu, has);
-          if (!bal) break;
-          const int cnt = __popc(bal);
-          if (qn + cnt > MWB_EQ_CAP) flush();
-          if (has) {
-            const int pos = qn + __popc(bal & ((1u << lane) - 1u));
-            uint32_t item;
-            if (need_mat) {
-              item = (1u << 21) | ((uint32_t)lane << 16) | (uint32_t)P.lazy_slot;
-              need_mat = false;
-            } else {
-              const int b = __ffs(mine) - 1;
-              mine &= mine - 1;
-              item = (((mine_full >> b) & 1u) << 21) | ((uint32_t)lane << 16) | (uint32_t)(sg.base + ws.chunk[b]);
-            }
-            equeue[pos] = item;
-          }
-          qn += cnt;
-        }
+        // phase 2: queue what this pixel could not decide
+        enqueue(mine, mine_full, [&](int b) { return sg.base + ws.chunk[b]; });
       }
     }
     if (qn) flush();
@@ -531,7 +652,16 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     int lazy_slot = -1;
     if (P.mode == MWB_PX_LAZY) {
       lazy_slot = P.lazy_slot;
-      code0 = depth != nullptr ? sample0_code<MSAA>(fetch(P.lazy_slot), px, py) : 0u;   // only the depth map needs it
+      if (depth != nullptr) {              // only the depth map needs sample 0's exact code
+        int owner = lazy_slot;
+        if (lazy_is_pair(P)) {             // which half of the quad owns sample 0: its diagonal edge decides
+          const float xs = (float)px + sample_x<MSAA>(0), ys = (float)py + sample_y<MSAA>(0);
+          if (!pair_sample_in_first(fetch(lazy_slot), (lazy_slot & 1) ? 1 : 2, xs, ys)) owner = lazy_slot ^ 1;
+        }
+        code0 = sample0_code<MSAA>(fetch(owner), px, py);
+      } else {
+        code0 = 0u;
+      }
     } else {
 #pragma unroll
       for (int s = 0; s < MSAA; ++s) P.keys[s] = skeys[s][lane];
@@ -589,7 +719,9 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
         }
       }
     }
-    if (depth != nullptr && px < W && py < H) depth[((size_t)i * H + py) * W + px] = depth_code_to_metres(code0);
+    // FrameBuffer.get_depth_map's float32 formula (two IEEE divisions per pixel) tabulated once per handle
+    if (depth != nullptr && px < W && py < H)
+      depth[((size_t)i * H + py) * W + px] = S.depth_lut != nullptr ? __ldg(S.depth_lut + code0) : depth_code_to_metres(code0);
   }
   if (obs != nullptr && frame_stage_bytes > 0) {
     __syncthreads();

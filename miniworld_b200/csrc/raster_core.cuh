@@ -254,6 +254,7 @@ struct MWB_ALIGN16 TriRec {
   float UA, UB, VA, VB, SA, SB;  // sum_k u_k A_k, sum_k u_k B_k, ... : per-triangle parts of du/dx, dv/dx, ...
   float K[3];                    // half-tile rejection: max of E_k over an 8x4 block at (x0, y0) is A x0 + B y0 + K
   float Kz;                      // likewise min of z - Zr: Za x0 + Zb y0 + Kz
+  int32_t flat;                  // 1: the three lit vertex colours are identical (flat normal under the directional light)
 };
 
 // the hot 76 bytes of a TriRec, held in registers while a tile is rasterised
@@ -337,6 +338,7 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   t.g[0] = b0.g; t.g[1] = b1.g; t.g[2] = b2.g;
   t.b[0] = b0.b; t.b[1] = b1.b; t.b[2] = b2.b;
   t.tex = tex;
+  t.flat = (b0.r == b1.r && b1.r == b2.r && b0.g == b1.g && b1.g == b2.g && b0.b == b1.b && b1.b == b2.b) ? 1 : 0;
   t.UA = t.u[0] * t.A[0] + t.u[1] * t.A[1] + t.u[2] * t.A[2];
   t.UB = t.u[0] * t.B[0] + t.u[1] * t.B[1] + t.u[2] * t.B[2];
   t.VA = t.v[0] * t.A[0] + t.v[1] * t.A[1] + t.v[2] * t.A[2];
@@ -448,6 +450,7 @@ struct PixelState {
   int32_t lazy_slot;
   float lazy_clo, lazy_chi;      // conservative bounds of the lazy triangle's depth codes here
   float bound;                   // EXPLICIT mode: an upper bound of every stored depth code
+  int32_t pair_skip;             // slot whose samples at this pixel are already accounted for (see classify_pixel), or -1
 };
 
 template <int MSAA>
@@ -459,7 +462,12 @@ MWB_DEV void pixel_init(PixelState<MSAA>& p) {
   p.lazy_slot = -1;
   p.lazy_clo = p.lazy_chi = 65535.0f;
   p.bound = 65535.0f;
+  p.pair_skip = -1;
 }
+
+// A lazy pixel held by a PAIR: the two fan triangles (0,1,2), (0,2,3) of one planar quad together cover every sample.
+template <int MSAA>
+MWB_DEV bool lazy_is_pair(const PixelState<MSAA>& p) { return p.pair_skip == (p.lazy_slot ^ 1); }
 
 // largest depth code that can currently be stored at any sample of the pixel
 template <int MSAA>
@@ -492,9 +500,20 @@ MWB_DEV ClassTri load_class(const TriRec* t) {
 // Cheap per-pixel triage of one triangle.  Returns 0 if it was skipped or installed lazily; else it
 // still needs exact per-sample processing at this pixel: 1 = partial coverage possible, 2 = it
 // certainly covers every sample (edge tests can be skipped).
+//
+// Quad pairs.  Room quads and box faces reach the rasteriser as the fan triangles (0,1,2), (0,2,3) of a planar quad,
+// stored in adjacent records / slots (2k, 2k + 1); the shared diagonal is edge 2 of the first and edge 1 of the
+// second, with exactly negated coefficients and complementary tie thresholds, so a sample inside the quad's four
+// OUTER edges belongs to exactly one of the two.  `partner` (or null) is the other record of such a pair: a pixel
+// whose samples are all certainly inside the four outer edges is held lazily by the pair -- which triangle owns a
+// given sample is only decided if the exact keys are ever needed (materialisation queues both; the depth map
+// evaluates the diagonal at sample 0).  Without this every pixel a diagonal crosses would go through the exact
+// per-sample path although it shows a single flat surface.
 template <int MSAA>
-MWB_DEV int classify_pixel(const ClassTri& t, int slot, int px, int py, PixelState<MSAA>& p) {
+MWB_DEV int classify_pixel(const ClassTri& t, int slot, int px, int py, PixelState<MSAA>& p, const TriRec* partner = nullptr,
+                           int diag = 0) {
   MWB_COUNT(0);
+  if (slot == p.pair_skip) return 0;                      // already covered through its partner at this pixel
   const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
   const float e0 = t.A[0] * cx + t.B[0] * cy + t.C[0];
   const float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
@@ -504,22 +523,60 @@ MWB_DEV int classify_pixel(const ClassTri& t, int slot, int px, int py, PixelSta
   const float zlo = zc - t.Zr, zhi = zc + t.Zr;
   if (zlo > 1.0f || zhi < 0.0f) { MWB_COUNT(2); return 0; }                           // certainly clipped away
   // depth codes any sample of this pixel can get lie in [clo, chi] (one code of slack each way)
-  const float clo = zlo * 65535.0f - 1.0f, chi = zhi * 65535.0f + 1.5f;
+  float clo = zlo * 65535.0f - 1.0f, chi = zhi * 65535.0f + 1.5f;
   if (clo > pixel_bound(p)) { MWB_COUNT(3); return 0; }                               // certainly occluded
-  const bool full = e0 - t.R[0] > 0.0f && e1 - t.R[1] > 0.0f && e2 - t.R[2] > 0.0f;   // covers every sample
+  const bool in0 = e0 - t.R[0] > 0.0f, in1 = e1 - t.R[1] > 0.0f, in2 = e2 - t.R[2] > 0.0f;
+  const bool full = in0 && in1 && in2;                                                // covers every sample
+  bool pair = false;
+  if (partner != nullptr && !full && in0 && (diag == 1 ? in2 : in1)) {
+    // only the diagonal is undecided here: do the partner's two outer edges certainly contain every sample too?
+    // (the partner's diagonal is edge 3 - diag; its plane is this one up to rounding: one more code of slack)
+    const int pd = 3 - diag, k1 = pd == 1 ? 2 : 1;
+    const float f0 = partner->A[0] * cx + partner->B[0] * cy + partner->C[0] - partner->R[0];
+    const float f1 = partner->A[k1] * cx + partner->B[k1] * cy + partner->C[k1] - partner->R[k1];
+    pair = f0 > 0.0f && f1 > 0.0f && zlo >= 2e-5f;
+    if (pair) { clo -= 1.0f; chi += 1.0f; }
+  }
   const bool unclipped = zlo >= 0.0f && zhi <= 1.0f && chi < 65535.0f;
-  if (full && unclipped) {
+  if ((full || pair) && unclipped) {
     const bool wins = p.mode == MWB_PX_EMPTY || (p.mode == MWB_PX_LAZY && chi < p.lazy_clo);
-    if (wins) {                      // every sample now certainly belongs to this triangle
+    if (wins) {                      // every sample now certainly belongs to this triangle (or its pair)
       p.mode = MWB_PX_LAZY;
       p.lazy_slot = slot;
       p.lazy_clo = clo;
       p.lazy_chi = chi;
+      if (pair) p.pair_skip = slot ^ 1;
       MWB_COUNT(5);
       return 0;
     }
   }
   return full ? 2 : 1;
+}
+
+// Record that no sample can ever hit (the culled half of a quad pair keeps its slot)
+MWB_DEV void empty_record(TriRec& r) {
+  for (int k = 0; k < 3; ++k) {
+    r.A[k] = r.B[k] = 0.0f;
+    r.C[k] = -1.0f;
+    r.R[k] = 0.0f;
+    r.T[k] = 0.0f;
+    r.K[k] = -1.0f;
+    r.u[k] = r.v[k] = r.r[k] = r.g[k] = r.b[k] = 0.0f;
+  }
+  r.Za = r.Zb = 0.0f;
+  r.Zc = 2.0f;
+  r.Zr = 0.0f;
+  r.Kz = 2.0f;
+  r.tex = -1;
+  r.flat = 1;
+  r.bx = 1;          // x0 = 1 > x1 = 0
+  r.by = 1;
+  r.UA = r.UB = r.VA = r.VB = r.SA = r.SB = 0.0f;
+}
+
+// Which record of a pair owns sample (xs, ys) that lies inside the quad: the one whose diagonal edge says so
+MWB_DEV bool pair_sample_in_first(const TriRec& t, int diag, float xs, float ys) {
+  return edge_value(t.A[diag], t.B[diag], t.C[diag], xs, ys) >= t.T[diag];
 }
 
 // One sample of the exact path: coverage by the three edge functions (unless the triangle is
@@ -582,9 +639,12 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
   const float inv = 1.0f / (e0 + e1 + e2);
 #endif
   float b0 = e0 * inv, b1 = e1 * inv, b2 = e2 * inv;
-  float r = b0 * t.r[0] + b1 * t.r[1] + b2 * t.r[2];
-  float g = b0 * t.g[0] + b1 * t.g[1] + b2 * t.g[2];
-  float b = b0 * t.b[0] + b1 * t.b[1] + b2 * t.b[2];
+  float r = t.r[0], g = t.g[0], b = t.b[0];
+  if (!t.flat) {                 // Gouraud: the weights sum to 1, so equal vertex colours need no interpolation
+    r = b0 * r + b1 * t.r[1] + b2 * t.r[2];
+    g = b0 * g + b1 * t.g[1] + b2 * t.g[2];
+    b = b0 * b + b1 * t.b[1] + b2 * t.b[2];
+  }
   if (t.tex >= 0) {
     const TexDev& T = A.tex[t.tex];
     float u = b0 * t.u[0] + b1 * t.u[1] + b2 * t.u[2];

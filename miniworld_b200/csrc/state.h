@@ -69,6 +69,7 @@ struct DevState {
   uint16_t* mesh_bin_idx;       // [N][E][MWB_BIN_REFS * mesh_cap]
   int32_t* mesh_bin_off;        // [N][E][MWB_MAX_BINS + 1]
   int32_t mesh_cap;             // 0 = the level has no mesh entities
+  const float* depth_lut;       // [65536] depth16 code -> metres (depth_code_to_metres of every code), or null
   TriRec* room_tris;            // [N][tri_cap] room + box triangle lists in HBM for levels whose lists do
                                 //   not fit shared memory (Maze); null = lists live in shared memory
 

@@ -17,7 +17,9 @@ import tempfile
 rep = sys.argv[1]
 so = sys.argv[2] if len(sys.argv) > 2 else "miniworld_b200/libmwb.so"
 kern = sys.argv[3] if len(sys.argv) > 3 else "_Z13render_kernelILi8ELi320ELi3ELb1E"
-root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "miniworld_b200", "csrc", "")
+if os.environ.get("CSRC"):
+    pass
+root = os.environ.get("CSRC") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "miniworld_b200", "csrc", "")
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -42,9 +44,9 @@ marks = {
                 (find(rc, "struct FrameMap"), "B geometry/setup"), (find(rc, "struct Segment"), "D seg lookup"),
                 (find(rc, "MWB_DEV uint32_t key_id"), "D resolve bookkeeping")]),
     rk: sorted([(1, "A prologue/TMA"), (find(rk, "B. room + box"), "B compaction"),
-                (find(rk, "visiting order of the room"), "B sort"), (find(rk, "C/D. one warp"), "C0 tile loop/tri test"),
+                (find(rk, "visiting order of the block-resident"), "B sort"), (find(rk, "candidate lists: one THREAD"), "B2 tile lists"), (find(rk, "C/D. one warp"), "C0 tile loop/tri test"),
                 (find(rk, "auto flush"), "C2 flush (sample-parallel exact)"),
-                (find(rk, "for (int sgi = 0"), "C0 tile loop/tri test"), (find(rk, "phase 2: queue"), "C2 enqueue"),
+                (find(rk, "sources of candidate triangles"), "C0 tile loop/tri test"), (find(rk, "phase 2: queue"), "C2 enqueue"),
                 (find(rk, "Lazy pixels join"), "D resolve/store")]),
 }
 
