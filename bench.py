@@ -41,6 +41,40 @@ W, H = 80, 60
 BYTES_RGB = W * H * 3
 BYTES_DEPTH = W * H * 4
 FALLBACK_HBM_GBS = 6650.0
+# BASELINE.json configs (index as in its `configs` list); envs = per GPU under weak scaling.  Config 3 is the one the
+# metric is quoted on and the default; 4 and 5 are the two configs it states for 8 GPUs (8192 / 8 and 4096 / 8 envs per GPU).
+CONFIGS = {
+    2: dict(level="MiniWorld-OneRoom-v0", envs=1024, w=80, h=60, depth=False, dr=False),
+    3: dict(level="MiniWorld-FourRooms-v0", envs=4096, w=80, h=60, depth=True, dr=False),
+    4: dict(level="MiniWorld-MazeS8-v0", envs=1024, w=80, h=60, depth=False, dr=True),
+    5: dict(level="MiniWorld-PickupObjects-v0", envs=512, w=160, h=120, depth=False, dr=False),
+}
+
+
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
+    (first-touch then places the pinned pages on that node): with 8 ranks on a two-socket box the device->host
+    copies otherwise cross the socket interconnect for half of the GPUs.  Returns (node, n_cpus) or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:
+        return None
 
 
 def measured_hbm():
@@ -107,8 +141,13 @@ class ClockSampler(threading.Thread):
 def _port_worker(args):
     """One process: the oracle port of the workload on one core; `warm_s` untimed seconds, then
     `budget_s` timed seconds.  Returns (env-steps, seconds) of the timed part."""
-    rank, warm_s, budget_s, seed0 = args
+    rank, warm_s, budget_s, seed0, cpu = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    if cpu is not None:
+        try:
+            os.sched_setaffinity(0, {cpu})      # one worker per PHYSICAL core, pinned: no migration, no sibling sharing
+        except OSError:
+            pass
     from miniworld_b200.assets import Texture
     from miniworld_b200.envs import LEVELS
     from oracle import softgl
@@ -138,14 +177,55 @@ def _port_worker(args):
     return n, time.perf_counter() - t0
 
 
+def physical_cores():
+    """One logical CPU per physical core (the first hyper-thread sibling of each), restricted to this process's
+    affinity mask."""
+    allowed = sorted(os.sched_getaffinity(0))
+    seen, out = set(), []
+    for c in allowed:
+        try:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c) as f:
+                sib = f.read().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            out.append(c)
+    return out
+
+
 def cpu_port_throughput(cores, warm_s, budget_s):
+    """cores: 1, or a list of logical CPUs to pin one worker each to."""
     if cores == 1:
-        n, dt = _port_worker((0, warm_s, budget_s, 1000))
+        n, dt = _port_worker((0, warm_s, budget_s, 1000, None))
         return n / dt, n
     import multiprocessing as mp
-    with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_port_worker, [(r, warm_s, budget_s, 1000) for r in range(cores)])
+    with mp.get_context("spawn").Pool(len(cores)) as pool:
+        res = pool.map(_port_worker, [(r, warm_s, budget_s, 1000, c) for r, c in enumerate(cores)])
     return sum(n / dt for n, dt in res), sum(n for n, _ in res)
+
+
+def reference_physics_only(seconds=4.0):
+    """BASELINE.md section 4 fallback 2a, where /root/reference exists (the build container, not the GPU box): the
+    UNMODIFIED reference's step() with GL stubbed out (no rendering) on one core -- an upper bound of what the
+    reference's own Python can do per core.  None when the reference is absent."""
+    try:
+        from oracle import ref_stub
+        if not ref_stub.reference_available():
+            return None
+        env = ref_stub.make_reference_env(LEVEL, record=False)
+        env.reset(seed=1000)
+        rng = np.random.default_rng(12345)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            _, _, te, tr, _ = env.step(int(rng.integers(0, 3)))
+            if te or tr:
+                env.reset()
+            n += 1
+        return {"value": n / (time.perf_counter() - t0), "unit": "env-steps/s", "cores": 1,
+                "what": "reference MiniWorldEnv.step, GL calls ignored (no frame is produced)"}
+    except Exception:
+        return None
 
 
 def run_reference_arm(args):
@@ -154,21 +234,26 @@ def run_reference_arm(args):
         return
     from oracle import softgl
     softgl.build()
-    cores = os.cpu_count() or 1
+    cpus = physical_cores()
+    cores = len(cpus)
     # the K "steps" are K equal slices of one continuous run (each slice a bounded sample of
     # the workload); W warm-up slices are discarded.  Whole arm <= ~2 minutes.
     slice_s = min(1.0, 100.0 / max(1, args.steps + args.warmup))
     warm_s, budget = slice_s * args.warmup, slice_s * args.steps
-    value, vals = cpu_port_throughput(cores, warm_s, budget)
+    value, vals = cpu_port_throughput(cpus, warm_s, budget)
+    ref_physics = reference_physics_only()
     line = {
         "impl": "reference", "metric": "env steps/sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
         "config": {"workload": "%s 80x60 RGB+depth, random actions, auto-reset" % LEVEL, "n_envs": cores,
-                   "note": "reference Pyglet/GL path cannot run on this box (no pyglet/GL/gymnasium); "
-                           "CPU oracle port timed instead, one env process per host core"},
+                   "note": "reference Pyglet/GL path cannot run on this box (no pyglet/GL/gymnasium, no libEGL/libGL); "
+                           "CPU oracle port timed instead, one env process pinned to each PHYSICAL host core",
+                   "per_core": value / cores,
+                   "reference_python_physics_only": ref_physics},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d env-steps total in %.0f s on %d processes (one env each)" % (vals, budget, cores)},
+                         "sample": "%d env-steps total in %.0f s on %d pinned processes (one env each), %.0f per core" % (
+                             vals, budget, cores, value / cores)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -184,24 +269,32 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = None if args.no_numa else bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cfg = CONFIGS[args.config]
+    LEVEL, W, H = cfg["level"], cfg["w"], cfg["h"]
+    BYTES_RGB, BYTES_DEPTH = W * H * 3, (W * H * 4 if cfg["depth"] else 0)
+    env_kw = dict(obs_width=W, obs_height=H, want_depth=cfg["depth"], domain_rand=cfg["dr"])
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, args.warmup
-    N = args.envs
+    N = args.envs if args.envs else cfg["envs"]
+    if args.scaling == "strong":                 # fixed total work: `--envs` (default the config's) is the GLOBAL count
+        assert N % world == 0, "strong scaling needs envs divisible by the number of GPUs"
+        N //= world
     sharded, peer = None, False
     if world > 1:
         from miniworld_b200.dist import ShardedMiniWorld
-        sharded = ShardedMiniWorld(LEVEL, world * N, dist=dist, device=local, obs_width=W, obs_height=H, want_depth=True)
+        sharded = ShardedMiniWorld(LEVEL, world * N, dist=dist, device=local, **env_kw)
         env = sharded.local
         sharded.reset(1000)
         peer = (not args.nccl_gather) and sharded.enable_peer_obs()
     else:
-        env = BatchedMiniWorld(LEVEL, N, obs_width=W, obs_height=H, want_depth=True, device=local)
+        env = BatchedMiniWorld(LEVEL, N, device=local, **env_kw)
         env.reset(seed=1000)
     total = Wm + K
     gen = np.random.default_rng(12345 + rank)
@@ -217,7 +310,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def one_step(t):
-        if peer:                          # K2 writes into rank 0's HBM over NVLink; 4-byte all-reduce as the fence
+        if peer:                          # K2 writes into rank 0's HBM over NVLink; one-way completion flags, no collective
             return sharded.step_peer(acts[t])
         obs, rew, te, tr, info = env.step(acts[t])
         if world > 1:
@@ -254,8 +347,10 @@ def run_ours(args):
 
     # ---- end-to-end arm: host buffers in, host buffers out
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-    out = dict(obs=pin((N, H, W, 3), torch.uint8), depth=pin((N, H, W, 1), torch.float32),
+    out = dict(obs=pin((N, H, W, 3), torch.uint8), depth=pin((N, H, W, 1), torch.float32) if cfg["depth"] else None,
                reward=pin((N,), torch.float64), terminated=pin((N,), torch.uint8), truncated=pin((N,), torch.uint8))
+    if peer:                               # the end-to-end leg renders into this rank's own buffer again
+        env._bufs["obs"] = torch.zeros((N, H, W, 3), dtype=torch.uint8, device=dev)
     acts_pin = torch.as_tensor(acts_np).pin_memory().numpy()
     for t in range(min(Wm, 3)):
         env.step_host(acts_pin[t], out)
@@ -265,10 +360,16 @@ def run_ours(args):
         env.step_host(acts_pin[t], out)      # synchronous: returns when the host buffers are filled
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    d2h_bytes = N * (BYTES_RGB + BYTES_DEPTH + 8 + 1 + 1)
+    my_d2h_gbs = d2h_bytes * K / e2e_s / 1e9
+    rank_d2h = [my_d2h_gbs]
     if world > 1:
         tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
+        allr = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allr, torch.tensor([my_d2h_gbs], dtype=torch.float64, device=dev))
+        rank_d2h = [float(x.item()) for x in allr]
     e2e_value = world * N * K / e2e_s
     sampler.join(timeout=2)
 
@@ -278,30 +379,33 @@ def run_ours(args):
         k2_avg_ms = k2_ms / max(1, n2)
         achieved = bytes_per_launch / (k2_avg_ms * 1e-3) / 1e9 if n2 else None
         cpu = {"value": None, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": "skipped"}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == 3:
             from oracle import softgl
             softgl.build()
             v, n = cpu_port_throughput(1, 1.0, 12.0)
             cpu = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                    "sample": "%d env-steps of 1 env in 12 s (oracle/physics_port.py + oracle/softgl.c)" % n}
-        traffic, limiter = None, None
-        try:   # DRAM bytes of one K2 launch from the committed ncu --set full capture (profiles/)
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes of one K2 launch: from the committed `ncu --set full` capture of THIS build and config
             with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
                 tj = json.load(f)
-            if N == N_ENVS:
+            if N == tj.get("n_envs") and args.config == tj.get("config", 3):
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            limiter = tj.get("limiter")      # what ncu says actually bounds the kernel (issue slots, not DRAM)
+                traffic_src = tj.get("source")
         except Exception:
             pass
         line = {
             "metric": "env steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64+f32", "data": "synthetic",
-            "config": {"workload": "%s N_envs=%d per GPU, 80x60 RGB+depth, 8x MSAA, random actions, next-step "
-                                   "auto-reset on device" % (LEVEL, N),
-                       "global_envs": world * N, "obs_gather": ("none" if world == 1 else "K2 stores its tiles straight into rank 0's buffer (CUDA IPC peer memory "
-                                      "over NVLink) + one 4-byte all-reduce per step" if peer else
+            "config": {"workload": "BASELINE.json configs[%d]: %s N_envs=%d per GPU, %dx%d RGB%s, 8x MSAA%s, random actions, "
+                                   "next-step auto-reset on device" % (args.config, LEVEL, N, W, H, "+depth" if cfg["depth"] else "",
+                                                                       ", domain_rand" if cfg["dr"] else ""),
+                       "global_envs": world * N, "partition": "%d GPUs x %d envs (%s scaling)" % (world, N, args.scaling),
+                       "obs_gather": ("none" if world == 1 else "K2 stores its frames straight into rank 0's buffer (CUDA IPC peer memory "
+                                      "over NVLink), double-buffered, one-way stream-ordered completion flags (no per-step collective)" if peer else
                                       "NCCL gather of uint8 obs to rank 0"),
+                       "numa": "rank 0 bound to NUMA node %d (%d CPUs)" % numa if numa else "not bound",
                        "l2": "per-step outputs %.1f MB > 126 MB L2; no explicit flush" % (bytes_per_launch / 1e6),
                        "episodes_finished_in_timed_region": done_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -309,10 +413,13 @@ def run_ours(args):
                          "kernel": "render_kernel<8>", "kernel_avg_ms": k2_avg_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "k1_avg_ms": k1_ms / max(1, n1), "kernel_share_of_step": k2_ms / ms if ms else None,
-                         "limiter": limiter},
+                         "non_kernel_ms_per_step": (ms - k1_ms - k2_ms) / K if ms else None,
+                         "traffic_source": traffic_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
-                    "d2h_bytes_per_step": N * (BYTES_RGB + BYTES_DEPTH + 8 + 1 + 1), "ms_per_step": e2e_s * 1e3 / K},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3 / K,
+                    "scope": "per rank: every rank copies its own envs' outputs to its own pinned host buffers",
+                    "d2h_gbs_per_rank": rank_d2h},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
@@ -348,7 +455,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU (default 4096)")
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (weak) / in total (strong); default: the config's")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE.json configs[] index (default 3)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--nccl-gather", action="store_true", help="gather observations with NCCL instead of peer stores")
     args = ap.parse_args()

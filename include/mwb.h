@@ -378,6 +378,17 @@ int mwb_shared_alloc(int device, size_t bytes, void** dev_ptr, unsigned char han
 int mwb_shared_open(int device, const unsigned char handle[64], void** dev_ptr);
 int mwb_shared_close(void* dev_ptr, int opened /* 1: from mwb_shared_open, 0: from mwb_shared_alloc */);
 
+/* ---- one-way completion flags for the multi-GPU observation path --------------
+ * The reference has no counterpart (it has no multi-device path at all, README.md:34); these replace the per-step
+ * rendezvous a gather collective would impose.  mwb_flag_write enqueues, on `stream`, a 32-bit store of `value` to
+ * `dev_ptr` (device memory of this or -- through mwb_shared_open -- of another GPU) that becomes visible system-wide
+ * only after everything enqueued before it on the stream, including a kernel's peer stores.  mwb_flag_wait_geq makes
+ * `stream` wait until *dev_ptr - value >= 0 (wrap-around compare).  mwb_flag_mode: 0 = CUDA stream memory operations,
+ * 1 = one-thread kernels (MWB_FLAG_MODE=kernel, or a driver without stream memory operations). */
+int mwb_flag_write(void* cuda_stream, uint32_t* dev_ptr, uint32_t value);
+int mwb_flag_wait_geq(void* cuda_stream, const uint32_t* dev_ptr, uint32_t value);
+int mwb_flag_mode(void);
+
 /* sizeof() of every ABI struct, in declaration order (config, params, tex_desc, mesh_desc,
  * room, quad, seg, proto, entity, op, geometry, world, rng_state, state_view, maze_desc): lets a
  * binding verify its mirror of this header.  Returns the number of entries written. */

@@ -1135,6 +1135,91 @@ extern "C" int mwb_shared_close(void* dev_ptr, int opened) {
   return MWB_OK;
 }
 
+// ------------------------------------------------------------------ stream-ordered flags (one-way completion signals)
+// The multi-GPU observation path needs no rendezvous: after its K2, rank r writes the step number into a slot of
+// rank 0's peer-mapped buffer, stream-ordered behind the kernel's stores (system-scope release); rank 0's stream waits
+// until every slot has reached the step.  Implemented with CUDA stream memory operations (cuStreamWriteValue32 /
+// cuStreamWaitValue32, looked up at run time so that the library keeps linking against cudart only); if the driver
+// does not offer them -- or MWB_FLAG_MODE=kernel -- one-thread kernels do the same (st.release.sys / ld.acquire.sys).
+#ifndef MWB_HOSTSIM
+__global__ void flag_write_kernel(uint32_t* p, uint32_t v) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void flag_wait_kernel(const uint32_t* p, uint32_t v) {
+  uint32_t cur;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(p) : "memory");
+    if ((int32_t)(cur - v) < 0) __nanosleep(200);
+  } while ((int32_t)(cur - v) < 0);
+}
+typedef int (*mwb_memop_fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static mwb_memop_fn g_write32 = nullptr, g_wait32 = nullptr;
+static int g_flag_mode = -1;     // 0 = stream memory operations, 1 = kernels
+static void flag_init() {
+  if (g_flag_mode >= 0) return;
+  g_flag_mode = 1;
+  const char* m = getenv("MWB_FLAG_MODE");
+  if (m && strcmp(m, "kernel") == 0) return;
+  void *w = nullptr, *q = nullptr;
+  cudaDriverEntryPointQueryResult r1, r2;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &r1) == cudaSuccess && r1 == cudaDriverEntryPointSuccess &&
+      cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &r2) == cudaSuccess && r2 == cudaDriverEntryPointSuccess &&
+      w && q) {
+    g_write32 = (mwb_memop_fn)w;
+    g_wait32 = (mwb_memop_fn)q;
+    g_flag_mode = 0;
+  } else {
+    cudaGetLastError();
+  }
+}
+#endif
+
+extern "C" int mwb_flag_write(void* stream, uint32_t* dev_ptr, uint32_t value) {
+#ifndef MWB_HOSTSIM
+  if (!dev_ptr) return fail(MWB_EINVAL, "null argument");
+  flag_init();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g_flag_mode == 0) {
+    if (g_write32(s, (unsigned long long)(uintptr_t)dev_ptr, value, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT: with memory barrier */) != 0)
+      return fail(MWB_ECUDA, "cuStreamWriteValue32 failed");
+  } else {
+    flag_write_kernel<<<1, 1, 0, s>>>(dev_ptr, value);
+    CK(cudaGetLastError());
+  }
+  return MWB_OK;
+#else
+  return fail(MWB_ENOCUDA, "host simulator has no streams");
+#endif
+}
+
+extern "C" int mwb_flag_wait_geq(void* stream, const uint32_t* dev_ptr, uint32_t value) {
+#ifndef MWB_HOSTSIM
+  if (!dev_ptr) return fail(MWB_EINVAL, "null argument");
+  flag_init();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g_flag_mode == 0) {
+    if (g_wait32(s, (unsigned long long)(uintptr_t)dev_ptr, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+      return fail(MWB_ECUDA, "cuStreamWaitValue32 failed");
+  } else {
+    flag_wait_kernel<<<1, 1, 0, s>>>(dev_ptr, value);
+    CK(cudaGetLastError());
+  }
+  return MWB_OK;
+#else
+  return fail(MWB_ENOCUDA, "host simulator has no streams");
+#endif
+}
+
+extern "C" int mwb_flag_mode(void) {
+#ifndef MWB_HOSTSIM
+  flag_init();
+  return g_flag_mode;
+#else
+  return -1;
+#endif
+}
+
 // ------------------------------------------------------------------ profiling
 #ifndef MWB_HOSTSIM
 static void prof_mark(mwb_handle* h, std::vector<cudaEvent_t>& v, stream_t s) {

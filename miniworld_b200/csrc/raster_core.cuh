@@ -634,7 +634,7 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
   float e1 = t.A[1] * cx + t.B[1] * cy + t.C[1];
   float e2 = t.A[2] * cx + t.B[2] * cy + t.C[2];
 #ifdef __CUDA_ARCH__
-  const float inv = __frcp_rn(e0 + e1 + e2);
+  const float inv = __fdividef(1.0f, e0 + e1 + e2);     // colour path: MUFU.RCP accuracy is ample (<= 1 LSB contract)
 #else
   const float inv = 1.0f / (e0 + e1 + e2);
 #endif
@@ -652,7 +652,11 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
     const float dudx = (t.UA - u * t.SA) * inv * (float)T.w, dvdx = (t.VA - v * t.SA) * inv * (float)T.h;
     const float dudy = (t.UB - u * t.SB) * inv * (float)T.w, dvdy = (t.VB - v * t.SB) * inv * (float)T.h;
     float rho2 = fmaxf(dudx * dudx + dvdx * dvdx, dudy * dudy + dvdy * dvdy);
+#ifdef __CUDA_ARCH__
+    float lambda = 0.5f * __log2f(fmaxf(rho2, 1e-20f));    // MUFU.LG2: the trilinear weight moves by < 1e-6
+#else
     float lambda = 0.5f * log2f(fmaxf(rho2, 1e-20f));
+#endif
     // magnification: GL_LINEAR on level 0; else GL_LINEAR_MIPMAP_LINEAR between floor(lambda) and +1
     const float lmax = (float)(T.nlev - 1);
     const float lc = lambda <= 0.0f ? 0.0f : (lambda >= lmax ? lmax : lambda);

@@ -69,51 +69,100 @@ class ShardedMiniWorld:
         return None
 
     # ---- peer-memory observations: K2 of every rank stores straight into rank 0's buffer
+    def _exchange(self, obj):
+        """all-gather of small Python objects (set-up only; works on NCCL and gloo process groups)."""
+        if self.dist is None or self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
     def enable_peer_obs(self):
-        """Rank 0 allocates uint8 [total, H, W, 3] and shares it over CUDA IPC; the other ranks map
-        it and render into their slice of it (stores cross NVLink inside K2).  Returns True if
-        every rank succeeded; otherwise the NCCL-gather path stays in use."""
+        """Rank 0 allocates two uint8 [total, H, W, 3] observation buffers (+ one completion slot per rank) and shares
+        them over CUDA IPC; the other ranks map them and render into their slice (K2's stores cross NVLink / the
+        GPU's own memory system directly into rank 0's HBM).  Every rank also shares a 4-byte "released" slot that
+        rank 0 writes.  No collective is left in the step: see step_peer.  Returns True if every rank succeeded;
+        otherwise the gather path stays in use."""
         import torch
         from .engine import EngineError, SharedDeviceBuffer
         H, W = self.local.obs_height, self.local.obs_width
-        shape = (self.total, H, W, 3)
+        frame = H * W * 3
+        obs_bytes = self.total * frame
+        self._flag_off = (2 * obs_bytes + 255) & ~255          # completion slots: one 128-byte line per rank
+        nbytes = self._flag_off + 128 * self.world
         dev = self.local.device
-        ok, self._peer = 1, None
-        payload = [None]
+        ok, self._peer, self._rel, self._rel_peers = 1, None, None, []
+        handle = None
         try:
+            self._rel = SharedDeviceBuffer(dev, (128,))             # this rank's "released" slot (written by rank 0)
             if self.rank == 0:
-                self._peer = SharedDeviceBuffer(dev, shape)
-                payload = [self._peer.handle]
+                self._peer = SharedDeviceBuffer(dev, (nbytes,))
+                handle = self._peer.handle
         except EngineError:
             ok = 0
-        if self.dist is not None and self.world > 1:
-            self.dist.broadcast_object_list(payload, src=0)
-            if self.rank != 0 and payload[0] is not None:
-                try:
-                    self._peer = SharedDeviceBuffer(dev, shape, handle=payload[0])
-                except EngineError:
-                    ok = 0
-            flag = torch.tensor([ok if payload[0] is not None else 0], device=torch.device("cuda", dev))
-            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
-            ok = int(flag.item())
+        infos = self._exchange((ok, handle, self._rel.handle if self._rel is not None else None))
+        ok = min(i[0] for i in infos)
+        if ok and self.rank != 0:
+            try:
+                self._peer = SharedDeviceBuffer(dev, (nbytes,), handle=infos[0][1])
+            except EngineError:
+                ok = 0
+        if ok and self.rank == 0:
+            try:
+                self._rel_peers = [self._rel] + [SharedDeviceBuffer(dev, (128,), handle=infos[r][2]) for r in range(1, self.world)]
+            except EngineError:
+                ok = 0
+        ok = min(self._exchange(ok))
         if not ok:
-            if self._peer is not None:
-                self._peer.close()
+            for b in [self._peer, self._rel] + self._rel_peers[1:]:
+                if b is not None:
+                    b.close()
             self._peer = None
             return False
-        self.obs_all = self._peer.tensor()                         # [total, H, W, 3] in rank 0's HBM
-        self.local._bufs_ready = self.local._ensure_torch()
-        self.local._bufs["obs"] = self.obs_all[self.start:self.start + self.count]   # this rank's slice
-        self._sync = torch.zeros(1, device=torch.device("cuda", dev))
+        flat = self._peer.tensor()
+        flat[self._flag_off:].zero_() if self.rank == 0 else None
+        self._rel.tensor().zero_()
+        torch.cuda.synchronize(dev)
+        self._exchange(0)                                           # slots are zero before anybody signals
+        self.obs_bufs = [flat[k * obs_bytes:(k + 1) * obs_bytes].view(self.total, H, W, 3) for k in range(2)]
+        self.obs_all = self.obs_bufs[0]                             # [total, H, W, 3] in rank 0's HBM
+        self.local._ensure_torch()
+        self._peer_step = 0
+        base = self._peer.ptr.value + self._flag_off
+        self._done_ptr = [base + 128 * r for r in range(self.world)]      # slot r lives in rank 0's memory
+        self._lib = self._peer.lib
         return True
 
     def step_peer(self, local_actions):
-        """K1 + K2 with observations written into rank 0's buffer; one tiny stream-ordered
-        all-reduce tells rank 0 that every slice is complete.  Returns obs_all on rank 0."""
-        obs, rew, te, tr, info = self.local.step(local_actions)
-        if self.dist is not None and self.world > 1:
-            self.dist.all_reduce(self._sync)
-        return self.obs_all if self.rank == 0 else None
+        """K1 + K2 with the observations of step t written into buffer t % 2 in rank 0's HBM.  No rendezvous:
+          * rank r != 0: [wait until rank 0 released buffer t % 2, i.e. its own slot >= t - 1] -> K1, K2 ->
+            stream-ordered store of t into slot r of rank 0's buffer (visible after K2's peer stores);
+          * rank 0: stream-ordered store of t - 1 into every rank's "released" slot (everything enqueued on the
+            stream so far -- the consumer of step t - 1's observations -- precedes it) -> K1, K2 -> wait until
+            every slot >= t.
+        A rank other than 0 only ever waits if it is more than one step ahead of rank 0.  Returns the complete
+        [total, H, W, 3] observations on rank 0 (valid until the call after next), None elsewhere."""
+        from .batched import _torch_stream
+        torch = self.local._torch
+        t = self._peer_step = self._peer_step + 1
+        buf = self.obs_bufs[t % 2]
+        self.local._bufs["obs"] = buf[self.start:self.start + self.count]
+        stream = _torch_stream(torch, self.local.device)
+        lib, check = self._lib, self.local.engine._check
+        if self.rank == 0:
+            if t > 1:
+                for r in range(1, self.world):
+                    check(lib.mwb_flag_write(stream, self._rel_peers[r].ptr, t - 1))
+        elif t > 2:
+            check(lib.mwb_flag_wait_geq(stream, self._rel.ptr, t - 2))     # buffer t % 2 was last used by step t - 2
+        self.local.step(local_actions)
+        if self.rank == 0:
+            for r in range(1, self.world):
+                check(lib.mwb_flag_wait_geq(stream, self._done_ptr[r], t))
+            self.obs_all = buf
+            return buf
+        check(lib.mwb_flag_write(stream, self._done_ptr[self.rank], t))
+        return None
 
     def step(self, local_actions):
         """Local K1 + K2, then the gather of obs / reward / flags to rank 0."""
@@ -123,5 +172,11 @@ class ShardedMiniWorld:
 
     def close(self):
         if getattr(self, "_peer", None) is not None:
-            self._peer.close()
+            import torch
+            torch.cuda.synchronize(self.local.device)
+            self._exchange(0)                       # nobody unmaps while a peer may still be storing / polling
+            for b in [self._peer, self._rel] + list(self._rel_peers[1:]):
+                if b is not None:
+                    b.close()
+            self._peer = None
         self.local.close()

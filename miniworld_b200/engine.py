@@ -121,6 +121,7 @@ EXPORTS = (
     "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
     "mwb_render_top_view", "mwb_visible_ents", "mwb_set_action_noise",
     "mwb_snapshot_size", "mwb_snapshot", "mwb_restore", "mwb_set_obs_format",
+    "mwb_flag_write", "mwb_flag_wait_geq", "mwb_flag_mode",
 )
 OBS_FORMATS = {"hwc": 0, "cwh": 1, "grey": 2}
 
@@ -167,6 +168,9 @@ def load_library(lib_path=None):
     lib.mwb_shared_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.mwb_shared_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
     lib.mwb_shared_close.argtypes = [vp, C.c_int]
+    lib.mwb_flag_write.argtypes = [vp, vp, C.c_uint32]
+    lib.mwb_flag_wait_geq.argtypes = [vp, vp, C.c_uint32]
+    lib.mwb_flag_mode.argtypes = []
     lib.mwb_overflow_count.argtypes = [vp]
     lib.mwb_overflow_count.restype = C.c_int64
     lib.mwb_profile.argtypes = [vp, C.c_int]

@@ -156,6 +156,8 @@ class RecGL:
 
     # ------------------------------------------------------------------ display lists
     def record_or_run(self, name, fn, args):
+        if not self.active and name in _DRAW_ONLY:
+            return None
         if self.compiling is not None and name not in _IMMEDIATE:
             self.compiling.append((fn, args))
             return None
@@ -171,6 +173,8 @@ class RecGL:
         self.compiling = None
 
     def glCallList(self, lst):
+        if not self.active:
+            return
         for fn, args in self.lists.get(_val(lst), []):
             fn(*args)
 
@@ -519,6 +523,8 @@ class RecGL:
         return self._ts
 
 
+_DRAW_ONLY = {"glBegin", "glEnd", "glVertex3f", "glNormal3f", "glTexCoord2f", "glColor3f", "glPushMatrix", "glPopMatrix",
+              "glTranslatef", "glRotatef", "glScalef", "vlist.draw"}     # (state that outlives a frame -- binds, enables, light -- is always tracked)
 _IMMEDIATE = {"glNewList", "glEndList", "glGenTextures", "glGenFramebuffers", "glGenRenderbuffers", "glGenQueries",
               "glGetIntegerv", "glCheckFramebufferStatus", "glReadPixels", "glGetQueryObjectuiv", "glDeleteLists",
               "glDeleteQueries", "glTexImage2D", "glTexImage2DMultisample", "glFramebufferTexture2D"}

@@ -1,5 +1,7 @@
-"""Two GPUs: the peer-memory observation path (K2 stores into rank 0's buffer over NVLink)
-returns exactly what the NCCL gather and a single-process run return.  Skipped with < 2 GPUs."""
+"""The peer-memory observation path (K2 of every rank stores into rank 0's buffer; one-way stream-ordered
+completion flags instead of a per-step collective) returns exactly what the NCCL gather and a single-process run
+return.  Two variants: two ranks on two GPUs over NVLink (skipped with < 2 GPUs), and two ranks sharing ONE GPU
+(CUDA IPC between processes, gloo for the set-up exchange) so that the path is exercised on any box."""
 import os
 import sys
 
@@ -70,4 +72,60 @@ def test_peer_observation_buffer_equals_gather(libmwb_path, total, steps):
     for t in range(steps):
         obs = env.step(torch.as_tensor(acts_all[t], device="cuda"))[0]
         assert np.array_equal(obs.cpu().numpy(), res["peer"][1][t])
+    env.close()
+
+
+def _worker_one_gpu(rank, world, port, total, steps, q, flag_mode):
+    """Two processes on cuda:0: the peer buffer crosses a process boundary (CUDA IPC), not a GPU boundary."""
+    sys.path.insert(0, ROOT)
+    os.environ["MWB_FLAG_MODE"] = flag_mode
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from miniworld_b200.dist import ShardedMiniWorld
+    acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)
+    env = ShardedMiniWorld("MiniWorld-FourRooms-v0", total, dist=dist, device=0)
+    env.reset(1000)
+    ok = env.enable_peer_obs()
+    frames = []
+    if ok:
+        for t in range(steps):              # no synchronisation between the ranks inside the loop: the flags order it
+            obs = env.step_peer(torch.as_tensor(acts_all[t, env.start:env.start + env.count], device="cuda"))
+            if rank == 0:
+                frames.append(obs.clone())  # stream-ordered after the completion waits
+        torch.cuda.synchronize()
+    mode = env._lib.mwb_flag_mode() if ok else -1
+    env.close()
+    if rank == 0:
+        q.put((ok, mode, np.stack([f.cpu().numpy() for f in frames]) if ok else None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("flag_mode", ["memop", "kernel"])
+@pytest.mark.parametrize("total,steps", [(64, 6), (2048, 4)])
+def test_peer_observation_buffer_two_processes_one_gpu(libmwb_path, total, steps, flag_mode):
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_one_gpu, args=(r, 2, port, total, steps, q, flag_mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, mode, frames = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok, "CUDA IPC peer buffer could not be established"
+    assert mode == (1 if flag_mode == "kernel" else mode)      # "memop" may fall back to kernels on an old driver
+    from miniworld_b200.batched import BatchedMiniWorld
+    env = BatchedMiniWorld("MiniWorld-FourRooms-v0", total)
+    env.reset(seed=1000)
+    acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)
+    for t in range(steps):
+        obs = env.step(torch.as_tensor(acts_all[t], device="cuda"))[0]
+        assert np.array_equal(obs.cpu().numpy(), frames[t]), "step %d" % t
     env.close()

@@ -183,3 +183,69 @@ def test_fused_observation_layouts_gpu(libmwb_path, level):
     reference wrappers' outputs on the HWC frames (host destinations: also covers the chunked D2H path)."""
     from helpers import obs_format_parity
     obs_format_parity(libmwb_path, n=300, steps=4, level=level)
+
+
+def test_step_is_ordered_after_asynchronous_action_producer(libmwb_path):
+    """The zero-copy RL loop: actions come out of torch kernels still in flight on the current stream when
+    step() is called, observations are consumed by torch kernels enqueued right after.  K1 / K2 must be ordered
+    behind the producer and before the consumer (torch's default stream is passed as cudaStreamLegacy)."""
+    import torch
+    from miniworld_b200.batched import BatchedMiniWorld
+    N, T = 512, 12
+    dev = torch.device("cuda", 0)
+    acts_np = np.random.default_rng(3).integers(0, 3, size=(T, N), dtype=np.int32)
+    big = torch.randn(6144, 6144, device=dev)
+
+    def rollout(async_producer, stream=None):
+        env = BatchedMiniWorld("MiniWorld-FourRooms-v0", N)
+        env.reset(seed=1000)
+        sums, rews = [], []
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            src = torch.as_tensor(acts_np, device=dev)
+            torch.cuda.current_stream().synchronize()
+            for t in range(T):
+                if async_producer:
+                    slow = (big @ big)[0, 0] * 0.0                  # milliseconds of work the actions depend on
+                    acts = (src[t].float() + slow).to(torch.int32)   # ready only when the matmul has finished
+                else:
+                    acts = src[t].clone()
+                    torch.cuda.current_stream().synchronize()
+                obs, rew, te, tr, _ = env.step(acts)
+                sums.append(obs.sum(dtype=torch.int64))              # consumer enqueued right behind the step
+                rews.append(rew.clone())
+            torch.cuda.current_stream().synchronize()
+        st = env.get_state()
+        env.close()
+        return torch.stack(sums).cpu().numpy(), torch.stack(rews).cpu().numpy(), st["agent_pos"], st["agent_dir"]
+
+    want = rollout(False)
+    for stream in (None, torch.cuda.Stream(device=dev)):
+        got = rollout(True, stream)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+
+
+def test_snapshot_after_asynchronous_step_sees_the_step(libmwb_path):
+    """snapshot() / get_state() run on the handle's own stream: they must wait for a step still in flight on a
+    torch side stream (stream_enter / stream_leave in csrc/mwb.cu)."""
+    import torch
+    from miniworld_b200.batched import BatchedMiniWorld
+    N = 2048
+    dev = torch.device("cuda", 0)
+    env = BatchedMiniWorld("MiniWorld-FourRooms-v0", N)
+    env.reset(seed=1000)
+    ref = BatchedMiniWorld("MiniWorld-FourRooms-v0", N)
+    ref.reset(seed=1000)
+    acts = torch.full((N,), 2, dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        with torch.cuda.stream(side):
+            env.step(acts)
+        blob = env.snapshot()                                       # no synchronize in between
+        ref.step(acts)
+        torch.cuda.synchronize()
+        assert np.array_equal(blob, ref.snapshot())
+    env.close()
+    ref.close()

@@ -46,7 +46,7 @@ marks = {
     rk: sorted([(1, "A prologue/TMA"), (find(rk, "B. room + box"), "B compaction"),
                 (find(rk, "visiting order of the block-resident"), "B sort"), (find(rk, "candidate lists: one THREAD"), "B2 tile lists"), (find(rk, "C/D. one warp"), "C0 tile loop/tri test"),
                 (find(rk, "auto flush"), "C2 flush (sample-parallel exact)"),
-                (find(rk, "sources of candidate triangles"), "C0 tile loop/tri test"), (find(rk, "phase 2: queue"), "C2 enqueue"),
+                (find(rk, "auto enqueue"), "C2 enqueue"), (find(rk, "hot path: this half-tile"), "C0 listed path"), (find(rk, "generic path: the mesh lists"), "C0 generic path"),
                 (find(rk, "Lazy pixels join"), "D resolve/store")]),
 }
 
