@@ -44,6 +44,8 @@ struct MeshDev {
 
 struct RenderAssets {
   const TexDev* tex;
+  const unsigned long long* tex_obj;   // [num_tex][MWB_MAX_LEVELS] CUDA texture objects, one per mip level (point sampled,
+                                 //   REPEAT, unorm8 -> float): K2 reads the 2x2 bilinear footprint with tld4; or null
   const uint32_t* texels;        // RGBA8 pool, row 0 = bottom of the image
   int32_t num_tex;
   const MeshDev* meshes;
@@ -609,10 +611,30 @@ MWB_DEV float texel_f(uint32_t t, int k) {
 
 MWB_DEV void bilinear(const RenderAssets& A, const TexDev& T, int level, float u, float v, float out[3]) {
   const int w = T.lw[level], h = T.lh[level];
-  const uint32_t* base = A.texels + T.off[level];
   const float x = (u - floorf(u)) * (float)w - 0.5f, y = (v - floorf(v)) * (float)h - 0.5f;   // in [-0.5, size - 0.5)
   const float xf = floorf(x), yf = floorf(y);
   const float fx = x - xf, fy = y - yf;
+#ifdef __CUDA_ARCH__
+  if (A.tex_obj != nullptr) {
+    // The texture unit fetches the footprint: tld4 (texture gather) at the texel CORNER shared by the four texels
+    // (xf, yf) .. (xf + 1, yf + 1) -- half a texel away from every footprint boundary, so the unit's own fixed-point
+    // coordinate arithmetic cannot pick another 2x2 block -- returns one channel of the four texels per instruction,
+    // already converted to float (exactly c / 255), with GL_REPEAT applied by the addressing hardware.  The weights
+    // fx, fy stay in float32 as above: only addressing, wrapping and unpacking moved to the TMU.
+    const cudaTextureObject_t obj = (cudaTextureObject_t)A.tex_obj[(size_t)(&T - A.tex) * MWB_MAX_LEVELS + level];
+    const float gu = (xf + 1.0f) / (float)w, gv = (yf + 1.0f) / (float)h;
+    const float4 c0 = tex2Dgather<float4>(obj, gu, gv, 0), c1 = tex2Dgather<float4>(obj, gu, gv, 1), c2 = tex2Dgather<float4>(obj, gu, gv, 2);
+    // gather order: x = (x0, y1), y = (x1, y1), z = (x1, y0), w = (x0, y0)
+    float top = c0.w + fx * (c0.z - c0.w), bot = c0.x + fx * (c0.y - c0.x);
+    out[0] = top + fy * (bot - top);
+    top = c1.w + fx * (c1.z - c1.w); bot = c1.x + fx * (c1.y - c1.x);
+    out[1] = top + fy * (bot - top);
+    top = c2.w + fx * (c2.z - c2.w); bot = c2.x + fx * (c2.y - c2.x);
+    out[2] = top + fy * (bot - top);
+    return;
+  }
+#endif
+  const uint32_t* base = A.texels + T.off[level];
   int x0 = (int)xf, y0 = (int)yf;
   x0 = x0 < 0 ? x0 + w : (x0 >= w ? x0 - w : x0);
   y0 = y0 < 0 ? y0 + h : (y0 >= h ? y0 - h : y0);
