@@ -378,6 +378,19 @@ int mwb_shared_alloc(int device, size_t bytes, void** dev_ptr, unsigned char han
 int mwb_shared_open(int device, const unsigned char handle[64], void** dev_ptr);
 int mwb_shared_close(void* dev_ptr, int opened /* 1: from mwb_shared_open, 0: from mwb_shared_alloc */);
 
+/* Device address of a per-env state array (valid for the handle's lifetime; contents are stream-ordered behind
+ * mwb_step / mwb_reset on the stream they were given).  Lets the host side expose what the reference's level step()s
+ * put into `info` without a state copy: info["health"] (envs/collecthealth.py:100) = MWB_ARRAY_COUNTER, the same
+ * counter PickupObjects keeps as num_picked_up (envs/pickupobjects.py:88); info["goal_pos"] (envs/tmaze.py:89) = rows
+ * of MWB_ARRAY_ENT_X/Y/Z ([max_ents][num_envs], entity-list slot major). */
+#define MWB_ARRAY_COUNTER 0      /* int32   [num_envs]            */
+#define MWB_ARRAY_STEP_COUNT 1   /* int32   [num_envs]            */
+#define MWB_ARRAY_ENT_X 2        /* float64 [max_ents][num_envs]  */
+#define MWB_ARRAY_ENT_Y 3
+#define MWB_ARRAY_ENT_Z 4
+#define MWB_ARRAY_ENT_DIR 5
+int mwb_state_array(mwb_handle* h, int which, void** dev_ptr, int64_t* count);
+
 /* ---- one-way completion flags for the multi-GPU observation path --------------
  * The reference has no counterpart (it has no multi-device path at all, README.md:34); these replace the per-step
  * rendezvous a gather collective would impose.  mwb_flag_write enqueues, on `stream`, a 32-bit store of `value` to

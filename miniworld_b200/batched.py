@@ -42,7 +42,7 @@ def _torch_stream(torch, device):
 
 class BatchedMiniWorld:
     def __init__(self, level, num_envs, obs_width=80, obs_height=60, domain_rand=False, autoreset=True,
-                 msaa_samples=8, device=0, lib_path=None, want_depth=False, level_kwargs=None, obs_format="hwc"):
+                 msaa_samples=8, device=0, want_depth=False, level_kwargs=None, obs_format="hwc"):
         self.level_cls = _resolve_level(level)
         self.level_kwargs = dict(level_kwargs or {})
         self.num_envs = int(num_envs)
@@ -99,7 +99,7 @@ class BatchedMiniWorld:
                              max_segs=caps[2], max_ents=max_ents, rule=rule, domain_rand=self.domain_rand,
                              max_episode_steps=int(min(self.max_episode_steps, 2 ** 31 - 1)),   # math.inf: never truncates
                              autoreset=autoreset and self.device_reset,
-                             device=device, lib_path=lib_path)
+                             device=device)
         self.autoreset = bool(autoreset)
         eng = self.engine
         eng.sync_assets()
@@ -146,7 +146,27 @@ class BatchedMiniWorld:
             self._bufs["term_view"] = self._bufs["terminated"].view(torch.bool)
             self._bufs["trunc_view"] = self._bufs["truncated"].view(torch.bool)
             self._info = {"depth": self._bufs["depth"]} if self.want_depth else {}
+            # what the level's step() puts into `info` / the observation, read in place from the device state
+            eng = self.engine
+            self._info_views = {}
+            for key, spec in (getattr(self.proto_env, "device_info", None) or {}).items():
+                if spec[0] == "counter":                   # CollectHealth: info["health"] (collecthealth.py:100)
+                    self._info[key] = torch.as_tensor(eng.state_array("counter"), device=dev)
+                elif spec[0] == "entity_pos":              # TMaze: info["goal_pos"] = self.box.pos (tmaze.py:89)
+                    self._info_views[key] = (int(spec[1]), [torch.as_tensor(eng.state_array(n), device=dev)
+                                                            for n in ("ent_x", "ent_y", "ent_z")])
+            self._obs_dict = dict(getattr(self.proto_env, "device_obs_extra", None) or {})
         return self._torch
+
+    def _wrap(self, obs):
+        """Observation / info as the level's own step() shapes them (Sign: {"obs", "goal"}, sign.py:176)."""
+        torch = self._torch
+        for key, (slot, xyz) in self._info_views.items():
+            self._info[key] = torch.stack([a[slot] for a in xyz], dim=1)          # float64 [N, 3]
+        if self._obs_dict:
+            obs = dict({k: torch.full((self.num_envs,), int(v), dtype=torch.int64, device=obs.device)
+                        for k, v in self._obs_dict.items()}, obs=obs)
+        return obs
 
     # ------------------------------------------------------------------ reset
     def reset(self, seed=None, env_ids=None):
@@ -168,7 +188,7 @@ class BatchedMiniWorld:
         else:
             self._host_reset(ids, seeds)
         self._seeded = True
-        return self.render(), {}
+        return self._wrap(self.render()), {}
 
     def _host_reset(self, ids, seeds, hold=False):
         """Host-side reset of the listed envs (levels without a device program).  The env's numpy
@@ -218,7 +238,7 @@ class BatchedMiniWorld:
                          terminated=b["terminated"], truncated=b["truncated"], stream=stream)
         if not self.device_reset and self.autoreset:
             self._host_done = (b["terminated"] | b["truncated"]).bool().cpu().numpy()
-        return b["obs"], b["reward"], b["term_view"], b["trunc_view"], self._info
+        return self._wrap(b["obs"]), b["reward"], b["term_view"], b["trunc_view"], self._info
 
     def step_host(self, actions, out=None, render=True):
         """Same step with HOST buffers end to end (numpy in, numpy out): actions are copied

@@ -1662,6 +1662,24 @@ extern "C" int mwb_restore(mwb_handle* h, const void* blob, size_t bytes) {
 }
 
 // ------------------------------------------------------------------ ABI: state exchange
+// Device address of one of the handle's per-env state arrays, so that a caller can read it in place (stream-ordered
+// after mwb_step) instead of copying the whole state: what the levels' step() put into `info` --
+// info["health"] (collecthealth.py:100) is the per-env counter, info["goal_pos"] (tmaze.py:89) three entity-pose rows.
+extern "C" int mwb_state_array(mwb_handle* h, int which, void** dev_ptr, int64_t* count) {
+  if (!h || !dev_ptr || !count) return fail(MWB_EINVAL, "null argument");
+  const int64_t N = h->S.N, E = h->S.E;
+  switch (which) {
+    case MWB_ARRAY_COUNTER: *dev_ptr = h->S.num_picked; *count = N; break;       // int32 [N]
+    case MWB_ARRAY_STEP_COUNT: *dev_ptr = h->S.step_count; *count = N; break;    // int32 [N]
+    case MWB_ARRAY_ENT_X: *dev_ptr = h->S.ent_px; *count = E * N; break;         // float64 [E][N]
+    case MWB_ARRAY_ENT_Y: *dev_ptr = h->S.ent_py; *count = E * N; break;
+    case MWB_ARRAY_ENT_Z: *dev_ptr = h->S.ent_pz; *count = E * N; break;
+    case MWB_ARRAY_ENT_DIR: *dev_ptr = h->S.ent_dir; *count = E * N; break;
+    default: return fail(MWB_EINVAL, "unknown array");
+  }
+  return MWB_OK;
+}
+
 extern "C" int mwb_get_state(mwb_handle* h, const mwb_state_view* out) {
   if (!h || !out) return fail(MWB_EINVAL, "null argument");
   const int N = h->S.N;

@@ -10,7 +10,7 @@
 //   MiniWorldEnv.near / _reward     :965-975, :1012-1017
 //   level rules                     envs/hallway.py:67-74 (goal), envs/pickupobjects.py:83-95
 // Outputs are bit-identical to the reference on this image (numpy 2.3.5, glibc 2.39):
-// tests/test_physics_gpu.py compares against trajectories dumped from the reference itself.
+// tests/test_gpu_physics.py compares against trajectories dumped from the reference itself.
 #pragma once
 #include "libm_sincos.cuh"
 #include "state.h"

@@ -1,9 +1,9 @@
 """ctypes binding of libmwb.so (include/mwb.h) -- the only way into the CUDA kernels.
 
 There is no fallback: if the shared library is missing, or CUDA is unavailable when a
-handle is created, construction raises.  `lib_path` exists so tests can point the binding
-at an explicitly built library; the package itself only ever loads `libmwb.so` from its
-own directory.
+handle is created, construction raises.  The package only ever loads `libmwb.so` from its
+own directory and no product class takes a library argument (tests reach the g++ build of
+the kernels' inner functions through the private `_override_library_for_tests` seam).
 """
 import ctypes as C
 import os
@@ -121,16 +121,27 @@ EXPORTS = (
     "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
     "mwb_render_top_view", "mwb_visible_ents", "mwb_set_action_noise",
     "mwb_snapshot_size", "mwb_snapshot", "mwb_restore", "mwb_set_obs_format",
-    "mwb_flag_write", "mwb_flag_wait_geq", "mwb_flag_mode",
+    "mwb_flag_write", "mwb_flag_wait_geq", "mwb_flag_mode", "mwb_state_array",
 )
 OBS_FORMATS = {"hwc": 0, "cwh": 1, "grey": 2}
 
 _libs = {}
 
 
-def load_library(lib_path=None):
-    """dlopen libmwb.so, declare prototypes, verify the struct mirrors.  No compute happens."""
-    path = os.path.abspath(lib_path or DEFAULT_LIB)
+_test_library = None
+
+
+def _override_library_for_tests(path):
+    """TEST SEAM, not product API: tests/ point the binding at the g++ build of the kernels' inner functions
+    (tests/hostsim) to debug kernel logic on a GPU-less box.  No product class takes a library argument; the
+    override only works inside a pytest / tools process that imports this private name on purpose."""
+    global _test_library
+    _test_library = os.path.abspath(path) if path else None
+
+
+def load_library():
+    """dlopen the in-tree libmwb.so, declare prototypes, verify the struct mirrors.  No compute happens."""
+    path = _test_library or os.path.abspath(DEFAULT_LIB)
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):
@@ -171,6 +182,7 @@ def load_library(lib_path=None):
     lib.mwb_flag_write.argtypes = [vp, vp, C.c_uint32]
     lib.mwb_flag_wait_geq.argtypes = [vp, vp, C.c_uint32]
     lib.mwb_flag_mode.argtypes = []
+    lib.mwb_state_array.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
     lib.mwb_overflow_count.argtypes = [vp]
     lib.mwb_overflow_count.restype = C.c_int64
     lib.mwb_profile.argtypes = [vp, C.c_int]
@@ -192,8 +204,8 @@ class SharedDeviceBuffer:
     """Device memory that other processes on the box can map (CUDA IPC), exposed to torch
     through __cuda_array_interface__ (zero copy)."""
 
-    def __init__(self, device, shape, handle=None, lib_path=None):
-        self.lib = load_library(lib_path)
+    def __init__(self, device, shape, handle=None):
+        self.lib = load_library()
         self.shape = tuple(int(v) for v in shape)
         self.nbytes = int(np.prod(self.shape))
         self.device = int(device)
@@ -289,8 +301,8 @@ class Engine:
 
     def __init__(self, num_envs, obs_width=80, obs_height=60, msaa_samples=8, shared_geometry=True,
                  max_rooms=8, max_quads=64, max_segs=64, max_ents=8, rule=(RULE_NONE, 0), domain_rand=False,
-                 max_episode_steps=1500, autoreset=False, device=0, lib_path=None):
-        self.lib = load_library(lib_path)
+                 max_episode_steps=1500, autoreset=False, device=0):
+        self.lib = load_library()
         cfg = Config(ABI_VERSION, int(device), int(num_envs), int(obs_width), int(obs_height), int(msaa_samples),
                      int(bool(shared_geometry)), int(max_rooms), int(max_quads), int(max_segs), int(max_ents),
                      int(rule[0]), int(rule[1]), int(bool(domain_rand)), int(max_episode_steps), int(bool(autoreset)))
@@ -477,6 +489,21 @@ class Engine:
         """uint32[N] (numpy or CUDA tensor): bit e = entity slot e passes the reference's occlusion query."""
         self._check(self.lib.mwb_visible_ents(self.h, _dev_or_host_ptr(mask), stream))
 
+    ARRAYS = {"counter": (0, "<i4"), "step_count": (1, "<i4"), "ent_x": (2, "<f8"), "ent_y": (3, "<f8"),
+              "ent_z": (4, "<f8"), "ent_dir": (5, "<f8")}
+
+    def state_array(self, name):
+        """Zero-copy view of a per-env device state array (mwb_state_array) as an object with
+        __cuda_array_interface__: "counter" / "step_count" int32 [N]; "ent_x|y|z|dir" float64 [max_ents, N]."""
+        which, typestr = self.ARRAYS[name]
+        ptr, count = C.c_void_p(), C.c_int64()
+        self._check(self.lib.mwb_state_array(self.h, which, C.byref(ptr), C.byref(count)))
+        shape = (self.N,) if count.value == self.N else (count.value // self.N, self.N)
+
+        class _View:
+            __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr.value, False), "version": 3, "strides": None}
+        return _View()
+
     def launch_count(self):
         return int(self.lib.mwb_launch_count(self.h))
 
@@ -512,9 +539,8 @@ class SingleEnvEngine:
     """N = 1 engine behind `world.MiniWorldEnv`: the env's Python objects stay authoritative;
     before each GPU call the (possibly user-modified) state is pushed, afterwards pulled."""
 
-    def __init__(self, obs_width, obs_height, msaa_samples, device, lib_path=None):
+    def __init__(self, obs_width, obs_height, msaa_samples, device):
         self.args = (obs_width, obs_height, msaa_samples)
-        self.lib_path = lib_path
         self.device = 0 if device in ("cuda", None) else int(str(device).split(":")[-1])
         self.engine = None
         self.caps = None
@@ -540,7 +566,7 @@ class SingleEnvEngine:
             self.engine = Engine(1, W, H, msaa, shared_geometry=False, max_rooms=caps[0], max_quads=caps[1],
                                  max_segs=caps[2], max_ents=min(caps[3], MAX_ENTS_CAP), rule=(RULE_NONE, 0),
                                  domain_rand=False, max_episode_steps=max_steps, autoreset=False,
-                                 device=self.device, lib_path=self.lib_path)
+                                 device=self.device)
             self.caps = caps
             self.engine.set_params(env.params)
         self.engine.sync_assets()

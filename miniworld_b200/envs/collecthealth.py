@@ -20,6 +20,7 @@ class CollectHealth(MiniWorldEnv, utils.EzPickle):
         self.health = 100
 
     device_rule = ("health", 0)
+    device_info = {"health": ("counter",)}             # info["health"] = self.health (kept by the rule on the device)
 
     def device_program(self, prog):
         kit = prog.proto(MeshEnt(mesh_name="medkit", height=0.40, static=False))

@@ -54,6 +54,10 @@ class Sign(MiniWorldEnv, utils.EzPickle):
     def device_rule(self):
         return ("sign", self._color_index | (self._goal << 8))
 
+    @property
+    def device_obs_extra(self):
+        return {"goal": self._goal}                    # the dict observation's constant entry (sign.py:176)
+
     def device_program(self, prog):
         s, gap = self._size, 0.25
         spots = [(Box(color="blue"), 1, 1), (Box(color="red"), 9, 1), (Box(color="green"), 9, 5),

@@ -30,6 +30,7 @@ class TMaze(MiniWorldEnv, utils.EzPickle):
         self.place_agent(dir=heading, room=stem)
 
     device_rule = ("goal", 0)
+    device_info = {"goal_pos": ("entity_pos", 0)}      # info["goal_pos"] = self.box.pos: the box is entity 0
 
     def device_program(self, prog):
         stem, bar = self.rooms[0], self.rooms[1]

@@ -4,7 +4,7 @@ A level's `device_program(prog)` re-states its `_gen_world()` placement calls ag
 builder; the result is the short CHOICE / UNIFORM / PLACE program csrc/reset.cuh interprets
 per environment on the GPU, drawing from that env's numpy-exact PCG64 stream in the same
 order as the Python `_gen_world()` does (reference miniworld.py:839-909).
-`tests/test_reset_program.py` checks every level's program against its `_gen_world()`.
+`tests/test_hostsim_kernels.py` (CPU) and `tests/test_gpu_physics.py` (B200) check every level's program against its `_gen_world()`.
 """
 import math
 

@@ -181,7 +181,7 @@ class MiniWorldEnv(gym.Env):
 
     def __init__(self, max_episode_steps=1500, obs_width=80, obs_height=60, window_width=800,
                  window_height=600, params=DEFAULT_PARAMS, domain_rand=False, render_mode=None,
-                 view="agent", device="cuda", msaa_samples=8, engine_lib=None):
+                 view="agent", device="cuda", msaa_samples=8):
         self.actions = MiniWorldEnv.Actions
         self.action_space = spaces.Discrete(len(self.actions))
         self.observation_space = spaces.Box(low=0, high=255, shape=(obs_height, obs_width, 3), dtype=np.uint8)
@@ -196,7 +196,6 @@ class MiniWorldEnv(gym.Env):
         self.window_width, self.window_height = window_width, window_height
         self.msaa_samples = msaa_samples
         self.device = device
-        self.engine_lib = engine_lib     # None: the in-tree libmwb.so
         self._engine = None
         self._vis_engine = None
         self.reset()
@@ -412,8 +411,7 @@ class MiniWorldEnv(gym.Env):
                                "stepping and rendering need the CUDA engine")
         if self._engine is None:
             from .engine import SingleEnvEngine
-            self._engine = SingleEnvEngine(self.obs_width, self.obs_height, self.msaa_samples, self.device,
-                                           lib_path=self.engine_lib)
+            self._engine = SingleEnvEngine(self.obs_width, self.obs_height, self.msaa_samples, self.device)
         return self._engine
 
     def _push_world(self):
@@ -485,8 +483,7 @@ class MiniWorldEnv(gym.Env):
             raise RuntimeError("MiniWorldEnv was built with device=None (world generation only)")
         if self._vis_engine is None:
             from .engine import SingleEnvEngine
-            self._vis_engine = SingleEnvEngine(self.window_width, self.window_height, self.msaa_samples, self.device,
-                                               lib_path=self.engine_lib)
+            self._vis_engine = SingleEnvEngine(self.window_width, self.window_height, self.msaa_samples, self.device)
         return self._vis_engine
 
     def render(self):

@@ -16,8 +16,7 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
-def libmwb_path():
-    """In-tree libmwb.so (built by __graft_entry__.build())."""
+def _libmwb_built():
     path = os.path.join(ROOT, "miniworld_b200", "libmwb.so")
     nvcc = os.path.exists("/usr/local/cuda/bin/nvcc")
     if nvcc:     # `make` is a no-op when the library is newer than its sources
@@ -26,11 +25,28 @@ def libmwb_path():
     return path
 
 
+@pytest.fixture
+def libmwb_path(_libmwb_built):
+    """In-tree libmwb.so (built by __graft_entry__.build()): the library every product class loads."""
+    from miniworld_b200 import engine
+    engine._override_library_for_tests(None)
+    return _libmwb_built
+
+
 @pytest.fixture(scope="session")
-def hostsim_path():
-    """Test-only CPU build of the kernels' inner functions (tests/hostsim/build.sh)."""
-    out = subprocess.check_output([os.path.join(ROOT, "tests", "hostsim", "build.sh")]).decode().strip().splitlines()[-1]
-    return out
+def _hostsim_built():
+    return subprocess.check_output([os.path.join(ROOT, "tests", "hostsim", "build.sh")]).decode().strip().splitlines()[-1]
+
+
+@pytest.fixture
+def hostsim_path(_hostsim_built):
+    """Test-only CPU build of the kernels' inner functions (tests/hostsim/build.sh).  The product classes take no
+    library argument: while a test holds this fixture the binding is pointed at the host build through the
+    private test seam `engine._override_library_for_tests`."""
+    from miniworld_b200 import engine
+    engine._override_library_for_tests(_hostsim_built)
+    yield _hostsim_built
+    engine._override_library_for_tests(None)
 
 
 @pytest.fixture(scope="session")

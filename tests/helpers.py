@@ -31,7 +31,7 @@ CASES = {
 def make_env(name, g, lib_path=None, n=None, **kw):
     level, dr = CASES[name]
     N = g["actions"].shape[1] if n is None else n
-    env = BatchedMiniWorld(level, N, domain_rand=dr, autoreset=True, lib_path=lib_path, **kw)
+    env = BatchedMiniWorld(level, N, domain_rand=dr, autoreset=True, **kw)
     seeds = [1000 + i for i in range(N)]
     if env.device_reset:
         env.engine.seed(np.arange(N), np.array([rng_state_of(s) for s in seeds], RNG_DTYPE))
@@ -124,7 +124,7 @@ def run_single_env_trajectory(name, g, lib_path=None, envs=2, steps=120, device=
     from miniworld_b200.envs import LEVELS
     level, kw = SINGLE_CASES[name]
     for i in range(envs):
-        env = LEVELS[level](engine_lib=lib_path, device=device, **kw)
+        env = LEVELS[level](device=device, **kw)
         env.reset(seed=1000 + i)
         done = False
         for t in range(min(steps, g["actions"].shape[0])):
@@ -152,12 +152,12 @@ def noise_parity(lib_path, n=4, steps=80, prob=0.6, random_action=None):
     from miniworld_b200.engine import RNG_DTYPE, rng_state_of
     from miniworld_b200.envs import Hallway
     from miniworld_b200.wrappers import StochasticActionWrapper
-    env = BatchedMiniWorld("MiniWorld-Hallway-v0", num_envs=n, domain_rand=True, autoreset=False, lib_path=lib_path)
+    env = BatchedMiniWorld("MiniWorld-Hallway-v0", num_envs=n, domain_rand=True, autoreset=False)
     ids = np.arange(n, dtype=np.int32)
     env.engine.seed(ids, np.array([rng_state_of(1000 + i) for i in range(n)], RNG_DTYPE))
     env.engine.reset(None)
     env.set_action_noise(prob, random_action)
-    singles = [StochasticActionWrapper(Hallway(domain_rand=True, engine_lib=lib_path), prob=prob, random_action=random_action)
+    singles = [StochasticActionWrapper(Hallway(domain_rand=True), prob=prob, random_action=random_action)
                for _ in range(n)]
     for i, s in enumerate(singles):
         s.reset(seed=1000 + i)
@@ -185,7 +185,7 @@ def noise_parity(lib_path, n=4, steps=80, prob=0.6, random_action=None):
 def snapshot_roundtrip(level, lib_path, n=6, domain_rand=True, before=25, after=40, **kw):
     """step -> snapshot -> step (recorded) -> restore -> step again: identical; also into a fresh handle."""
     def make():
-        e = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=True, lib_path=lib_path, **kw)
+        e = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=True, **kw)
         return e
     env = make()
     ids = np.arange(n, dtype=np.int32)
@@ -222,7 +222,7 @@ def obs_format_parity(lib_path, n=5, steps=6, level="MiniWorld-FourRooms-v0", **
     """K2's fused PyTorchObsWrapper / GreyscaleWrapper epilogues == the wrappers applied to the HWC frames."""
     frames = {}
     for fmt in ("hwc", "cwh", "grey"):
-        env = BatchedMiniWorld(level, num_envs=n, autoreset=True, lib_path=lib_path, obs_format=fmt, **kw)
+        env = BatchedMiniWorld(level, num_envs=n, autoreset=True, obs_format=fmt, **kw)
         ids = np.arange(n, dtype=np.int32)
         env.engine.seed(ids, np.array([rng_state_of(3000 + i) for i in range(n)], RNG_DTYPE))
         env.engine.reset(None)
@@ -246,7 +246,7 @@ def batched_equals_single_env(level, lib_path, n=3, steps=4, domain_rand=False, 
     """The batched engine (device-side reset program, lowered rule) and the drop-in single-env class (host world
     generation, Python rule) produce identical frames, rewards and flags from the same seeds and actions."""
     from miniworld_b200.envs import LEVELS
-    env = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=False, lib_path=lib_path, **kw)
+    env = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=False, **kw)
     assert env.device_reset
     ids = np.arange(n, dtype=np.int32)
     env.engine.seed(ids, np.array([rng_state_of(4000 + i) for i in range(n)], RNG_DTYPE))
@@ -254,7 +254,7 @@ def batched_equals_single_env(level, lib_path, n=3, steps=4, domain_rand=False, 
     first = np.zeros((n, env.obs_height, env.obs_width, 3), np.uint8)
     env.engine.render(obs=first)
     dr = {"domain_rand": True} if domain_rand else {}
-    singles = [LEVELS[level](engine_lib=lib_path, **dr, **kw) for _ in range(n)]
+    singles = [LEVELS[level](**dr, **kw) for _ in range(n)]
     for i, s in enumerate(singles):
         o, _ = s.reset(seed=4000 + i)
         o = o["obs"] if isinstance(o, dict) else o
@@ -278,13 +278,13 @@ def batched_equals_python_levels(level, lib_path, domain_rand, n=3, steps=200, s
     drop-in class, same seeds and actions, with next-step auto-reset: poses, rewards, flags and every entity position
     are identical at every step.  Independent of the golden files: any seed, either domain_rand setting."""
     from miniworld_b200.envs import LEVELS
-    env = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=True, lib_path=lib_path)
+    env = BatchedMiniWorld(level, num_envs=n, domain_rand=domain_rand, autoreset=True)
     assert env.device_reset
     ids = np.arange(n, dtype=np.int32)
     env.engine.seed(ids, np.array([rng_state_of(seed0 + i) for i in range(n)], RNG_DTYPE))
     env.engine.reset(None)
     kw = {"domain_rand": True} if domain_rand else {}
-    singles = [LEVELS[level](engine_lib=lib_path, **kw) for _ in range(n)]
+    singles = [LEVELS[level](**kw) for _ in range(n)]
     for i, s in enumerate(singles):
         s.reset(seed=seed0 + i)
     na = env.action_space.n

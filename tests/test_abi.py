@@ -26,7 +26,7 @@ def test_header_functions_all_exported(libmwb_path):
 
 
 def test_struct_mirrors_match(libmwb_path):
-    engine.load_library(libmwb_path)      # raises EngineError on any sizeof mismatch
+    engine.load_library()                 # raises EngineError on any sizeof mismatch
 
 
 def test_no_cpu_fallback(libmwb_path):
@@ -39,5 +39,22 @@ def test_no_cpu_fallback(libmwb_path):
 
 
 def test_missing_library_is_loud(tmp_path):
-    with pytest.raises(engine.EngineError, match="not found"):
-        engine.load_library(str(tmp_path / "libmwb.so"))
+    engine._override_library_for_tests(str(tmp_path / "libmwb.so"))
+    try:
+        with pytest.raises(engine.EngineError, match="not found"):
+            engine.load_library()
+    finally:
+        engine._override_library_for_tests(None)
+
+
+def test_product_classes_take_no_library_argument():
+    """The only library the package loads is its own libmwb.so: no constructor accepts a path (the host build of the
+    kernels used by CPU tests is reachable only through the private test seam)."""
+    import inspect
+    from miniworld_b200.batched import BatchedMiniWorld
+    from miniworld_b200.dist import ShardedMiniWorld
+    from miniworld_b200.world import MiniWorldEnv
+    for cls in (BatchedMiniWorld, MiniWorldEnv, engine.Engine, engine.SingleEnvEngine, engine.SharedDeviceBuffer, ShardedMiniWorld):
+        params = inspect.signature(cls.__init__).parameters
+        assert not any("lib" in name for name in params), (cls.__name__, list(params))
+    assert list(inspect.signature(engine.load_library).parameters) == []

@@ -7,8 +7,8 @@ import pytest
 
 
 @pytest.fixture(scope="module")
-def hs(hostsim_path):
-    return C.CDLL(hostsim_path)
+def hs(_hostsim_built):
+    return C.CDLL(_hostsim_built)
 
 
 @pytest.mark.parametrize("scale", [0.12, 0.8, 2.4, 10.0, 1000.0, 1e5])

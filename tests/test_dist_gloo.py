@@ -26,8 +26,10 @@ def _worker(rank, world, port, hostsim, total, steps, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    from miniworld_b200 import engine
     from miniworld_b200.dist import ShardedMiniWorld
-    env = ShardedMiniWorld("MiniWorld-FourRooms-v0", total, dist=dist, lib_path=hostsim)
+    engine._override_library_for_tests(hostsim)          # spawned worker: select the host build of the kernels here too
+    env = ShardedMiniWorld("MiniWorld-FourRooms-v0", total, dist=dist)
     env.local.engine.seed(np.arange(env.count), np.array(
         [__import__("miniworld_b200.engine", fromlist=["x"]).rng_state_of(1000 + env.start + k) for k in range(env.count)]))
     env.local.engine.reset()
@@ -63,7 +65,7 @@ def test_two_ranks_equal_single_process(hostsim_path):
     # single process reference run
     from miniworld_b200.batched import BatchedMiniWorld
     from miniworld_b200.engine import rng_state_of
-    env = BatchedMiniWorld("MiniWorld-FourRooms-v0", total, lib_path=hostsim_path)
+    env = BatchedMiniWorld("MiniWorld-FourRooms-v0", total)
     env.engine.seed(np.arange(total), np.array([rng_state_of(1000 + k) for k in range(total)]))
     env.engine.reset()
     acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)

@@ -70,7 +70,7 @@ def test_host_reset_fallback_for_levels_without_a_device_program(libmwb_path, na
     host_only = type("HostOnly" + LEVELS[level].__name__, (LEVELS[level],), {"device_program": None})
     g = golden(name)
     n = 8
-    env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True, lib_path=libmwb_path)
+    env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True)
     assert not env.device_reset
     env._host_reset(np.arange(n, dtype=np.int32), [1000 + i for i in range(n)])
     env._seeded = True

@@ -249,3 +249,44 @@ def test_snapshot_after_asynchronous_step_sees_the_step(libmwb_path):
         assert np.array_equal(blob, ref.snapshot())
     env.close()
     ref.close()
+
+
+@pytest.mark.parametrize("level", ["MiniWorld-CollectHealth-v0", "MiniWorld-TMaze-v0", "MiniWorld-Sign-v0"])
+def test_batched_info_and_dict_observation_follow_the_level(libmwb_path, level):
+    """info["health"] (envs/collecthealth.py:100), info["goal_pos"] (envs/tmaze.py:89) and Sign's dict observation
+    (envs/sign.py:176) from the batched class == what the drop-in single-env class (the level's own Python step())
+    returns, env for env and step for step."""
+    import torch
+    from miniworld_b200.batched import BatchedMiniWorld
+    from miniworld_b200.envs import LEVELS
+    N, T = 3, 14
+    env = BatchedMiniWorld(level, N, autoreset=False)
+    obs, _ = env.reset(seed=500)
+    singles = [LEVELS[level]() for _ in range(N)]
+    first = [s.reset(seed=500 + i)[0] for i, s in enumerate(singles)]
+    if level.startswith("MiniWorld-Sign"):
+        assert isinstance(obs, dict) and set(obs) == {"obs", "goal"}
+        assert all(int(obs["goal"][i]) == first[i]["goal"] for i in range(N))
+        assert all(np.array_equal(obs["obs"][i].cpu().numpy(), first[i]["obs"]) for i in range(N))
+    rng = np.random.default_rng(9)
+    alive = [True] * N
+    for t in range(T):
+        acts = rng.integers(0, env.action_space.n, size=N).astype(np.int32)
+        obs, rew, te, tr, info = env.step(torch.as_tensor(acts, device="cuda"))
+        for i, s in enumerate(singles):
+            if not alive[i]:
+                continue
+            o, r, term, trunc, inf = s.step(int(acts[i]))
+            assert r == float(rew[i]) and term == bool(te[i]) and trunc == bool(tr[i])
+            if "health" in inf:
+                assert int(info["health"][i]) == inf["health"]
+            if "goal_pos" in inf:
+                assert np.array_equal(info["goal_pos"][i].cpu().numpy(), np.asarray(inf["goal_pos"], float))
+            if isinstance(o, dict):
+                assert int(obs["goal"][i]) == o["goal"] and np.array_equal(obs["obs"][i].cpu().numpy(), o["obs"])
+            alive[i] = not (term or trunc)
+    assert ("health" in info) == level.startswith("MiniWorld-CollectHealth")
+    assert ("goal_pos" in info) == level.startswith("MiniWorld-TMaze")
+    for s in singles:
+        s.close()
+    env.close()

@@ -76,18 +76,18 @@ def test_render_mode_and_wrappers_on_host_sim(hostsim_path):
     """reference tests/test_miniworld.py:17-64 (render vs obs mean, wrapper shapes), kernels on the CPU."""
     from miniworld_b200.envs import Hallway
     from miniworld_b200.wrappers import GreyscaleWrapper, PyTorchObsWrapper, StochasticActionWrapper
-    env = Hallway(render_mode="rgb_array", window_width=200, window_height=150, engine_lib=hostsim_path)
+    env = Hallway(render_mode="rgb_array", window_width=200, window_height=150)
     env.reset(seed=0)
     for _ in range(3):
         obs, _, _, _, _ = env.step(2)
         frame = env.render()
         assert frame.shape == (150, 200, 3) and abs(obs.mean() - frame.mean()) < 5
     env.close()
-    w = PyTorchObsWrapper(Hallway(engine_lib=hostsim_path))
+    w = PyTorchObsWrapper(Hallway())
     assert w.reset()[0].shape == (3, 80, 60) == tuple(w.observation_space.shape)
-    g = GreyscaleWrapper(Hallway(engine_lib=hostsim_path))
+    g = GreyscaleWrapper(Hallway())
     assert g.reset()[0].shape == (60, 80, 1)
-    s = StochasticActionWrapper(Hallway(engine_lib=hostsim_path), prob=0.5)
+    s = StochasticActionWrapper(Hallway(), prob=0.5)
     s.reset(seed=1)
     s.step(0)
     for e in (w, g, s):
@@ -101,7 +101,7 @@ def test_top_view_and_visible_ents_match_oracle(hostsim_path, softgl_lib, level)
     the CPU vs the immediate-mode oracle (depth-buffered draws with GL_ANY_SAMPLES_PASSED bookkeeping)."""
     from miniworld_b200.assets import Texture
     from miniworld_b200.envs import LEVELS
-    env = LEVELS[level](engine_lib=hostsim_path)
+    env = LEVELS[level]()
     seen = 0
     for seed in (3, 4):
         env.reset(seed=seed)
@@ -166,7 +166,7 @@ def test_every_level_views_match_oracle(hostsim_path, softgl_lib):
         if lvl in ("MiniWorld-Maze-v0", "MiniWorld-MazeS8-v0"):
             continue          # 8x8 maze: slow on the sequential host sim; MazeS2 / S3 cover the level
         kw = {} if "Sign" in lvl else {"domain_rand": True}
-        env = LEVELS[lvl](engine_lib=hostsim_path, **kw)
+        env = LEVELS[lvl](**kw)
         env.reset(seed=int(rng.integers(0, 10 ** 6)))
         for _ in range(5):
             _, _, te, tr, _ = env.step(int(rng.integers(0, env.action_space.n)))
@@ -206,7 +206,7 @@ def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, n
     host_only = type("HostOnly" + LEVELS[level].__name__, (LEVELS[level],), {"device_program": None})
     g = golden(name)
     n = 4
-    env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True, lib_path=hostsim_path)
+    env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True)
     assert not env.device_reset
     env._host_reset(np.arange(n, dtype=np.int32), [1000 + i for i in range(n)])
     env._seeded = True
@@ -233,7 +233,7 @@ def test_text_frame_with_arbitrary_text(hostsim_path, softgl_lib):
             super()._gen_world()
             self.entities.append(TextFrame(pos=[0, 1.35, 7], dir=math.pi / 2, str="this is a test"))
 
-    env = TestText(engine_lib=hostsim_path)
+    env = TestText()
     env.reset(seed=2)
     env.agent.pos = np.array([0.0, 0.0, 4.0])
     env.agent.dir = -math.pi / 2          # facing +z, towards the wall that carries the text
@@ -253,7 +253,7 @@ def test_env_checker_invariants(hostsim_path):
     for eid, cls in LEVELS.items():
         if "Maze-v0" in eid or "MazeS8" in eid:
             continue
-        env = cls(engine_lib=hostsim_path)
+        env = cls()
         o1, info1 = env.reset(seed=123)
         p1 = env.agent.pos.copy()
         o2, _ = env.reset(seed=123)
