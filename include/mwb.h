@@ -378,6 +378,11 @@ int mwb_shared_alloc(int device, size_t bytes, void** dev_ptr, unsigned char han
 int mwb_shared_open(int device, const unsigned char handle[64], void** dev_ptr);
 int mwb_shared_close(void* dev_ptr, int opened /* 1: from mwb_shared_open, 0: from mwb_shared_alloc */);
 
+/* The camera K2 derives for every env, read back for parity tests against the reference's Agent.cam_pos / cam_dir /
+ * cam_fov_y (entity.py:476-503) and its gluLookAt / gluPerspective arguments (miniworld.py:1200-1219): per env 16
+ * floats -- eye[3], right s[3], up u[3], forward f[3], projection scales (cot / aspect, cot), z_clip = za w - zb. */
+int mwb_debug_camera(mwb_handle* h, float* out /* host [num_envs][16] */);
+
 /* Device address of a per-env state array (valid for the handle's lifetime; contents are stream-ordered behind
  * mwb_step / mwb_reset on the stream they were given).  Lets the host side expose what the reference's level step()s
  * put into `info` without a state copy: info["health"] (envs/collecthealth.py:100) = MWB_ARRAY_COUNTER, the same

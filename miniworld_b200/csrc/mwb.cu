@@ -135,9 +135,8 @@ struct mwb_handle {
   bool last_valid;
 #endif
 #ifndef MWB_HOSTSIM
-  std::vector<cudaArray_t> tex_arrays;            // one CUDA array + texture object per (texture, mip level)
+  std::vector<cudaArray_t> tex_arrays;            // the texture atlas K2 gathers from (+ its texture object)
   std::vector<cudaTextureObject_t> tex_objects;
-  void* tex_obj_table;
 #endif
   std::vector<int> mesh_counts;   // triangles per uploaded mesh (host copy)
   void* mesh_tris_buf;
@@ -547,9 +546,6 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->profiling = false;
   h->frames_copied = false;
   h->have_params = h->have_protos = h->have_template = false;
-#ifndef MWB_HOSTSIM
-  h->tex_obj_table = nullptr;
-#endif
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = h->mesh_tex = nullptr;
   h->protos = h->ops = h->maze = h->maze_cdf = nullptr;
   h->mesh_tris_buf = nullptr;
@@ -734,7 +730,6 @@ extern "C" int mwb_destroy(mwb_handle* h) {
     if (p) dev_free(p);
 #ifndef MWB_HOSTSIM
   release_texture_objects(h);
-  if (h->tex_obj_table) dev_free(h->tex_obj_table);
   cudaStreamSynchronize(h->copy_stream);
   for (cudaEvent_t e : h->ev_k1) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
@@ -836,58 +831,83 @@ extern "C" int mwb_upload_textures(mwb_handle* h, const mwb_tex_desc* descs, int
     }
     T.nlev = lev;
   }
+#ifndef MWB_HOSTSIM
+  // ---- atlas for K2's tld4 path: every mip level of every texture in ONE 2-D CUDA array (so that the texture
+  // handle is the same for every lane whatever surface / LOD its pixel needs), each level framed by a one-texel
+  // wrapped border.  Shelf packing, tallest first; width 4096, height the next power of two.
+  release_texture_objects(h);
+  h->A.atlas = 0ull;
+  {
+    const char* tm = getenv("MWB_K2_TMU");
+    if (!tm || atoi(tm) != 0) {
+      struct Item { int t, l, w, hgt; };
+      std::vector<Item> items;
+      for (int t = 0; t < n; ++t)
+        for (int l = 0; l < td[t].nlev; ++l) items.push_back({t, l, td[t].lw[l] + 2, td[t].lh[l] + 2});
+      std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.hgt > b.hgt; });
+      const int AW = 4096;
+      int cx = 0, cy = 0, shelf = 0;
+      std::vector<std::pair<int, int>> at(items.size());
+      for (size_t k = 0; k < items.size(); ++k) {
+        if (cx + items[k].w > AW) { cx = 0; cy += shelf; shelf = 0; }
+        at[k] = {cx, cy};
+        cx += items[k].w;
+        shelf = std::max(shelf, items[k].hgt);
+      }
+      int AH = 1;
+      while (AH < cy + shelf) AH <<= 1;
+      if (AH <= 32768) {
+        std::vector<uint32_t> atlas((size_t)AW * AH, 0u);
+        for (size_t k = 0; k < items.size(); ++k) {
+          const Item& it = items[k];
+          const int lw = it.w - 2, lh = it.hgt - 2;
+          const uint32_t* src = pool.data() + td[it.t].off[it.l];
+          for (int y = -1; y <= lh; ++y)
+            for (int x = -1; x <= lw; ++x)
+              atlas[(size_t)(at[k].second + 1 + y) * AW + (at[k].first + 1 + x)] = src[(size_t)((y + lh) % lh) * lw + ((x + lw) % lw)];
+          td[it.t].ax[it.l] = (float)(at[k].first + 1);
+          td[it.t].ay[it.l] = (float)(at[k].second + 1);
+        }
+        const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        bool ok = cudaMallocArray(&arr, &fmt, AW, AH, cudaArrayTextureGather) == cudaSuccess;
+        if (ok) {
+          h->tex_arrays.push_back(arr);
+          ok = cudaMemcpy2DToArray(arr, 0, 0, atlas.data(), (size_t)AW * 4, (size_t)AW * 4, AH, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        cudaTextureObject_t obj = 0;
+        if (ok) {
+          cudaResourceDesc rd;
+          memset(&rd, 0, sizeof(rd));
+          rd.resType = cudaResourceTypeArray;
+          rd.res.array.array = arr;
+          cudaTextureDesc tdesc;
+          memset(&tdesc, 0, sizeof(tdesc));
+          tdesc.addressMode[0] = tdesc.addressMode[1] = cudaAddressModeClamp;
+          tdesc.filterMode = cudaFilterModePoint;
+          tdesc.readMode = cudaReadModeNormalizedFloat;
+          tdesc.normalizedCoords = 1;
+          ok = cudaCreateTextureObject(&obj, &rd, &tdesc, nullptr) == cudaSuccess;
+        }
+        if (ok) {
+          h->tex_objects.push_back(obj);
+          h->A.atlas = (unsigned long long)obj;
+          h->A.atlas_iw = 1.0f / (float)AW;
+          h->A.atlas_ih = 1.0f / (float)AH;
+        } else {
+          cudaGetLastError();
+          release_texture_objects(h);      // the pool path stays in use
+        }
+      }
+    }
+  }
+#endif
   int rc = replace_buf(&h->tex_desc, td.data(), td.size() * sizeof(TexDev), h->stream);
   if (!rc) rc = replace_buf(&h->texels, pool.data(), pool.size() * sizeof(uint32_t), h->stream);
   if (rc) return rc;
   h->A.tex = (const TexDev*)h->tex_desc;
   h->A.texels = (const uint32_t*)h->texels;
   h->A.num_tex = n;
-#ifndef MWB_HOSTSIM
-  // Texture objects for K2's tld4 path: every mip level is its own 2-D CUDA array (texture gather does not take a
-  // level of detail), RGBA8 read as normalised floats, point "filtering", GL_REPEAT in both directions.
-  release_texture_objects(h);
-  h->A.tex_obj = nullptr;
-  // Measured on B200 (FourRooms 4096 x 80x60): K2 1.12 ms with this path vs 1.03 ms with plain loads from the pool.
-  // 14 % fewer instructions, but the per-(texture, level) objects make the handle non-uniform across a warp (pixels
-  // of one half-tile straddle LOD levels and surfaces), which the compiler serialises; off unless MWB_K2_TMU=1.
-  const char* tm = getenv("MWB_K2_TMU");
-  if (tm && atoi(tm) != 0) {
-    std::vector<unsigned long long> table((size_t)n * MWB_MAX_LEVELS, 0ull);
-    bool ok = true;
-    const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-    for (int t = 0; t < n && ok; ++t)
-      for (int l = 0; l < td[t].nlev && ok; ++l) {
-        cudaArray_t arr = nullptr;
-        const int lw = td[t].lw[l], lh = td[t].lh[l];
-        if (cudaMallocArray(&arr, &fmt, lw, lh, cudaArrayTextureGather) != cudaSuccess) { ok = false; break; }
-        h->tex_arrays.push_back(arr);
-        if (cudaMemcpy2DToArray(arr, 0, 0, pool.data() + td[t].off[l], (size_t)lw * 4, (size_t)lw * 4, lh, cudaMemcpyHostToDevice) !=
-            cudaSuccess) { ok = false; break; }
-        cudaResourceDesc rd;
-        memset(&rd, 0, sizeof(rd));
-        rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = arr;
-        cudaTextureDesc tdesc;
-        memset(&tdesc, 0, sizeof(tdesc));
-        tdesc.addressMode[0] = tdesc.addressMode[1] = cudaAddressModeWrap;
-        tdesc.filterMode = cudaFilterModePoint;
-        tdesc.readMode = cudaReadModeNormalizedFloat;
-        tdesc.normalizedCoords = 1;
-        cudaTextureObject_t obj = 0;
-        if (cudaCreateTextureObject(&obj, &rd, &tdesc, nullptr) != cudaSuccess) { ok = false; break; }
-        h->tex_objects.push_back(obj);
-        table[(size_t)t * MWB_MAX_LEVELS + l] = (unsigned long long)obj;
-      }
-    if (ok) {
-      rc = replace_buf(&h->tex_obj_table, table.data(), table.size() * sizeof(unsigned long long), h->stream);
-      if (rc) return rc;
-      h->A.tex_obj = (const unsigned long long*)h->tex_obj_table;
-    } else {
-      cudaGetLastError();
-      release_texture_objects(h);      // the pool path stays in use
-    }
-  }
-#endif
   return MWB_OK;
 }
 
@@ -1658,6 +1678,42 @@ extern "C" int mwb_restore(mwb_handle* h, const void* blob, size_t bytes) {
     p += v[k].second;
   }
   if (sync_stream(h->stream) != 0) return fail(MWB_ECUDA, "sync failed");
+  return MWB_OK;
+}
+
+// ------------------------------------------------------------------ ABI: camera read-back (parity tests)
+#ifndef MWB_HOSTSIM
+__global__ void camera_kernel(DevState S, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.N) return;
+  const Camera c = make_camera(S, i);
+  float* o = out + (size_t)i * 16;
+  o[0] = c.ex; o[1] = c.ey; o[2] = c.ez; o[3] = c.sx; o[4] = c.sy; o[5] = c.sz; o[6] = c.ux; o[7] = c.uy; o[8] = c.uz;
+  o[9] = c.fx; o[10] = c.fy; o[11] = c.fz; o[12] = c.px; o[13] = c.py; o[14] = c.za; o[15] = c.zb;
+}
+#endif
+
+extern "C" int mwb_debug_camera(mwb_handle* h, float* out) {
+  if (!h || !out) return fail(MWB_EINVAL, "null argument");
+  const int N = h->S.N;
+#ifndef MWB_HOSTSIM
+  if (stream_enter(h, h->stream)) return MWB_ECUDA;
+  float* d = nullptr;
+  if (dev_alloc((void**)&d, (size_t)N * 16 * sizeof(float)) != 0) return fail(MWB_ECUDA, "device allocation failed");
+  camera_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(h->S, d);
+  h->launches++;
+  int rc = d2h(out, d, (size_t)N * 16 * sizeof(float), h->stream);
+  rc |= sync_stream(h->stream);
+  dev_free(d);
+  if (rc) return fail(MWB_ECUDA, "readback failed");
+#else
+  for (int i = 0; i < N; ++i) {
+    const Camera c = make_camera(h->S, i);
+    float* o = out + (size_t)i * 16;
+    o[0] = c.ex; o[1] = c.ey; o[2] = c.ez; o[3] = c.sx; o[4] = c.sy; o[5] = c.sz; o[6] = c.ux; o[7] = c.uy; o[8] = c.uz;
+    o[9] = c.fx; o[10] = c.fy; o[11] = c.fz; o[12] = c.px; o[13] = c.py; o[14] = c.za; o[15] = c.zb;
+  }
+#endif
   return MWB_OK;
 }
 

@@ -36,6 +36,7 @@ struct TexDev {
   int32_t w, h, nlev, pad;
   int32_t lw[MWB_MAX_LEVELS], lh[MWB_MAX_LEVELS];
   int32_t off[MWB_MAX_LEVELS];   // texel offset of each level in the pool
+  float ax[MWB_MAX_LEVELS], ay[MWB_MAX_LEVELS];   // atlas position of texel (0, 0) of each level (see RenderAssets.atlas)
 };
 
 struct MeshDev {
@@ -44,8 +45,10 @@ struct MeshDev {
 
 struct RenderAssets {
   const TexDev* tex;
-  const unsigned long long* tex_obj;   // [num_tex][MWB_MAX_LEVELS] CUDA texture objects, one per mip level (point sampled,
-                                 //   REPEAT, unorm8 -> float): K2 reads the 2x2 bilinear footprint with tld4; or null
+  unsigned long long atlas;      // CUDA texture object over ONE 2-D array holding every mip level of every texture, each
+                                 //   with a one-texel wrapped border (so a bilinear footprint never leaves its rectangle):
+                                 //   K2 reads the 2x2 footprint with tld4 through a warp-uniform handle; 0 = use the pool
+  float atlas_iw, atlas_ih;      // 1 / atlas width, height (powers of two: the scaling is exact)
   const uint32_t* texels;        // RGBA8 pool, row 0 = bottom of the image
   int32_t num_tex;
   const MeshDev* meshes;
@@ -615,16 +618,16 @@ MWB_DEV void bilinear(const RenderAssets& A, const TexDev& T, int level, float u
   const float xf = floorf(x), yf = floorf(y);
   const float fx = x - xf, fy = y - yf;
 #ifdef __CUDA_ARCH__
-  if (A.tex_obj != nullptr) {
+  if (A.atlas != 0ull) {
     // The texture unit fetches the footprint: tld4 (texture gather) at the texel CORNER shared by the four texels
     // (xf, yf) .. (xf + 1, yf + 1) -- half a texel away from every footprint boundary, so the unit's own fixed-point
     // coordinate arithmetic cannot pick another 2x2 block -- returns one channel of the four texels per instruction,
-    // already converted to float (exactly c / 255), with GL_REPEAT applied by the addressing hardware.  The weights
-    // fx, fy stay in float32 as above: only addressing, wrapping and unpacking moved to the TMU.
-    const cudaTextureObject_t obj = (cudaTextureObject_t)A.tex_obj[(size_t)(&T - A.tex) * MWB_MAX_LEVELS + level];
-    const float gu = (xf + 1.0f) / (float)w, gv = (yf + 1.0f) / (float)h;
+    // already converted to float (exactly c / 255).  xf ranges over -1 .. w - 1: GL_REPEAT is the atlas rectangle's
+    // wrapped border.  The weights fx, fy stay in float32 as above: addressing and unpacking moved to the TMU.
+    const float gu = (T.ax[level] + (xf + 1.0f)) * A.atlas_iw, gv = (T.ay[level] + (yf + 1.0f)) * A.atlas_ih;
+    const cudaTextureObject_t obj = (cudaTextureObject_t)A.atlas;
     const float4 c0 = tex2Dgather<float4>(obj, gu, gv, 0), c1 = tex2Dgather<float4>(obj, gu, gv, 1), c2 = tex2Dgather<float4>(obj, gu, gv, 2);
-    // gather order: x = (x0, y1), y = (x1, y1), z = (x1, y0), w = (x0, y0)
+    // gather order (tools/gather_probe.cu): x = (x0, y1), y = (x1, y1), z = (x1, y0), w = (x0, y0)
     float top = c0.w + fx * (c0.z - c0.w), bot = c0.x + fx * (c0.y - c0.x);
     out[0] = top + fy * (bot - top);
     top = c1.w + fx * (c1.z - c1.w); bot = c1.x + fx * (c1.y - c1.x);

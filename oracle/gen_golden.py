@@ -31,9 +31,11 @@ CASES = [
     ("oneroom", "MiniWorld-OneRoom-v0", {}, 64, 300),
     ("fourrooms", "MiniWorld-FourRooms-v0", {}, 64, 300),
     ("fourrooms_dr", "MiniWorld-FourRooms-v0", {"domain_rand": True}, 32, 300),
-    ("pickup", "MiniWorld-PickupObjects-v0", {}, 32, 450),
+    ("pickup", "MiniWorld-PickupObjects-v0", {}, 64, 450),
     ("pickup_dr", "MiniWorld-PickupObjects-v0", {"domain_rand": True}, 16, 300),
-    ("maze_dr", "MiniWorld-Maze-v0", {"domain_rand": True}, 8, 200),
+    ("maze_dr", "MiniWorld-Maze-v0", {"domain_rand": True}, 64, 300),
+    # beyond max_episode_steps = 1536 (maze.py:49: num_rows * num_cols * 24): the truncation branch of step() fires
+    ("maze_long", "MiniWorld-Maze-v0", {"domain_rand": True}, 2, 1600),
     ("mazes3", "MiniWorld-MazeS3-v0", {}, 16, 300),
     # levels outside BASELINE.json's configs (single-env path)
     ("tmaze", "MiniWorld-TMaze-v0", {}, 8, 300),

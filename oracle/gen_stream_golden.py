@@ -45,7 +45,7 @@ CASES = {
 }
 # the same trajectories rendered at BASELINE.json config 5's observation size
 # extra envs replayed only for their first steps: known pick-up events of the golden trajectories (env: last row)
-EVENT_ENVS = {"pickup": {19: 2, 9: 6, 13: 6}, "pickup_dr": {13: 5, 9: 10}, "pickup_160": {19: 2, 9: 6}}
+EVENT_ENVS = {"pickup": {19: 2, 9: 4, 13: 4}, "pickup_dr": {13: 5, 9: 10}, "pickup_160": {19: 2, 9: 4}}
 BIG = {"pickup_160": ("pickup", {"obs_width": 160, "obs_height": 120}, (0,), (0, 3, 21, 89))}
 
 

@@ -13,6 +13,7 @@ CASES = {
     "pickup": ("MiniWorld-PickupObjects-v0", False),
     "pickup_dr": ("MiniWorld-PickupObjects-v0", True),
     "maze_dr": ("MiniWorld-MazeS8-v0", True),
+    "maze_long": ("MiniWorld-MazeS8-v0", True),          # 1600 steps: the max_episode_steps = 1536 truncation fires
     "mazes3": ("MiniWorld-MazeS3-v0", False),
     # levels beyond BASELINE.json's configs whose _gen_world() / rule are lowered too
     "tmaze": ("MiniWorld-TMaze-v0", False),
@@ -347,7 +348,30 @@ def stream_parity(name, lib_path=None, max_rows=None, check_views=True):
     for k, (t, i) in enumerate(s["sel"]):
         if max_rows is None or t <= max_rows:
             rows.setdefault(int(t), []).append((k, int(i)))
-    stats = dict(frames=0, worst=0, same=0, total=0, events=0, tops=0, vis=0)
+    stats = dict(frames=0, worst=0, same=0, total=0, events=0, tops=0, vis=0, cams=0, cam_exact=0)
+    aspect = W / float(H)
+
+    def check_camera(t):
+        """K2's camera (mwb_debug_camera) vs the reference's Agent.cam_pos / cam_dir / cam_fov_y at that moment
+        (entity.py:476-503) pushed through GLU's gluLookAt / gluPerspective arithmetic in float64 and rounded once:
+        every component within 1 float32 ulp (the two float64 routes differ in their last bits), nearly all identical."""
+        cam = env.engine.debug_camera()
+        for k, i in rows[t]:
+            eye, d, fov = s["cam_pos"][k], s["cam_dir"][k], float(s["cam_fov_y"][k])
+            assert np.array_equal(s["lookat"][k][:3], eye) and np.array_equal(s["lookat"][k][3:6], eye + d)
+            f = (eye + d) - eye
+            f = f / np.sqrt(f @ f)
+            sv = np.cross(f, [0.0, 1.0, 0.0])
+            sv = sv / np.sqrt(sv @ sv)
+            u = np.cross(sv, f)
+            cot = np.cos(fov / 2 * np.pi / 180) / np.sin(fov / 2 * np.pi / 180)
+            want = np.concatenate([eye, sv, u, f, [cot / aspect, cot]]).astype(np.float32)
+            got = cam[i, :14]
+            ulp = np.spacing(np.maximum(np.abs(want), np.float32(1e-3)))
+            assert (np.abs(got - want) <= ulp).all(), "%s row %d env %d: camera %r != %r" % (name, t, i, got, want)
+            stats["cams"] += 14
+            stats["cam_exact"] += int((got == want).sum())
+
     out = dict(obs=np.zeros((N, H, W, 3), np.uint8), reward=np.zeros(N), terminated=np.zeros(N, np.uint8),
                truncated=np.zeros(N, np.uint8), depth=np.zeros((N, H, W, 1), np.float32))
     top = np.zeros((N, H, W, 3), np.uint8)
@@ -386,10 +410,12 @@ def stream_parity(name, lib_path=None, max_rows=None, check_views=True):
     if 0 in rows:
         env.engine.render(obs=out["obs"], depth=out["depth"])
         check(0)
+        check_camera(0)
     for t in range(1, max(rows) + 1):
         need = t in rows
         env.step_host(g["actions"][t - 1, :N], out, render=need)
         if need:
             check(t)
+            check_camera(t)
     env.close()
     return stats

@@ -23,9 +23,14 @@ def test_lowered_extra_levels_bit_exact(libmwb_path, name):
     run_trajectory(name, golden(name), libmwb_path, check_every=5)
 
 
-@pytest.mark.parametrize("name", ["mazes3", "maze_dr"])
-def test_host_reset_levels_bit_exact(libmwb_path, name):
-    run_trajectory(name, golden(name), libmwb_path, check_every=5)
+@pytest.mark.parametrize("name", ["mazes3", "maze_dr", "maze_long"])
+def test_maze_levels_bit_exact(libmwb_path, name):
+    """Device-generated mazes (csrc/maze.cuh); maze_dr: BASELINE.json config 4 at N = 64 x T = 300 (SURVEY 8d);
+    maze_long: 1600 steps, so the truncation at max_episode_steps = 1536 (maze.py:49) and the reset after it happen."""
+    g = golden(name)
+    T, N = run_trajectory(name, g, libmwb_path, check_every=5)
+    if name == "maze_long":
+        assert T == 1600 and g["truncated"].sum() >= 1 and g["step_count"].max() == 1536
 
 
 def test_rng_stream_position_after_rollout(libmwb_path):

@@ -16,3 +16,4 @@ def test_k2_matches_reference_stream_frames(libmwb_path, name):
           "%d visibility sets" % (name, st["frames"], st["events"], st["worst"], 100.0 * st["same"] / st["total"],
                                   st["tops"], st["vis"]))
     assert st["frames"] >= 4 and st["worst"] <= 1 and st["same"] / st["total"] > 0.995
+    assert st["cams"] > 0 and st["cam_exact"] / st["cams"] > 0.98          # camera vs Agent.cam_pos / cam_dir / cam_fov_y

@@ -63,6 +63,14 @@ def test_device_maze_long_rollout_with_resets(hostsim_path):
     run_trajectory("mazes3", golden("mazes3"), hostsim_path, steps=300, n=8, check_every=25)
 
 
+def test_maze_truncation_at_max_episode_steps(hostsim_path):
+    """1600 steps of the 8 x 8 maze: step_count reaches max_episode_steps = 1536 (maze.py:49), the step is truncated
+    (reward 0, terminated False) and the next one resets -- bit for bit as the reference did."""
+    g = golden("maze_long")
+    assert g["truncated"].sum() >= 1 and g["step_count"].max() == 1536
+    run_trajectory("maze_long", g, hostsim_path, n=1, check_every=64)
+
+
 @pytest.mark.parametrize("name", ["tmaze", "ymaze_dr", "roomobjs", "putnext_dr", "pickup", "wallgap", "sidewalk_dr",
                                   "collecthealth", "collecthealth_pick", "threerooms_dr", "sign"])
 def test_single_env_levels_follow_reference(hostsim_path, name):

@@ -71,3 +71,4 @@ def test_hostsim_matches_reference_stream_frames(hostsim_path, name):
     big = name in ("maze_dr", "pickup_160")
     st = stream_parity(name, hostsim_path, max_rows=21 if big else 89)
     assert st["frames"] >= 4 and st["same"] / st["total"] > 0.995
+    assert st["cams"] > 0 and st["cam_exact"] / st["cams"] > 0.98
