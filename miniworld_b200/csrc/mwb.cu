@@ -118,6 +118,9 @@ struct mwb_handle {
   bool frames_copied;
   int k2_variant;
   int k2_flags;                   // MWB_K2_* measurement switches (env MWB_K2_FLAGS)
+  const void* peer_checked;       // last observation pointer whose home device was looked up, and the answer
+  bool peer_result;
+  bool obs_is_peer;               // this launch's observation buffer lives on another GPU (K2 stages whole frames)
   int k2_static_smem;             // static shared memory of the K2 instantiation in use (cudaFuncGetAttributes)
   TriRec* vis_tris;              // scratch of mwb_visible_ents, allocated on first use
   ViewSpec view;                 // what the next render launch draws (agent camera unless mwb_render_top_view)
@@ -135,8 +138,7 @@ struct mwb_handle {
   bool last_valid;
 #endif
 #ifndef MWB_HOSTSIM
-  std::vector<cudaArray_t> tex_arrays;            // the texture atlas K2 gathers from (+ its texture object)
-  std::vector<cudaTextureObject_t> tex_objects;
+  struct AtlasEntry* atlas;                       // the (shared) texture atlas K2 gathers from, or null
 #endif
   std::vector<int> mesh_counts;   // triangles per uploaded mesh (host copy)
   void* mesh_tris_buf;
@@ -148,11 +150,26 @@ struct mwb_handle {
 };
 
 #ifndef MWB_HOSTSIM
+struct AtlasEntry {
+  int device;
+  uint64_t hash;
+  size_t texels;
+  int refs;
+  cudaArray_t arr;
+  cudaTextureObject_t obj;
+  float iw, ih;
+  std::vector<float> ax, ay;       // [texture][level] position of texel (0, 0)
+};
+static std::vector<AtlasEntry*> g_atlases;
 static void release_texture_objects(mwb_handle* h) {
-  for (cudaTextureObject_t o : h->tex_objects) cudaDestroyTextureObject(o);
-  for (cudaArray_t a : h->tex_arrays) cudaFreeArray(a);
-  h->tex_objects.clear();
-  h->tex_arrays.clear();
+  AtlasEntry* e = h->atlas;
+  h->atlas = nullptr;
+  if (!e || --e->refs > 0) return;
+  for (size_t k = 0; k < g_atlases.size(); ++k)
+    if (g_atlases[k] == e) g_atlases.erase(g_atlases.begin() + k);
+  cudaDestroyTextureObject(e->obj);
+  cudaFreeArray(e->arr);
+  delete e;
 }
 #endif
 
@@ -490,6 +507,9 @@ static int k2_list_bytes(const mwb_handle* h) {
 static int k2_frame_stage_bytes(const mwb_handle* h) {
   const size_t bytes = (size_t)h->S.obs_w * h->S.obs_h * 3;
   if (h->k2_parts != 1 || h->obs_format == MWB_OBS_GREY_F64 || bytes > 16384 || (bytes & 15) != 0) return 0;
+  // Staging the whole frame pays only when the stores leave the GPU (peer memory of rank 0: full 16-byte address-ordered
+  // stores instead of 8-byte row segments, 52 % -> 89 % weak-scaling efficiency on 8 GPUs); for local HBM it costs 6 %.
+  if ((h->k2_flags & MWB_K2_NO_FRAME_STAGE) || !(h->obs_is_peer || (h->k2_flags & MWB_K2_FORCE_FRAME_STAGE))) return 0;
   // not at the price of a resident block: three blocks per SM (+ 1 KB each for the system) must still fit in 227 KB
   const size_t per_block = (size_t)k2_list_bytes(h) + bytes + (size_t)h->k2_static_smem + 1024;
   if (3 * per_block > 232448) return 0;
@@ -546,6 +566,9 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->profiling = false;
   h->frames_copied = false;
   h->have_params = h->have_protos = h->have_template = false;
+#ifndef MWB_HOSTSIM
+  h->atlas = nullptr;
+#endif
   h->tex_desc = h->texels = h->mesh_desc = h->mesh_pos = h->mesh_nrm = h->mesh_uv = h->mesh_rgb = h->mesh_tex = nullptr;
   h->protos = h->ops = h->maze = h->maze_cdf = nullptr;
   h->mesh_tris_buf = nullptr;
@@ -555,6 +578,8 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->vis_tris = nullptr;
   h->obs_format = MWB_OBS_HWC_U8;
   h->obs_px_bytes = 3;
+  h->peer_checked = nullptr;
+  h->peer_result = h->obs_is_peer = false;
   h->k2_static_smem = 19456;
   memset(&h->S, 0, sizeof(DevState));
   memset(&h->A, 0, sizeof(RenderAssets));
@@ -707,8 +732,14 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
       case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, true>, 320, smem); break;
       default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 4, true>, 256, smem); break;
     }
-    fprintf(stderr, "[mwb] K2 variant %d: dynamic smem %d B, parts %d, resident blocks/SM (8x MSAA) %d\n", h->k2_variant, smem,
-            h->k2_parts, nb);
+    const int launch_smem = k2_smem_bytes(h);
+    switch (h->k2_variant) {
+      case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 3, true>, 256, launch_smem); break;
+      case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, true>, 320, launch_smem); break;
+      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 4, true>, 256, launch_smem); break;
+    }
+    fprintf(stderr, "[mwb] K2 variant %d: dynamic smem %d B (local destination), parts %d, resident blocks/SM (8x MSAA) %d\n",
+            h->k2_variant, launch_smem, h->k2_parts, nb);
   }
 #endif
   *out = h;
@@ -834,70 +865,102 @@ extern "C" int mwb_upload_textures(mwb_handle* h, const mwb_tex_desc* descs, int
 #ifndef MWB_HOSTSIM
   // ---- atlas for K2's tld4 path: every mip level of every texture in ONE 2-D CUDA array (so that the texture
   // handle is the same for every lane whatever surface / LOD its pixel needs), each level framed by a one-texel
-  // wrapped border.  Shelf packing, tallest first; width 4096, height the next power of two.
+  // wrapped border.  Shelf packing, tallest first; width 4096, height the next power of two.  Atlases are shared
+  // between the handles of a process (keyed by device + a hash of the texel pool): building one costs ~0.1-0.5 s.
   release_texture_objects(h);
   h->A.atlas = 0ull;
   {
     const char* tm = getenv("MWB_K2_TMU");
     if (!tm || atoi(tm) != 0) {
-      struct Item { int t, l, w, hgt; };
-      std::vector<Item> items;
-      for (int t = 0; t < n; ++t)
-        for (int l = 0; l < td[t].nlev; ++l) items.push_back({t, l, td[t].lw[l] + 2, td[t].lh[l] + 2});
-      std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.hgt > b.hgt; });
-      const int AW = 4096;
-      int cx = 0, cy = 0, shelf = 0;
-      std::vector<std::pair<int, int>> at(items.size());
-      for (size_t k = 0; k < items.size(); ++k) {
-        if (cx + items[k].w > AW) { cx = 0; cy += shelf; shelf = 0; }
-        at[k] = {cx, cy};
-        cx += items[k].w;
-        shelf = std::max(shelf, items[k].hgt);
-      }
-      int AH = 1;
-      while (AH < cy + shelf) AH <<= 1;
-      if (AH <= 32768) {
-        std::vector<uint32_t> atlas((size_t)AW * AH, 0u);
+      uint64_t hash = 1469598103934665603ull;
+      auto mix = [&hash](uint64_t v) { hash = (hash ^ v) * 1099511628211ull; };
+      mix((uint64_t)n);
+      for (int t = 0; t < n; ++t) { mix((uint64_t)td[t].w << 32 | (uint32_t)td[t].h); mix((uint64_t)td[t].nlev); }
+      for (size_t k = 0; k + 1 < pool.size(); k += 2) mix((uint64_t)pool[k] << 32 | pool[k + 1]);
+      AtlasEntry* e = nullptr;
+      for (AtlasEntry* c : g_atlases)
+        if (c->device == h->cfg.device && c->hash == hash && c->texels == pool.size()) e = c;
+      if (!e) {
+        struct Item { int t, l, w, hgt; };
+        std::vector<Item> items;
+        for (int t = 0; t < n; ++t)
+          for (int l = 0; l < td[t].nlev; ++l) items.push_back({t, l, td[t].lw[l] + 2, td[t].lh[l] + 2});
+        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.hgt > b.hgt; });
+        const int AW = 4096;
+        int cx = 0, cy = 0, shelf = 0;
+        std::vector<std::pair<int, int>> at(items.size());
         for (size_t k = 0; k < items.size(); ++k) {
-          const Item& it = items[k];
-          const int lw = it.w - 2, lh = it.hgt - 2;
-          const uint32_t* src = pool.data() + td[it.t].off[it.l];
-          for (int y = -1; y <= lh; ++y)
-            for (int x = -1; x <= lw; ++x)
-              atlas[(size_t)(at[k].second + 1 + y) * AW + (at[k].first + 1 + x)] = src[(size_t)((y + lh) % lh) * lw + ((x + lw) % lw)];
-          td[it.t].ax[it.l] = (float)(at[k].first + 1);
-          td[it.t].ay[it.l] = (float)(at[k].second + 1);
+          if (cx + items[k].w > AW) { cx = 0; cy += shelf; shelf = 0; }
+          at[k] = {cx, cy};
+          cx += items[k].w;
+          shelf = std::max(shelf, items[k].hgt);
         }
-        const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-        cudaArray_t arr = nullptr;
-        bool ok = cudaMallocArray(&arr, &fmt, AW, AH, cudaArrayTextureGather) == cudaSuccess;
-        if (ok) {
-          h->tex_arrays.push_back(arr);
-          ok = cudaMemcpy2DToArray(arr, 0, 0, atlas.data(), (size_t)AW * 4, (size_t)AW * 4, AH, cudaMemcpyHostToDevice) == cudaSuccess;
+        int AH = 1;
+        while (AH < cy + shelf) AH <<= 1;
+        if (AH <= 32768) {
+          e = new AtlasEntry();
+          e->device = h->cfg.device;
+          e->hash = hash;
+          e->texels = pool.size();
+          e->refs = 0;
+          e->arr = nullptr;
+          e->obj = 0;
+          e->ax.assign((size_t)n * MWB_MAX_LEVELS, 0.0f);
+          e->ay.assign((size_t)n * MWB_MAX_LEVELS, 0.0f);
+          std::vector<uint32_t> atlas((size_t)AW * AH, 0u);
+          for (size_t k = 0; k < items.size(); ++k) {
+            const Item& it = items[k];
+            const int lw = it.w - 2, lh = it.hgt - 2;
+            const uint32_t* src = pool.data() + td[it.t].off[it.l];
+            for (int y = -1; y <= lh; ++y) {
+              uint32_t* dst = &atlas[(size_t)(at[k].second + 1 + y) * AW + at[k].first];
+              const uint32_t* row = src + (size_t)((y + lh) % lh) * lw;
+              dst[0] = row[lw - 1];
+              memcpy(dst + 1, row, (size_t)lw * 4);
+              dst[lw + 1] = row[0];
+            }
+            e->ax[(size_t)it.t * MWB_MAX_LEVELS + it.l] = (float)(at[k].first + 1);
+            e->ay[(size_t)it.t * MWB_MAX_LEVELS + it.l] = (float)(at[k].second + 1);
+          }
+          const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+          bool ok = cudaMallocArray(&e->arr, &fmt, AW, AH, cudaArrayTextureGather) == cudaSuccess;
+          if (ok) ok = cudaMemcpy2DToArray(e->arr, 0, 0, atlas.data(), (size_t)AW * 4, (size_t)AW * 4, AH, cudaMemcpyHostToDevice) == cudaSuccess;
+          if (ok) {
+            cudaResourceDesc rd;
+            memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = e->arr;
+            cudaTextureDesc tdesc;
+            memset(&tdesc, 0, sizeof(tdesc));
+            tdesc.addressMode[0] = tdesc.addressMode[1] = cudaAddressModeClamp;
+            tdesc.filterMode = cudaFilterModePoint;
+            tdesc.readMode = cudaReadModeNormalizedFloat;
+            tdesc.normalizedCoords = 1;
+            ok = cudaCreateTextureObject(&e->obj, &rd, &tdesc, nullptr) == cudaSuccess;
+          }
+          if (ok) {
+            e->iw = 1.0f / (float)AW;
+            e->ih = 1.0f / (float)AH;
+            g_atlases.push_back(e);
+          } else {
+            cudaGetLastError();
+            if (e->arr) cudaFreeArray(e->arr);
+            delete e;
+            e = nullptr;                     // the pool path stays in use
+          }
         }
-        cudaTextureObject_t obj = 0;
-        if (ok) {
-          cudaResourceDesc rd;
-          memset(&rd, 0, sizeof(rd));
-          rd.resType = cudaResourceTypeArray;
-          rd.res.array.array = arr;
-          cudaTextureDesc tdesc;
-          memset(&tdesc, 0, sizeof(tdesc));
-          tdesc.addressMode[0] = tdesc.addressMode[1] = cudaAddressModeClamp;
-          tdesc.filterMode = cudaFilterModePoint;
-          tdesc.readMode = cudaReadModeNormalizedFloat;
-          tdesc.normalizedCoords = 1;
-          ok = cudaCreateTextureObject(&obj, &rd, &tdesc, nullptr) == cudaSuccess;
-        }
-        if (ok) {
-          h->tex_objects.push_back(obj);
-          h->A.atlas = (unsigned long long)obj;
-          h->A.atlas_iw = 1.0f / (float)AW;
-          h->A.atlas_ih = 1.0f / (float)AH;
-        } else {
-          cudaGetLastError();
-          release_texture_objects(h);      // the pool path stays in use
-        }
+      }
+      if (e) {
+        e->refs++;
+        h->atlas = e;
+        for (int t = 0; t < n; ++t)
+          for (int l = 0; l < td[t].nlev; ++l) {
+            td[t].ax[l] = e->ax[(size_t)t * MWB_MAX_LEVELS + l];
+            td[t].ay[l] = e->ay[(size_t)t * MWB_MAX_LEVELS + l];
+          }
+        h->A.atlas = (unsigned long long)e->obj;
+        h->A.atlas_iw = e->iw;
+        h->A.atlas_ih = e->ih;
       }
     }
   }
@@ -1356,6 +1419,14 @@ extern "C" int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int
 // Launch K2 for envs [env0, env0 + count) (obs / depth point at env 0 of the full buffers).
 static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int count, stream_t s) {
 #ifndef MWB_HOSTSIM
+  if (obs != h->peer_checked) {         // the observation destination rarely changes: query its home device once
+    cudaPointerAttributes pa;
+    h->peer_checked = obs;
+    h->peer_result = obs && cudaPointerGetAttributes(&pa, obs) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+                     pa.device != h->cfg.device;
+    cudaGetLastError();
+  }
+  h->obs_is_peer = h->peer_result;
   const int smem = k2_smem_bytes(h), fstage = k2_frame_stage_bytes(h);
   const K2Layout lay = k2_layout(h->smem_tris, h->tri_cap, h->stage_bytes, k2_halves_per_part(h->S.obs_w, h->S.obs_h, h->k2_parts), fstage);
   if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");

@@ -31,10 +31,14 @@
 #define MWB_TILE_CAP 16              // candidate triangles listed per half-tile; fuller half-tiles scan the lists
 #define MWB_K2_LISTS 1               // kernel flags (env MWB_K2_FLAGS, default all on): per-half-tile candidate lists,
 #define MWB_K2_PAIRS 2               // quad-pair lazy pixels
+#define MWB_K2_NO_FRAME_STAGE 4      // host side: never stage the whole frame in shared memory
+#define MWB_K2_FORCE_FRAME_STAGE 8   // host side: stage it even when the destination is local memory
 
 // K2's dynamic shared memory, in this order (host and kernel share the arithmetic):
-//   [triangle records (small levels)] [staged static quads] [visit order u16 + depth keys f32]
-//   [slot of every record u16] [per-half-tile candidate counts u16 + lists u16 x MWB_TILE_CAP] [frame stage]
+//   [triangle records (small levels)]
+//   [staged static quads  |  visit order u16 + depth keys f32 + slot of every record u16 + per-half-tile candidate
+//    counts u16 + lists u16 x MWB_TILE_CAP]      <- one region: the TMA-staged quads are dead once the triangles are set up
+//   [frame stage]
 struct K2Layout {
   int order_off, zkey_off, slot_off, cnt_off, list_off, stage_off, end;
 };
@@ -46,12 +50,13 @@ K2Layout k2_layout(bool smem_tris, int tri_cap, int stage_bytes, int halves_per_
   K2Layout L;
   const int tri_bytes = smem_tris ? tri_cap * (int)sizeof(TriRec) : 0;
   const int cap2 = (tri_cap + 1) & ~1;
-  L.order_off = tri_bytes + stage_bytes;
+  L.order_off = tri_bytes;
   L.zkey_off = L.order_off + cap2 * 2;
   L.slot_off = L.zkey_off + tri_cap * 4;
   L.cnt_off = L.slot_off + cap2 * 2;
   L.list_off = L.cnt_off + ((halves_per_part + 1) & ~1) * 2;
-  L.stage_off = (L.list_off + halves_per_part * MWB_TILE_CAP * 2 + 15) & ~15;
+  const int lists_end = L.list_off + halves_per_part * MWB_TILE_CAP * 2, quads_end = tri_bytes + stage_bytes;
+  L.stage_off = ((lists_end > quads_end ? lists_end : quads_end) + 15) & ~15;
   L.end = L.stage_off + frame_stage_bytes;
   return L;
 }
@@ -392,6 +397,8 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   }
   __syncthreads();
   const int nsegs = 1 + fmap.n_ents + (fmap.agent_task >= 0 ? 1 : 0);
+  bool has_mesh = false;                 // any list in HBM (mesh entity) in this frame?
+  for (int k = 1; k <= fmap.n_ents; ++k) has_mesh = has_mesh || fmap.ent_kind[k - 1] == MWB_KIND_MESH;
 
   // ---- visiting order of the block-resident triangles (rooms, boxes, the map view's marker): front to back by
   // their nearest possible depth, so that the conservative occlusion tests fire early (the image does not depend
@@ -579,7 +586,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
 
     // ---- generic path: the mesh lists in HBM (and, for a half-tile whose candidate list overflowed, the resident lists)
 #pragma unroll 1
-    for (int sgi = 0; sgi < nsegs; ++sgi) {
+    for (int sgi = (listed && !has_mesh) ? nsegs : 0; sgi < nsegs; ++sgi) {
       const Segment sg = segs[sgi];
       if (sg.count == 0 || (listed && sg.bbox == nullptr)) continue;
       if ((sg.bx & 0xFFFF) > tx0 + 7 || (sg.bx >> 16) < tx0 || (sg.by & 0xFFFF) > ty0 + 3 || (sg.by >> 16) < ty0) continue;

@@ -688,6 +688,43 @@ MWB_DEV void shade_pixel(const RenderAssets& A, const TriRec& t, int px, int py,
     const int l0 = (int)lc;
     const float f = lc - (float)l0;
     float tc[3] = {0.0f, 0.0f, 0.0f};
+#ifdef __CUDA_ARCH__
+    if (A.atlas != 0ull) {
+      // texture-unit path: the gathers of BOTH mip levels are issued before any of their results is used, so the two
+      // texture round trips overlap (the loop below would serialise them)
+      const cudaTextureObject_t obj = (cudaTextureObject_t)A.atlas;
+      const float fu = u - floorf(u), fv = v - floorf(v);
+      const float xa = fu * (float)T.lw[l0] - 0.5f, ya = fv * (float)T.lh[l0] - 0.5f;
+      const float xaf = floorf(xa), yaf = floorf(ya);
+      const float gua = (T.ax[l0] + (xaf + 1.0f)) * A.atlas_iw, gva = (T.ay[l0] + (yaf + 1.0f)) * A.atlas_ih;
+      const float4 a0 = tex2Dgather<float4>(obj, gua, gva, 0), a1 = tex2Dgather<float4>(obj, gua, gva, 1), a2 = tex2Dgather<float4>(obj, gua, gva, 2);
+      float4 b0 = a0, b1 = a1, b2 = a2;
+      float fxb = 0.0f, fyb = 0.0f;
+      if (f > 0.0f) {                       // (f > 0 implies l0 + 1 < nlev)
+        const int l1 = l0 + 1;
+        const float xb = fu * (float)T.lw[l1] - 0.5f, yb = fv * (float)T.lh[l1] - 0.5f;
+        const float xbf = floorf(xb), ybf = floorf(yb);
+        const float gub = (T.ax[l1] + (xbf + 1.0f)) * A.atlas_iw, gvb = (T.ay[l1] + (ybf + 1.0f)) * A.atlas_ih;
+        b0 = tex2Dgather<float4>(obj, gub, gvb, 0);
+        b1 = tex2Dgather<float4>(obj, gub, gvb, 1);
+        b2 = tex2Dgather<float4>(obj, gub, gvb, 2);
+        fxb = xb - xbf;
+        fyb = yb - ybf;
+      }
+      const float fxa = xa - xaf, fya = ya - yaf, wa = 1.0f - f;
+      // gather order (tools/gather_probe.cu): x = (x0, y1), y = (x1, y1), z = (x1, y0), w = (x0, y0)
+#define MWB_BILERP(c, fx, fy) ((c.w + fx * (c.z - c.w)) + fy * ((c.x + fx * (c.y - c.x)) - (c.w + fx * (c.z - c.w))))
+      tc[0] = wa * MWB_BILERP(a0, fxa, fya);
+      tc[1] = wa * MWB_BILERP(a1, fxa, fya);
+      tc[2] = wa * MWB_BILERP(a2, fxa, fya);
+      if (f > 0.0f) {
+        tc[0] += f * MWB_BILERP(b0, fxb, fyb);
+        tc[1] += f * MWB_BILERP(b1, fxb, fyb);
+        tc[2] += f * MWB_BILERP(b2, fxb, fyb);
+      }
+#undef MWB_BILERP
+    } else
+#endif
 #pragma unroll 1
     for (int j = 0; j < 2; ++j) {
       const float wj = j == 0 ? 1.0f - f : f;
