@@ -377,6 +377,11 @@ int mwb_profile_read(mwb_handle* h, double* k1_ms, double* k2_ms, int64_t* k1_la
 int mwb_shared_alloc(int device, size_t bytes, void** dev_ptr, unsigned char handle[64]);
 int mwb_shared_open(int device, const unsigned char handle[64], void** dev_ptr);
 int mwb_shared_close(void* dev_ptr, int opened /* 1: from mwb_shared_open, 0: from mwb_shared_alloc */);
+/* Tell the handle whether the `obs` pointer of the following mwb_step / mwb_render_obs calls is another GPU's memory
+ * (1), local memory (0), or to look it up per pointer (-1, the default).  For a peer destination K2 stages each
+ * frame (or band of a frame) in shared memory and writes it out as address-ordered 16-byte stores, which is what NVLink
+ * needs; for local HBM it stores row segments directly. */
+int mwb_set_obs_peer(mwb_handle* h, int peer);
 
 /* The camera K2 derives for every env, read back for parity tests against the reference's Agent.cam_pos / cam_dir /
  * cam_fov_y (entity.py:476-503) and its gluLookAt / gluPerspective arguments (miniworld.py:1200-1219): per env 16

@@ -118,6 +118,7 @@ struct mwb_handle {
   bool frames_copied;
   int k2_variant;
   int k2_flags;                   // MWB_K2_* measurement switches (env MWB_K2_FLAGS)
+  int obs_peer_hint;              // mwb_set_obs_peer: 1 / 0 = the caller says where observations go, -1 = look it up
   const void* peer_checked;       // last observation pointer whose home device was looked up, and the answer
   bool peer_result;
   bool obs_is_peer;               // this launch's observation buffer lives on another GPU (K2 stages whole frames)
@@ -505,15 +506,19 @@ static int k2_list_bytes(const mwb_handle* h) {
   return (int)L.stage_off;
 }
 static int k2_frame_stage_bytes(const mwb_handle* h) {
-  const size_t bytes = (size_t)h->S.obs_w * h->S.obs_h * 3;
-  if (h->k2_parts != 1 || h->obs_format == MWB_OBS_GREY_F64 || bytes > 16384 || (bytes & 15) != 0) return 0;
-  // Staging the whole frame pays only when the stores leave the GPU (peer memory of rank 0: full 16-byte address-ordered
-  // stores instead of 8-byte row segments, 52 % -> 89 % weak-scaling efficiency on 8 GPUs); for local HBM it costs 6 %.
+  const int W = h->S.obs_w, H = h->S.obs_h, tiles_x = (W + 7) >> 3;
+  // bytes one block stages: the whole frame, or (frames cut into several blocks) its band of whole half-tile rows
+  const size_t rows = h->k2_parts == 1 ? (size_t)H : (size_t)(k2_halves_per_part(W, H, h->k2_parts) / tiles_x) * 4;
+  const size_t bytes = rows * W * 3;
+  if (h->obs_format == MWB_OBS_GREY_F64 || bytes > 16384 || (bytes & 15) != 0 || (W & 7) != 0) return 0;
+  if (h->k2_parts != 1 && (h->obs_format != MWB_OBS_HWC_U8 || (H & 3) != 0)) return 0;
+  // Staging pays only when the stores leave the GPU (peer memory of rank 0: full 16-byte address-ordered stores
+  // instead of 8-byte row segments, 52 % -> 89 % weak-scaling efficiency on 8 GPUs); for local HBM it costs 6 %.
   if ((h->k2_flags & MWB_K2_NO_FRAME_STAGE) || !(h->obs_is_peer || (h->k2_flags & MWB_K2_FORCE_FRAME_STAGE))) return 0;
   // not at the price of a resident block: three blocks per SM (+ 1 KB each for the system) must still fit in 227 KB
   const size_t per_block = (size_t)k2_list_bytes(h) + bytes + (size_t)h->k2_static_smem + 1024;
   if (3 * per_block > 232448) return 0;
-  return (int)bytes;      // a multiple of 16: every env's frame starts 16-byte aligned
+  return (int)bytes;      // a multiple of 16: every band starts 16-byte aligned
 }
 static int k2_smem_bytes(const mwb_handle* h) { return k2_list_bytes(h) + k2_frame_stage_bytes(h); }
 
@@ -578,6 +583,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   h->vis_tris = nullptr;
   h->obs_format = MWB_OBS_HWC_U8;
   h->obs_px_bytes = 3;
+  h->obs_peer_hint = -1;
   h->peer_checked = nullptr;
   h->peer_result = h->obs_is_peer = false;
   h->k2_static_smem = 19456;
@@ -1426,7 +1432,7 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
                      pa.device != h->cfg.device;
     cudaGetLastError();
   }
-  h->obs_is_peer = h->peer_result;
+  h->obs_is_peer = h->obs_peer_hint >= 0 ? h->obs_peer_hint != 0 : h->peer_result;
   const int smem = k2_smem_bytes(h), fstage = k2_frame_stage_bytes(h);
   const K2Layout lay = k2_layout(h->smem_tris, h->tri_cap, h->stage_bytes, k2_halves_per_part(h->S.obs_w, h->S.obs_h, h->k2_parts), fstage);
   if (ensure_k2_smem(h, smem)) return fail(MWB_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
@@ -1564,6 +1570,12 @@ extern "C" int mwb_render_obs(mwb_handle* h, uint8_t* obs, float* depth, void* s
                          obs_host ? obs : nullptr, depth_host ? depth : nullptr);
   if (rc) return rc;
   return finish_outputs(h, obs, obs_host, depth, depth_host, nullptr, nullptr, nullptr, s, stream != nullptr);
+}
+
+extern "C" int mwb_set_obs_peer(mwb_handle* h, int peer) {
+  if (!h) return fail(MWB_EINVAL, "null handle");
+  h->obs_peer_hint = peer ? 1 : 0;
+  return MWB_OK;
 }
 
 extern "C" int mwb_set_obs_format(mwb_handle* h, int format) {

@@ -65,8 +65,12 @@ static inline
 __host__ __device__
 #endif
 int k2_halves_per_part(int W, int H, int parts) {
-  const int n_halves = ((W + 7) >> 3) * ((H + 3) >> 2);
-  return (n_halves + parts - 1) / parts;
+  const int tiles_x = (W + 7) >> 3, n_halves = tiles_x * ((H + 3) >> 2);
+  int per = (n_halves + parts - 1) / parts;
+  // frames cut into several blocks: every part covers whole rows of half-tiles, i.e. a contiguous band of the
+  // frame in memory (what lets the band be staged and written out with ordered 16-byte stores)
+  if (parts > 1) per = (per + tiles_x - 1) / tiles_x * tiles_x;
+  return per;
 }
 
 #ifdef __CUDACC__
@@ -444,8 +448,9 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   const int tiles_x = (W + 7) >> 3;
   const float inv_tiles_x = 1.0f / (float)tiles_x;
   const int halves_y = (H + 3) >> 2;
-  const int n_halves = tiles_x * halves_y, per_part = (n_halves + parts - 1) / parts;
-  const int h_begin = part * per_part, h_end = min(n_halves, h_begin + per_part);
+  const int n_halves = tiles_x * halves_y, per_part = k2_halves_per_part(W, H, parts);
+  const int h_begin = min(n_halves, part * per_part), h_end = min(n_halves, h_begin + per_part);
+  const int band_row0 = (h_begin / tiles_x) << 2;         // first pixel row of this block's band (parts > 1: whole rows)
   for (int hl = tid; hl < h_end - h_begin; hl += THREADS) {
     const int half = h_begin + hl;
     const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;
@@ -685,7 +690,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
           for (int c = 0; c < 3; ++c) fstage[((size_t)c * W + px) * H + py] = rgb[c];
         } else {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) fstage[((size_t)py * W + px) * 3 + c] = rgb[c];
+          for (int c = 0; c < 3; ++c) fstage[((size_t)(py - band_row0) * W + px) * 3 + c] = rgb[c];
         }
       }
     } else if (obs != nullptr) {
@@ -732,11 +737,13 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   }
   if (obs != nullptr && frame_stage_bytes > 0) {
     __syncthreads();
-    const size_t frame = (size_t)W * H * 3;
-    uint8_t* dst = obs + (size_t)i * frame;
-    const int vec = (int)(frame >> 4);
+    // this block's band of the frame (the whole frame when parts == 1; channel-first frames are only staged whole)
+    const int band_rows = min(H, ((h_end + tiles_x - 1) / tiles_x) << 2) - band_row0;
+    const size_t frame = (size_t)W * H * 3, band = (size_t)max(band_rows, 0) * W * 3;
+    uint8_t* dst = obs + (size_t)i * frame + (size_t)band_row0 * W * 3;
+    const int vec = (int)(band >> 4);
     for (int o = tid; o < vec; o += THREADS) reinterpret_cast<uint4*>(dst)[o] = reinterpret_cast<const uint4*>(fstage)[o];
-    for (int o = (vec << 4) + tid; o < (int)frame; o += THREADS) dst[o] = fstage[o];
+    for (int o = (vec << 4) + tid; o < (int)band; o += THREADS) dst[o] = fstage[o];
   }
 }
 

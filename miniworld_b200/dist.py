@@ -100,7 +100,9 @@ class ShardedMiniWorld:
                 handle = self._peer.handle
         except EngineError:
             ok = 0
-        infos = self._exchange((ok, handle, self._rel.handle if self._rel is not None else None))
+        import torch as _t
+        uuid = str(_t.cuda.get_device_properties(dev).uuid) if hasattr(_t.cuda.get_device_properties(dev), "uuid") else str(dev)
+        infos = self._exchange((ok, handle, self._rel.handle if self._rel is not None else None, uuid))
         ok = min(i[0] for i in infos)
         if ok and self.rank != 0:
             try:
@@ -127,6 +129,9 @@ class ShardedMiniWorld:
         self.obs_bufs = [flat[k * obs_bytes:(k + 1) * obs_bytes].view(self.total, H, W, 3) for k in range(2)]
         self.obs_all = self.obs_bufs[0]                             # [total, H, W, 3] in rank 0's HBM
         self.local._ensure_torch()
+        # K2 stages frames for ordered 16-byte stores only when they cross NVLink (two ranks sharing one GPU: local)
+        remote = self.rank != 0 and infos[0][3] != infos[self.rank][3]
+        self.local.engine.set_obs_peer(remote)
         self._peer_step = 0
         base = self._peer.ptr.value + self._flag_off
         self._done_ptr = [base + 128 * r for r in range(self.world)]      # slot r lives in rank 0's memory

@@ -121,7 +121,7 @@ EXPORTS = (
     "mwb_overflow_count", "mwb_shared_alloc", "mwb_shared_open", "mwb_shared_close",
     "mwb_render_top_view", "mwb_visible_ents", "mwb_set_action_noise",
     "mwb_snapshot_size", "mwb_snapshot", "mwb_restore", "mwb_set_obs_format",
-    "mwb_flag_write", "mwb_flag_wait_geq", "mwb_flag_mode", "mwb_state_array", "mwb_debug_camera",
+    "mwb_flag_write", "mwb_flag_wait_geq", "mwb_flag_mode", "mwb_state_array", "mwb_debug_camera", "mwb_set_obs_peer",
 )
 OBS_FORMATS = {"hwc": 0, "cwh": 1, "grey": 2}
 
@@ -183,6 +183,7 @@ def load_library():
     lib.mwb_flag_wait_geq.argtypes = [vp, vp, C.c_uint32]
     lib.mwb_flag_mode.argtypes = []
     lib.mwb_debug_camera.argtypes = [vp, vp]
+    lib.mwb_set_obs_peer.argtypes = [vp, C.c_int]
     lib.mwb_state_array.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
     lib.mwb_overflow_count.argtypes = [vp]
     lib.mwb_overflow_count.restype = C.c_int64
@@ -504,6 +505,10 @@ class Engine:
         class _View:
             __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr.value, False), "version": 3, "strides": None}
         return _View()
+
+    def set_obs_peer(self, peer):
+        """peer: True / False = observations go to another GPU's / this GPU's memory; None = look it up per pointer."""
+        self._check(self.lib.mwb_set_obs_peer(self.h, -1 if peer is None else int(bool(peer))))
 
     def debug_camera(self):
         """float32 [N, 16]: eye, right, up, forward, (cot / aspect, cot), (za, zb) of every env's camera as K2 derives it."""
