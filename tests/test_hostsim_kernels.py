@@ -77,7 +77,7 @@ def test_single_env_levels_follow_reference(hostsim_path, name):
     """Levels outside the batched configs (and PickupObjects for the carry path) through the
     N = 1 engine with the level's own Python rule."""
     from helpers import run_single_env_trajectory
-    run_single_env_trajectory(name, golden(name), hostsim_path, envs=2, steps=100)
+    run_single_env_trajectory(name, golden(name), hostsim_path, envs=2, steps=40 if name == "pickup" else 100)
 
 
 def test_render_mode_and_wrappers_on_host_sim(hostsim_path):
@@ -202,7 +202,7 @@ def test_device_programs_equal_python_levels(hostsim_path, level, dr):
     batched_equals_python_levels(level, hostsim_path, dr, n=2, steps=150)
 
 
-@pytest.mark.parametrize("name,steps", [("hallway", 300), ("fourrooms_dr", 300)])
+@pytest.mark.parametrize("name,steps", [("hallway", 120), ("fourrooms_dr", 150)])
 def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, name, steps):
     """A level class that only names its rule (no `device_program`) still runs batched: worlds are generated by its
     Python `_gen_world()` on the host and uploaded (`mwb_set_world`), the env's numpy stream is handed back and forth

@@ -68,7 +68,8 @@ def test_reference_light_is_directional():
 
 @pytest.mark.parametrize("name", stream_cases())
 def test_hostsim_matches_reference_stream_frames(hostsim_path, name):
-    big = name in ("maze_dr", "pickup_160")
-    st = stream_parity(name, hostsim_path, max_rows=21 if big else 89)
+    # (the CPU build of the kernels is slow on mesh levels: fewer rows there; the GPU test replays every row)
+    rows = {"maze_dr": 21, "pickup_160": 3, "pickup": 34, "pickup_dr": 34}.get(name, 89)
+    st = stream_parity(name, hostsim_path, max_rows=rows)
     assert st["frames"] >= 4 and st["same"] / st["total"] > 0.995
     assert st["cams"] > 0 and st["cam_exact"] / st["cams"] > 0.98
