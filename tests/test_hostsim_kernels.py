@@ -202,7 +202,7 @@ def test_device_programs_equal_python_levels(hostsim_path, level, dr):
     batched_equals_python_levels(level, hostsim_path, dr, n=2, steps=150)
 
 
-@pytest.mark.parametrize("name,steps", [("hallway", 120), ("fourrooms_dr", 150)])
+@pytest.mark.parametrize("name,steps", [("hallway", 260), ("fourrooms_dr", 260)])
 def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, name, steps):
     """A level class that only names its rule (no `device_program`) still runs batched: worlds are generated by its
     Python `_gen_world()` on the host and uploaded (`mwb_set_world`), the env's numpy stream is handed back and forth
@@ -213,7 +213,7 @@ def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, n
     level, dr = CASES[name]
     host_only = type("HostOnly" + LEVELS[level].__name__, (LEVELS[level],), {"device_program": None})
     g = golden(name)
-    n = 4
+    n = 2
     env = BatchedMiniWorld(host_only, n, domain_rand=dr, autoreset=True)
     assert not env.device_reset
     env._host_reset(np.arange(n, dtype=np.int32), [1000 + i for i in range(n)])
@@ -222,8 +222,9 @@ def test_host_reset_fallback_for_levels_without_a_device_program(hostsim_path, n
     out = None
     for t in range(steps):
         out = env.step_host(g["actions"][t, :n], out, render=False)
-        bad = state_mismatches(env, g, t + 1, n, out)
-        assert not bad, "step %d: %s" % (t + 1, "; ".join(bad))
+        if t % 3 == 2 or t >= 245:           # every state around the truncation at step 250 and the reset after it
+            bad = state_mismatches(env, g, t + 1, n, out)
+            assert not bad, "step %d: %s" % (t + 1, "; ".join(bad))
     assert g["was_reset"][1:steps + 1, :n].any()
     env.close()
 
