@@ -40,7 +40,7 @@
 //    counts u16 + lists u16 x MWB_TILE_CAP]      <- one region: the TMA-staged quads are dead once the triangles are set up
 //   [frame stage]
 struct K2Layout {
-  int order_off, zkey_off, slot_off, cnt_off, list_off, stage_off, end;
+  int order_off, zkey_off, slot_off, cnt_off, list_off, tmp_off, stage_off, end;
 };
 static inline
 #ifdef __CUDACC__
@@ -55,7 +55,8 @@ K2Layout k2_layout(bool smem_tris, int tri_cap, int stage_bytes, int halves_per_
   L.slot_off = L.zkey_off + tri_cap * 4;
   L.cnt_off = L.slot_off + cap2 * 2;
   L.list_off = L.cnt_off + ((halves_per_part + 1) & ~1) * 2;
-  const int lists_end = L.list_off + halves_per_part * MWB_TILE_CAP * 2, quads_end = tri_bytes + stage_bytes;
+  L.tmp_off = L.list_off + halves_per_part * MWB_TILE_CAP * 2;      // second builder thread's entries before the merge
+  const int lists_end = L.tmp_off + halves_per_part * MWB_TILE_CAP * 2, quads_end = tri_bytes + stage_bytes;
   L.stage_off = ((lists_end > quads_end ? lists_end : quads_end) + 15) & ~15;
   L.end = L.stage_off + frame_stage_bytes;
   return L;
@@ -304,10 +305,12 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   uint16_t* tri_slot = reinterpret_cast<uint16_t*>(smem_raw + lay.slot_off);     // record position -> slot (draw order)
   uint16_t* tile_cnt = reinterpret_cast<uint16_t*>(smem_raw + lay.cnt_off);      // candidates per half-tile of this part
   uint16_t* tile_list = reinterpret_cast<uint16_t*>(smem_raw + lay.list_off);    // [half-tile][MWB_TILE_CAP] record positions
+  uint16_t* tile_tmp = reinterpret_cast<uint16_t*>(smem_raw + lay.tmp_off);
   // whole-frame RGB stage (frame_stage_bytes > 0): warps drop their pixels here and the block writes the frame
   // out at the end with 16-byte stores in address order
   uint8_t* fstage = smem_raw + lay.stage_off;
   __shared__ double trig[6];
+  __shared__ float ent_cs[MWB_MAX_DRAWN][2];   // (cos, sin) of every entity slot's model rotation (Box form of the angle)
   __shared__ int next_half;
   if (tid == 0) mbar_init(&quad_bar, 1);
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
@@ -319,6 +322,14 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     trig[tid] = (tid & 1) ? mwb_libm::sin_glibc(ang[tid >> 1]) : mwb_libm::cos_glibc(ang[tid >> 1]);
   } else if (tid == 32) {
     fmap = build_frame_map(S, i, view.mode == 1 && view.render_agent != 0);   // meanwhile another warp lays out the draw list
+  } else if (tid >= 64 && tid < 64 + 2 * MWB_MAX_DRAWN) {
+    // ... and two threads per entity slot evaluate the glibc-exact cos / sin of its model rotation, so that the twelve
+    // triangle tasks of a Box do not each repeat them in the set-up phase (they were that phase's stragglers)
+    const int e = (tid - 64) >> 1;
+    if (e < S.num_slots[i] && e < S.E) {
+      const double a = box_rotation_angle(entity_pose(S, i, e).dir);
+      ent_cs[e][tid & 1] = (float)((tid & 1) ? mwb_libm::sin_glibc(a) : mwb_libm::cos_glibc(a));
+    }
   }
   __syncthreads();
   if (tid == 0) cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i, trig);
@@ -332,7 +343,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     const int task = start + tid;
     TriRec rec;
     int keep = 0, seg = 0;
-    if (task < fmap.n_tasks) keep = task_triangle(S, A, cam, fmap, quads, i, task, W, H, rec, seg) ? 1 : 0;
+    if (task < fmap.n_tasks) keep = task_triangle(S, A, cam, fmap, quads, i, task, W, H, rec, seg, ent_cs) ? 1 : 0;
     // quads stay PAIRS: tasks (2k, 2k + 1) are the fan halves of one planar quad (room quad, box face; the map
     // view's marker pairs with nothing).  If either half survives both keep a record -- the culled one an empty record
     // -- so that records / slots (2k, 2k + 1) always belong together (classify_pixel's pair logic relies on it).
@@ -451,24 +462,43 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   const int n_halves = tiles_x * halves_y, per_part = k2_halves_per_part(W, H, parts);
   const int h_begin = min(n_halves, part * per_part), h_end = min(n_halves, h_begin + per_part);
   const int band_row0 = (h_begin / tiles_x) << 2;         // first pixel row of this block's band (parts > 1: whole rows)
-  for (int hl = tid; hl < h_end - h_begin; hl += THREADS) {
-    const int half = h_begin + hl;
-    const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;
-    const int tx0 = hcol << 3, ty0 = hrow << 2;
-    const float fx0 = (float)tx0, fy0 = (float)ty0;
-    int cnt = 0;
-    for (int q = 0; q < n_res; ++q) {
-      const int p = order[q];
-      const TriRec& t = tris[p];
-      const int bx = t.bx, by = t.by;
-      if ((bx & 0xFFFF) > tx0 + 7 || (bx >> 16) < tx0 || (by & 0xFFFF) > ty0 + 3 || (by >> 16) < ty0) continue;
-      if (t.A[0] * fx0 + t.B[0] * fy0 + t.K[0] < 0.0f || t.A[1] * fx0 + t.B[1] * fy0 + t.K[1] < 0.0f ||
-          t.A[2] * fx0 + t.B[2] * fy0 + t.K[2] < 0.0f)
-        continue;
-      if (cnt < MWB_TILE_CAP) tile_list[hl * MWB_TILE_CAP + cnt] = (uint16_t)p;
-      ++cnt;
+  // Two threads (adjacent lanes) per half-tile: the first takes the nearer half of the ranked triangles, the second the
+  // farther half (into a scratch list appended behind the first's), which halves this phase's critical path.
+  {
+    const int n_tiles = h_end - h_begin, mid = (n_res + 1) >> 1;
+    for (int w0 = 0; w0 < 2 * n_tiles; w0 += THREADS) {
+      const int w = w0 + tid, hl = w >> 1, j = w & 1;
+      int cnt = 0;
+      if (hl < n_tiles) {
+        const int half = h_begin + hl;
+        const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;
+        const int tx0 = hcol << 3, ty0 = hrow << 2;
+        const float fx0 = (float)tx0, fy0 = (float)ty0;
+        uint16_t* dst = (j ? tile_tmp : tile_list) + hl * MWB_TILE_CAP;
+        const int q1 = j ? n_res : mid;
+        for (int q = j ? mid : 0; q < q1; ++q) {
+          const int p = order[q];
+          const TriRec& t = tris[p];
+          const int bx = t.bx, by = t.by;
+          if ((bx & 0xFFFF) > tx0 + 7 || (bx >> 16) < tx0 || (by & 0xFFFF) > ty0 + 3 || (by >> 16) < ty0) continue;
+          if (t.A[0] * fx0 + t.B[0] * fy0 + t.K[0] < 0.0f || t.A[1] * fx0 + t.B[1] * fy0 + t.K[1] < 0.0f ||
+              t.A[2] * fx0 + t.B[2] * fy0 + t.K[2] < 0.0f)
+            continue;
+          if (cnt < MWB_TILE_CAP) dst[cnt] = (uint16_t)p;
+          ++cnt;
+        }
+      }
+      const int other = __shfl_xor_sync(0xffffffffu, cnt, 1);      // (THREADS is a multiple of 32: whole warps get here)
+      if (hl < n_tiles) {
+        if (j) {                                  // append behind the first thread's entries
+          uint16_t* lst = tile_list + hl * MWB_TILE_CAP;
+          const uint16_t* src = tile_tmp + hl * MWB_TILE_CAP;
+          for (int k = 0; k < cnt && other + k < MWB_TILE_CAP; ++k) lst[other + k] = src[k];
+        } else {
+          tile_cnt[hl] = (uint16_t)min(cnt + other, 0xFFFF);
+        }
+      }
     }
-    tile_cnt[hl] = (uint16_t)min(cnt, 0xFFFF);
   }
   __syncthreads();
 

@@ -916,8 +916,15 @@ MWB_DEV void box_corner(int f, int v, int& sx, int& top, int& sz) {
   sz = Z[f][v];
 }
 
-// triangle t (0..11) of a Box: face t / 2 in drawBox order, fan half t % 2
-MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput& in) {
+// the angle model_rotation takes the cosine / sine of, for the Box / frame form of the degrees (see model_rotation)
+MWB_DEV double box_rotation_angle(double dir) {
+  const double deg = d_mul(dir, 57.29577951308232);
+  return d_div(d_mul((double)(float)deg, 3.141592653589793), 180.0);
+}
+
+// triangle t (0..11) of a Box: face t / 2 in drawBox order, fan half t % 2.  cs: the box's (cos, sin) if the caller
+// already has them (K2 evaluates every entity's pair once per frame, in parallel with the camera's), else null
+MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput& in, const float* cs = nullptr) {
   const int f = t >> 1, half = t & 1;
   const double ex = P.size > 0.0 ? P.size : pr.size[0], ey = P.size > 0.0 ? P.size : pr.size[1],
                ez = P.size > 0.0 ? P.size : pr.size[2];
@@ -925,7 +932,12 @@ MWB_DEV void box_triangle(const mwb_proto& pr, const EntPose& P, int t, TriInput
   const float NX[6] = {0, 0, -1, 1, 0, 0}, NY[6] = {0, 0, 0, 0, 1, -1}, NZ[6] = {1, -1, 0, 0, 0, 0};
   // glTranslatef(pos) * glRotatef(dir in degrees, 0, 1, 0): x' = x c + z s, z' = z c - x s
   float c, s;
-  model_rotation(P.dir, 0, c, s);
+  if (cs != nullptr) {
+    c = cs[0];
+    s = cs[1];
+  } else {
+    model_rotation(P.dir, 0, c, s);
+  }
   const float tx = (float)P.x, ty = (float)P.y, tz = (float)P.z;
   const float nx = f_add(f_mul(NX[f], c), f_mul(NZ[f], s)), ny = NY[f], nz = f_sub(f_mul(NZ[f], c), f_mul(NX[f], s));
 #pragma unroll
@@ -1022,7 +1034,8 @@ MWB_DEV const mwb_quad* env_quads(const DevState& S, int i) { return S.quads + (
 
 // shared-memory triangle task -> (segment, record); false if culled / nonexistent
 MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camera& cam, const FrameMap& m,
-                           const mwb_quad* quads, int i, int task, int W, int H, TriRec& out, int& seg) {
+                           const mwb_quad* quads, int i, int task, int W, int H, TriRec& out, int& seg,
+                           const float (*ent_cs)[2] = nullptr) {
   TriInput in;
   if (task < 2 * m.n_quads) {
     seg = 0;
@@ -1034,7 +1047,8 @@ MWB_DEV bool task_triangle(const DevState& S, const RenderAssets& A, const Camer
     int k = 0;
     while (k + 1 < m.n_ents && (m.ent_task0[k] < 0 || task >= m.ent_task0[k] + 12)) ++k;
     seg = 1 + k;
-    box_triangle(S.protos[m.ent_proto[k]], entity_pose(S, i, m.ent_slot[k]), task - m.ent_task0[k], in);
+    box_triangle(S.protos[m.ent_proto[k]], entity_pose(S, i, m.ent_slot[k]), task - m.ent_task0[k], in,
+                 ent_cs != nullptr ? ent_cs[m.ent_slot[k]] : nullptr);
   }
   return finish_triangle(cam, in, W, H, out);
 }
