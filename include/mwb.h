@@ -360,7 +360,8 @@ int mwb_restore(mwb_handle* h, const void* blob, size_t bytes);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mwb_launch_count(mwb_handle* h);
 
-/* frames whose culled triangle list did not fit the kernel's shared-memory budget (must stay 0) */
+/* capacity faults (must stay 0): frames whose culled triangle list did not fit the kernel's budget, device-side maze
+ * generation that ran out of room / quad / segment capacity (the env is left empty instead of searching forever) */
 int64_t mwb_overflow_count(mwb_handle* h);
 
 /* Device-side timing of the two kernels: when enabled, every K1 / K2 launch is bracketed by

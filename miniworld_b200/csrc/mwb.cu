@@ -206,9 +206,19 @@ static int stream_leave(mwb_handle*, stream_t) { return 0; }
 #endif
 
 // ------------------------------------------------------------------ kernels / loops
+// K1 runs an env's scalar logic on all 32 lanes of a warp with identical values (every store writes the same value).
+// The read-modify-write sequences on per-env state (step counter, RNG stream, entity list edits) rely on the lanes
+// not drifting apart between the loads and the stores: explicit warp barriers pin that down.
+#ifdef __CUDA_ARCH__
+#define MWB_WARP_SYNC() __syncwarp()
+#else
+#define MWB_WARP_SYNC()
+#endif
+
 MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const double* step_params, double* reward,
                       uint8_t* term, uint8_t* trunc) {
   StepOut o;
+  MWB_WARP_SYNC();
   const int nr = S.needs_reset[i];
   if (nr == 2 || (nr == 1 && S.autoreset)) {
     // "next-step" auto-reset: this step performs the reset instead of stepping.  nr == 2: the
@@ -223,7 +233,9 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
     if (S.act_noise) {            // wrapper.action() runs before env.step() draws its three parameters
       NpRng r = load_rng(S, i);
       if (!(rng_uniform(r, 0.0, 1.0) < S.act_prob)) action = S.act_random >= 0 ? S.act_random : (int)rng_integers(r, 6u);
+      MWB_WARP_SYNC();
       store_rng(S, i, r);
+      MWB_WARP_SYNC();
     }
     double fs, fd, ts;
     if (step_params) {
@@ -235,7 +247,9 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
       fs = rng_uniform(r, S.params.forward_step_lo, S.params.forward_step_rng);
       fd = rng_uniform(r, S.params.forward_drift_lo, S.params.forward_drift_rng);
       ts = rng_uniform(r, S.params.turn_step_lo, S.params.turn_step_rng);
+      MWB_WARP_SYNC();
       store_rng(S, i, r);
+      MWB_WARP_SYNC();
     } else {
       fs = S.params.forward_step;
       fd = S.params.forward_drift;
@@ -251,6 +265,7 @@ MWB_DEV void step_one(const DevState& S, int i, const int32_t* actions, const do
 #endif
     }
   }
+  MWB_WARP_SYNC();
   if (reward) reward[i] = o.reward;
   if (term) term[i] = (uint8_t)o.terminated;
   if (trunc) trunc[i] = (uint8_t)o.truncated;
@@ -647,6 +662,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (!rc) rc = alloc_arr(h, &h->d_depth, N * (size_t)S.obs_w * S.obs_h);
   if (!rc) rc = alloc_arr(h, &h->d_ids, N);
   if (!rc) rc = alloc_arr(h, &h->d_overflow, 1);
+  S.fault = h->d_overflow;
   if (!rc) rc = alloc_arr(h, &h->d_upload, N);
   if (rc) {
     mwb_destroy(h);

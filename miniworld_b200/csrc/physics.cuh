@@ -211,6 +211,9 @@ MWB_DEV StepOut physics_step(const DevState& S, int i, int action, double fwd_st
   const double ar = S.protos[S.ent_proto[as * N + i]].radius;   // Agent.radius (0.4 unless the level changes it)
   int carrying = S.carrying[i];
   int sc = S.step_count[i] + 1;
+#ifdef __CUDA_ARCH__
+  __syncwarp();                 // every lane has read the counter before any lane writes it back
+#endif
   S.step_count[i] = sc;
   S.ghost_slot[i] = -1;
 

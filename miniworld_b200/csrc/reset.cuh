@@ -56,7 +56,19 @@ MWB_DEV void device_reset(const DevState& S, int i) {
     const mwb_op& op = S.ops[pc];
     if (op.op == MWB_OP_END) break;
     if (op.op == MWB_OP_MAZE) {          // per-episode topology: regenerate this env's rooms
-      if (S.maze != nullptr && !S.shared_geom && maze_generate(S, *S.maze, S.maze_cdf, i, rng)) n_rooms = S.num_rooms[g];
+      if (S.maze != nullptr && !S.shared_geom && maze_generate(S, *S.maze, S.maze_cdf, i, rng)) {
+        n_rooms = S.num_rooms[g];
+      } else {
+        // out of capacity (unreachable when the host sized the handle from a generated maze, mwb_set_maze): placing
+        // entities into stale geometry could search forever, so the env is left empty and the fault is counted
+#ifdef __CUDA_ARCH__
+        if ((threadIdx.x & 31) == 0) atomicAdd(S.fault, 1);
+#else
+        *S.fault += 1;
+#endif
+        store_rng(S, i, rng);
+        return;
+      }
       continue;
     }
     if (op.op == MWB_OP_IFEQ) {
