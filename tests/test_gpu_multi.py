@@ -75,10 +75,12 @@ def test_peer_observation_buffer_equals_gather(libmwb_path, total, steps):
     env.close()
 
 
-def _worker_one_gpu(rank, world, port, total, steps, q, flag_mode):
+def _worker_one_gpu(rank, world, port, total, steps, q, flag_mode, level="MiniWorld-FourRooms-v0", size=(80, 60), staged=False):
     """Two processes on cuda:0: the peer buffer crosses a process boundary (CUDA IPC), not a GPU boundary."""
     sys.path.insert(0, ROOT)
     os.environ["MWB_FLAG_MODE"] = flag_mode
+    if staged:
+        os.environ["MWB_K2_FLAGS"] = "11"       # lists | pairs | force the frame stage although the destination is local
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -86,7 +88,8 @@ def _worker_one_gpu(rank, world, port, total, steps, q, flag_mode):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from miniworld_b200.dist import ShardedMiniWorld
     acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)
-    env = ShardedMiniWorld("MiniWorld-FourRooms-v0", total, dist=dist, device=0)
+    env = ShardedMiniWorld(level, total, dist=dist, device=0, obs_width=size[0], obs_height=size[1])
+    acts_all = np.random.default_rng(5).integers(0, env.local.action_space.n, size=(steps, total), dtype=np.int32)
     env.reset(1000)
     ok = env.enable_peer_obs()
     frames = []
@@ -125,6 +128,37 @@ def test_peer_observation_buffer_two_processes_one_gpu(libmwb_path, total, steps
     env = BatchedMiniWorld("MiniWorld-FourRooms-v0", total)
     env.reset(seed=1000)
     acts_all = np.random.default_rng(5).integers(0, 3, size=(steps, total), dtype=np.int32)
+    for t in range(steps):
+        obs = env.step(torch.as_tensor(acts_all[t], device="cuda"))[0]
+        assert np.array_equal(obs.cpu().numpy(), frames[t]), "step %d" % t
+    env.close()
+
+
+@pytest.mark.parametrize("level,size,total", [("MiniWorld-FourRooms-v0", (80, 60), 64), ("MiniWorld-FourRooms-v0", (80, 60), 2048),
+                                              ("MiniWorld-PickupObjects-v0", (160, 120), 24)])
+def test_staged_peer_stores_on_one_gpu(libmwb_path, level, size, total):
+    """The store shape K2 uses towards another GPU -- the frame, or the block's band of whole half-tile rows when a
+    frame is cut into several blocks (80x60 at small N: 3-row bands; 160x120: 8-row bands), collected in shared memory
+    and written as address-ordered 16-byte stores -- forced on for a local destination, so that a one-GPU box
+    exercises it: two ranks on cuda:0 must reproduce the single-process frames."""
+    import torch
+    import torch.multiprocessing as mp
+    steps = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29750 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_one_gpu, args=(r, 2, port, total, steps, q, "memop", level, size, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, mode, frames = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
+    from miniworld_b200.batched import BatchedMiniWorld
+    env = BatchedMiniWorld(level, total, obs_width=size[0], obs_height=size[1])
+    env.reset(seed=1000)
+    acts_all = np.random.default_rng(5).integers(0, env.action_space.n, size=(steps, total), dtype=np.int32)
     for t in range(steps):
         obs = env.step(torch.as_tensor(acts_all[t], device="cuda"))[0]
         assert np.array_equal(obs.cpu().numpy(), frames[t]), "step %d" % t
