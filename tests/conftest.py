@@ -56,6 +56,13 @@ def softgl_lib():
     return softgl
 
 
+_golden_cache = {}
+
+
 def golden(name):
+    """Golden trajectory as a dict of arrays (an NpzFile would decompress an array again on every access)."""
     import numpy as np
-    return np.load(os.path.join(GOLDEN, "traj_%s.npz" % name))
+    if name not in _golden_cache:
+        with np.load(os.path.join(GOLDEN, "traj_%s.npz" % name)) as z:
+            _golden_cache[name] = {k: z[k] for k in z.files}
+    return _golden_cache[name]

@@ -335,7 +335,8 @@ def stream_parity(name, lib_path=None, max_rows=None, check_views=True):
     which the picked-up object is still drawn although the level's step() already removed it from the entity list."""
     import os
     from conftest import GOLDEN, golden
-    s = np.load(os.path.join(GOLDEN, "stream_%s.npz" % name))
+    with np.load(os.path.join(GOLDEN, "stream_%s.npz" % name)) as z:
+        s = {k: z[k] for k in z.files}
     traj = str(s["meta"][2])
     g = golden(traj)
     H, W = s["rgb"].shape[1:3]

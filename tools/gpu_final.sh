@@ -13,6 +13,6 @@ d=json.load(open("gpurun_out/final_bench.json")); r=d["roofline"]
 print("value=%.0f e2e=%.0f k2=%.4f k1=%.4f frac=%.4f cpu=%s launches=%s clocks=%s" % (d["value"], d["e2e"]["value"], r["kernel_avg_ms"], r["k1_avg_ms"], r["frac"], d["cpu_baseline"]["value"], d["gpu_launches"], d["clocks"]))
 PY
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/final_bench_reference.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/final_bench_reference.json')); print('reference arm: %.0f env-steps/s on %d cores (%.0f per core)' % (d['value'], d['cpu_baseline']['cores'], d['config']['per_core']))"
+import json; d=json.load(open('gpurun_out/final_bench_reference.json')); print('reference arm: %.0f env-steps/s on %d cores (%.0f per core)' % (d['value'], d['cpu_baseline']['cores'], d['config']['per_physical_core']))"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > /dev/null 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 4 -c 1 -f -o gpurun_out/prof_k2_final python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_final.log 2>&1; echo "ncu rc=$?"
