@@ -384,12 +384,32 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
     std::vector<TriRec> tris;
     TriRec rec;
     int seg;
-    for (int task = 0; task < 2 * fm.n_quads; ++task)
-      if (task_triangle(S, A, cam, fm, env_quads(S, i), i, task, W, H, rec, seg)) tris.push_back(rec);
+    // Like K2, quads stay PAIRS in adjacent records (the culled half of a pair keeps an empty record) so that the
+    // quad-pair logic of classify_pixel is exercised here too; `pairable[j]` marks records that belong to such a pair.
+    std::vector<char> pairable;
+    auto push_pair = [&](int task0) {
+      TriRec a, b;
+      int sg;
+      const bool ka = task_triangle(S, A, cam, fm, env_quads(S, i), i, task0, W, H, a, sg);
+      const bool kb = task_triangle(S, A, cam, fm, env_quads(S, i), i, task0 + 1, W, H, b, sg);
+      if (!ka && !kb) return;
+      if (tris.size() & 1) {               // pairs start at even positions (a mesh list may have left an odd count)
+        TriRec e;
+        empty_record(e);
+        tris.push_back(e);
+        pairable.push_back(0);
+      }
+      if (!ka) empty_record(a);
+      if (!kb) empty_record(b);
+      tris.push_back(a);
+      tris.push_back(b);
+      pairable.push_back(1);
+      pairable.push_back(1);
+    };
+    for (int task = 0; task < 2 * fm.n_quads; task += 2) push_pair(task);
     for (int k = 0; k < fm.n_ents; ++k) {
       if (fm.ent_kind[k] == MWB_KIND_BOX) {
-        for (int t = 0; t < 12; ++t)
-          if (task_triangle(S, A, cam, fm, env_quads(S, i), i, fm.ent_task0[k] + t, W, H, rec, seg)) tris.push_back(rec);
+        for (int t = 0; t < 12; t += 2) push_pair(fm.ent_task0[k] + t);
       } else {
         const mwb_proto& pr = S.protos[fm.ent_proto[k]];
         const EntPose P = entity_pose(S, i, fm.ent_slot[k]);
@@ -398,11 +418,18 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
         for (int t = 0; t < A.meshes[pr.mesh_id].count; ++t) {
           TriInput in;
           mesh_triangle(A, pr, P, c, s, t, in);
-          if (finish_triangle(cam, in, W, H, rec)) tris.push_back(rec);
+          if (finish_triangle(cam, in, W, H, rec)) {
+            tris.push_back(rec);
+            pairable.push_back(0);
+          }
         }
       }
     }
-    if (fm.agent_task >= 0 && task_triangle(S, A, cam, fm, env_quads(S, i), i, fm.agent_task, W, H, rec, seg)) tris.push_back(rec);
+    if (fm.agent_task >= 0 && task_triangle(S, A, cam, fm, env_quads(S, i), i, fm.agent_task, W, H, rec, seg)) {
+      tris.push_back(rec);
+      pairable.push_back(0);
+    }
+    const bool use_pairs = !getenv("MWB_HS_NOPAIRS");
     // test-only experiment: visit triangles front to back (MWB_HS_SORT=1); slots keep draw order
     std::vector<int> order(tris.size());
     for (size_t j = 0; j < tris.size(); ++j) order[j] = (int)j;
@@ -455,9 +482,11 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
           const int j = order[jj];
           const TriRec& t = tris[j];
           if ((t.bx & 0xFFFF) > px || (t.bx >> 16) < px || (t.by & 0xFFFF) > py || (t.by >> 16) < py) continue;
-          if (classify_pixel<MSAA>(load_class(&t), j, px, py, P) == 0) continue;
-          if (P.mode == MWB_PX_LAZY) {     // materialise the lazily held triangle first
+          const TriRec* partner = use_pairs && pairable[j] ? &tris[j ^ 1] : nullptr;
+          if (classify_pixel<MSAA>(load_class(&t), j, px, py, P, partner, (j & 1) ? 1 : 2) == 0) continue;
+          if (P.mode == MWB_PX_LAZY) {     // materialise the lazily held triangle (both halves of a lazily held pair) first
             raster_pixel<MSAA>(load_hot(&tris[P.lazy_slot]), P.lazy_slot, px, py, P.keys, P.kmax);
+            if (lazy_is_pair(P)) raster_pixel<MSAA>(load_hot(&tris[P.lazy_slot ^ 1]), P.lazy_slot ^ 1, px, py, P.keys, P.kmax);
           }
           P.mode = MWB_PX_EXPLICIT;
           raster_pixel<MSAA>(load_hot(&t), j, px, py, P.keys, P.kmax);
@@ -470,7 +499,12 @@ static void hostsim_render_t(const DevState& S, const RenderAssets& A, const Vie
           shade_pixel(A, t, px, py, c);
           uint8_t rgb[3] = {to_unorm8(c[0]), to_unorm8(c[1]), to_unorm8(c[2])};
           if (obs) memcpy(obs + (((size_t)i * H + py) * W + px) * 3, rgb, 3);
-          code0 = sample0_code<MSAA>(t, px, py);
+          int owner = P.lazy_slot;
+          if (lazy_is_pair(P)) {           // which half of the quad owns sample 0: its diagonal edge decides
+            const float xs = (float)px + sample_x<MSAA>(0), ys = (float)py + sample_y<MSAA>(0);
+            if (!pair_sample_in_first(t, (P.lazy_slot & 1) ? 1 : 2, xs, ys)) owner = P.lazy_slot ^ 1;
+          }
+          code0 = sample0_code<MSAA>(tris[owner], px, py);
         } else {
           if (obs) {
             uint8_t rgb[3];
