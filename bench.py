@@ -234,11 +234,11 @@ def run_reference_arm(args):
         return
     from oracle import softgl
     softgl.build()
-    # one worker pinned to every logical CPU this process may use (hyper-threads included: on this box 2 x 64 workers
-    # produce more frames than 64); the per-physical-core figure is reported beside the total
-    cpus = sorted(os.sched_getaffinity(0))
+    # one worker pinned to every PHYSICAL core: measured on the 2 x 32-core box, 64 pinned workers deliver 7.3 k
+    # env-steps/s, 128 (one per hyper-thread) only 5.0 k -- the port is cache / memory bound under full load
+    cpus = physical_cores()
     cores = len(cpus)
-    n_phys = max(1, len(physical_cores()))
+    n_phys = cores
     # the K "steps" are K equal slices of one continuous run (each slice a bounded sample of
     # the workload); W warm-up slices are discarded.  Whole arm <= ~2 minutes.
     slice_s = min(1.0, 100.0 / max(1, args.steps + args.warmup))
@@ -251,12 +251,13 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
         "config": {"workload": "%s 80x60 RGB+depth, random actions, auto-reset" % LEVEL, "n_envs": cores,
                    "note": "reference Pyglet/GL path cannot run on this box (no pyglet/GL/gymnasium, no libEGL/libGL); "
-                           "CPU oracle port timed instead, one env process pinned to each logical CPU",
+                           "CPU oracle port timed instead, one env process pinned to each physical core "
+                           "(its best configuration: one per hyper-thread is slower)",
                    "per_worker": value / cores, "physical_cores": n_phys, "per_physical_core": value / n_phys,
                    "reference_python_physics_only": ref_physics},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d env-steps total in %.0f s on %d pinned processes (one env each, one per logical CPU), "
-                                   "%.0f per physical core" % (vals, budget, cores, value / n_phys)},
+                         "sample": "%d env-steps total in %.0f s on %d pinned processes (one env each, one per physical core), "
+                                   "%.0f per core" % (vals, budget, cores, value / n_phys)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
