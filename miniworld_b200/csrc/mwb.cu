@@ -684,7 +684,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   AL(rng_s_hi, N); AL(rng_s_lo, N); AL(rng_inc_hi, N); AL(rng_inc_lo, N); AL(rng_has32, N); AL(rng_cache, N);
   AL(num_rooms, G); AL(num_quads, G); AL(num_segs, G);
   AL(rooms, G * S.R); AL(quads, G * S.Q + 2); AL(segs, G * S.S); AL(room_tex, N * S.R * 3);
-  AL(mesh_seg, N * E);
+  AL(mesh_seg, N * E); AL(cam_trig, 6 * N); AL(ent_cs, E * 2 * N);
 #undef AL
   if (!rc) rc = alloc_arr(h, &h->d_actions, N);
   if (!rc) rc = alloc_arr(h, &h->d_step_params, 3 * N);
@@ -1513,6 +1513,12 @@ static int launch_render(mwb_handle* h, uint8_t* obs, float* depth, stream_t s, 
                          float* host_depth = nullptr) {
   if (!h->A.tex) return fail(MWB_ESTATE, "textures not uploaded");
 #ifndef MWB_HOSTSIM
+  {
+    const long long threads = (long long)h->S.N * (6 + 2 * h->S.E);
+    frame_trig_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(h->S);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
   if (h->S.mesh_cap > 0) {
     mesh_setup_kernel<<<dim3(h->S.N, h->S.E), 256, 0, s>>>(h->S, h->A, h->view);
     h->launches++;

@@ -105,6 +105,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- per-frame trigonometry: thread (env i, k): k < 6 the camera's cos / sin, else entity slot (k - 6) / 2 -----------
+__global__ void frame_trig_kernel(DevState S) {
+  const int per = 6 + 2 * S.E;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)S.N * per) return;
+  const int k = (int)(g / S.N), i = (int)(g % S.N);       // env index fastest: coalesced state reads and stores
+  const size_t N = S.N;
+  if (k < 6) {
+    double ang[3];
+    camera_angles(S, i, ang);
+    S.cam_trig[(size_t)k * N + i] = (k & 1) ? mwb_libm::sin_glibc(ang[k >> 1]) : mwb_libm::cos_glibc(ang[k >> 1]);
+    return;
+  }
+  const int e = (k - 6) >> 1, j = (k - 6) & 1;
+  const int p = e == S.ghost_slot[i] ? S.ghost_proto[i] : (e < S.num_slots[i] ? S.ent_proto[e * N + i] : -1);
+  if (p < 0) return;
+  const double dir = entity_pose(S, i, e).dir;
+  const double deg = S.protos[p].deg_form ? d_div(d_mul(dir, 180.0), 3.141592653589793) : d_mul(dir, 57.29577951308232);
+  const double rad = d_div(d_mul((double)(float)deg, 3.141592653589793), 180.0);      // as model_rotation
+  S.ent_cs[((size_t)e * 2 + j) * N + i] = (float)(j ? mwb_libm::sin_glibc(rad) : mwb_libm::cos_glibc(rad));
+}
+
 // ---- mesh pre-pass: block (env i, entity slot e) sets up that entity's triangles ----------
 __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAssets A, ViewSpec view) {
   const int i = blockIdx.x, e = blockIdx.y;
@@ -120,15 +142,20 @@ __global__ void __launch_bounds__(256) mesh_setup_kernel(DevState S, RenderAsset
     return;
   }
   if (tid == 0) {
-    cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i);
+    if (view.mode == 1) {
+      cam = make_top_camera(S, i, view);
+    } else {
+      double trig[6];
+      for (int k = 0; k < 6; ++k) trig[k] = S.cam_trig[(size_t)k * N + i];
+      cam = make_camera(S, i, trig);
+    }
     box[0] = box[1] = 0x7fffffff;
     box[2] = box[3] = -1;
   }
   __syncthreads();
   const mwb_proto& pr = S.protos[p];
   const EntPose P = entity_pose(S, i, e);
-  float c, s;
-  model_rotation(P.dir, pr.deg_form, c, s);
+  const float c = S.ent_cs[((size_t)e * 2 + 0) * N + i], s = S.ent_cs[((size_t)e * 2 + 1) * N + i];   // frame_trig_kernel
   const int ntris = A.meshes[pr.mesh_id].count;
   TriRec* out = S.mesh_tris + ((size_t)i * S.E + e) * S.mesh_cap;
   uint2* out_bbox = S.mesh_bbox + ((size_t)i * S.E + e) * S.mesh_cap;
@@ -316,20 +343,14 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
   if (tid == 0 && staged) tma_bulk_g2s(squads, gquads, quad_bytes, &quad_bar);
-  if (tid < 6) {                       // six independent glibc-exact sin / cos evaluations, one per thread
-    double ang[3];
-    camera_angles(S, i, ang);
-    trig[tid] = (tid & 1) ? mwb_libm::sin_glibc(ang[tid >> 1]) : mwb_libm::cos_glibc(ang[tid >> 1]);
+  if (tid < 6) {                       // the camera's cos / sin (glibc-exact, evaluated by frame_trig_kernel)
+    trig[tid] = S.cam_trig[(size_t)tid * S.N + i];
   } else if (tid == 32) {
     fmap = build_frame_map(S, i, view.mode == 1 && view.render_agent != 0);   // meanwhile another warp lays out the draw list
   } else if (tid >= 64 && tid < 64 + 2 * MWB_MAX_DRAWN) {
-    // ... and two threads per entity slot evaluate the glibc-exact cos / sin of its model rotation, so that the twelve
-    // triangle tasks of a Box do not each repeat them in the set-up phase (they were that phase's stragglers)
+    // ... and the (cos, sin) of every entity slot's model rotation, for the twelve triangle tasks of each Box
     const int e = (tid - 64) >> 1;
-    if (e < S.num_slots[i] && e < S.E) {
-      const double a = box_rotation_angle(entity_pose(S, i, e).dir);
-      ent_cs[e][tid & 1] = (float)((tid & 1) ? mwb_libm::sin_glibc(a) : mwb_libm::cos_glibc(a));
-    }
+    if (e < S.num_slots[i] && e < S.E) ent_cs[e][tid & 1] = S.ent_cs[((size_t)e * 2 + (tid & 1)) * S.N + i];
   }
   __syncthreads();
   if (tid == 0) cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i, trig);

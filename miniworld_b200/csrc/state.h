@@ -71,6 +71,11 @@ struct DevState {
   uint16_t* mesh_bin_idx;       // [N][E][MWB_BIN_REFS * mesh_cap]
   int32_t* mesh_bin_off;        // [N][E][MWB_MAX_BINS + 1]
   int32_t mesh_cap;             // 0 = the level has no mesh entities
+  // per-frame trigonometry, written by frame_trig_kernel right before every render launch: the glibc-exact
+  // cos / sin of the camera's three angles and of every entity slot's model rotation (one thread each), so that
+  // neither K2's nor mesh_setup_kernel's blocks wait for a thread that evaluates them
+  double* cam_trig;             // [6][N]  cos, sin of heading, pitch, half field of view
+  float* ent_cs;                // [E][2][N]  cos, sin of the slot's glRotatef angle (the form its prototype's render() uses)
   const float* depth_lut;       // [65536] depth16 code -> metres (depth_code_to_metres of every code), or null
   TriRec* room_tris;            // [N][tri_cap] room + box triangle lists in HBM for levels whose lists do
                                 //   not fit shared memory (Maze); null = lists live in shared memory
