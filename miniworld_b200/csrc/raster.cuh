@@ -336,15 +336,21 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   // whole-frame RGB stage (frame_stage_bytes > 0): warps drop their pixels here and the block writes the frame
   // out at the end with 16-byte stores in address order
   uint8_t* fstage = smem_raw + lay.stage_off;
-  __shared__ double trig[6];
   __shared__ float ent_cs[MWB_MAX_DRAWN][2];   // (cos, sin) of every entity slot's model rotation (Box form of the angle)
   __shared__ int next_half;
   if (tid == 0) mbar_init(&quad_bar, 1);
   if (tid < MWB_MAX_SEGS) seg_count[tid] = 0;
   __syncthreads();
   if (tid == 0 && staged) tma_bulk_g2s(squads, gquads, quad_bytes, &quad_bar);
-  if (tid < 6) {                       // the camera's cos / sin (glibc-exact, evaluated by frame_trig_kernel)
-    trig[tid] = S.cam_trig[(size_t)tid * S.N + i];
+  if (tid == 0) {                      // the camera, from the glibc-exact cos / sin frame_trig_kernel evaluated
+    if (view.mode == 1) {
+      cam = make_top_camera(S, i, view);
+    } else {
+      double tr[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tr[k] = S.cam_trig[(size_t)k * S.N + i];
+      cam = make_camera(S, i, tr);
+    }
   } else if (tid == 32) {
     fmap = build_frame_map(S, i, view.mode == 1 && view.render_agent != 0);   // meanwhile another warp lays out the draw list
   } else if (tid >= 64 && tid < 64 + 2 * MWB_MAX_DRAWN) {
@@ -353,10 +359,16 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     if (e < S.num_slots[i] && e < S.E) ent_cs[e][tid & 1] = S.ent_cs[((size_t)e * 2 + (tid & 1)) * S.N + i];
   }
   __syncthreads();
-  if (tid == 0) cam = view.mode == 1 ? make_top_camera(S, i, view) : make_camera(S, i, trig);
-  __syncthreads();
   if (staged) mbar_wait(&quad_bar, 0);
   const mwb_quad* quads = staged ? squads : gquads;
+
+  // half-tiles of this block (a frame is cut into `parts` bands of whole half-tile rows)
+  const int tiles_x = (W + 7) >> 3;
+  const float inv_tiles_x = 1.0f / (float)tiles_x;
+  const int halves_y = (H + 3) >> 2;
+  const int n_halves = tiles_x * halves_y, per_part = k2_halves_per_part(W, H, parts);
+  const int h_begin = min(n_halves, part * per_part), h_end = min(n_halves, h_begin + per_part);
+  const int band_row0 = (h_begin / tiles_x) << 2;         // first pixel row of this block's band (parts > 1: whole rows)
 
   // ---- B. room + box triangles -> shared memory, draw order preserved
   int ntris = 0;
@@ -400,7 +412,15 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
     ntris += total;
     __syncthreads();
   }
+  const int n_res = ntris < tri_cap ? ntris : tri_cap;
+  // (while thread 0 fills the segment table, everybody computes the depth keys of the visiting order: neither needs the other)
+  for (int t = tid; t < n_res; t += THREADS) {
+    const TriRec& T = tris[t];
+    const float x0 = (float)(T.bx & 0xFFFF), x1 = (float)((T.bx >> 16) + 1), y0 = (float)(T.by & 0xFFFF), y1 = (float)((T.by >> 16) + 1);
+    zkey[t] = T.Zc + fminf(T.Za * x0, T.Za * x1) + fminf(T.Zb * y0, T.Zb * y1);
+  }
   if (tid == 0) {
+    if (DYN) next_half = h_begin + WARPS;
     if (ntris > tri_cap) atomicAdd(overflow, 1);
     // segment table: smem-resident lists are contiguous in draw order; mesh lists live in HBM
     int smem_pos = 0, slot = 0;
@@ -439,12 +459,8 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   // ---- visiting order of the block-resident triangles (rooms, boxes, the map view's marker): front to back by
   // their nearest possible depth, so that the conservative occlusion tests fire early (the image does not depend
   // on the order: per sample the result is the minimum over (depth code, slot))
-  const int n_res = ntris < tri_cap ? ntris : tri_cap;
   {
     for (int t = tid; t < n_res; t += THREADS) {
-      const TriRec& T = tris[t];
-      const float x0 = (float)(T.bx & 0xFFFF), x1 = (float)((T.bx >> 16) + 1), y0 = (float)(T.by & 0xFFFF), y1 = (float)((T.by >> 16) + 1);
-      zkey[t] = T.Zc + fminf(T.Za * x0, T.Za * x1) + fminf(T.Zb * y0, T.Zb * y1);
       // slot of record t: the records of one list are contiguous, in draw order
       int slot = t;
       for (int k = 0; k < nsegs; ++k) {
@@ -455,7 +471,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
       }
       tri_slot[t] = (uint16_t)slot;
     }
-    __syncthreads();
     if (n_res <= MWB_SORT_LIMIT) {
       for (int t = tid; t < n_res; t += THREADS) {
         const float z = zkey[t];
@@ -477,12 +492,6 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   // used to repeat per 32-triangle chunk is done once per (triangle, half-tile) pair here, lanes = half-tiles, the
   // triangle fields broadcast from shared memory.  A half-tile with more than MWB_TILE_CAP candidates keeps only
   // the count; its warp then scans the lists the old way.
-  const int tiles_x = (W + 7) >> 3;
-  const float inv_tiles_x = 1.0f / (float)tiles_x;
-  const int halves_y = (H + 3) >> 2;
-  const int n_halves = tiles_x * halves_y, per_part = k2_halves_per_part(W, H, parts);
-  const int h_begin = min(n_halves, part * per_part), h_end = min(n_halves, h_begin + per_part);
-  const int band_row0 = (h_begin / tiles_x) << 2;         // first pixel row of this block's band (parts > 1: whole rows)
   // Two threads (adjacent lanes) per half-tile: the first takes the nearer half of the ranked triangles, the second the
   // farther half (into a scratch list appended behind the first's), which halves this phase's critical path.
   {
@@ -535,11 +544,7 @@ render_kernel(DevState S, RenderAssets A, ViewSpec view, int fmt, uint8_t* __res
   uint32_t(*skeys)[32] = ws.keys;
   uint32_t* equeue = ws.items;
   // half-tiles in row-major order of 8x4 blocks: index h -> column h % tiles_x, row h / tiles_x
-  if (DYN) {
-    if (tid == 0) next_half = h_begin + WARPS;
-    __syncthreads();
-  }
-  int half = h_begin + warp;
+  int half = h_begin + warp;            // (DYN: next_half was set with the segment table, several barriers ago)
 #pragma unroll 1
   while (half < h_end) {
     const int hrow = (int)(((float)half + 0.5f) * inv_tiles_x), hcol = half - hrow * tiles_x;   // exact: half < 2^20
