@@ -585,7 +585,7 @@ static int ensure_k2_smem(mwb_handle* h, int smem) {
   switch (h->k2_variant) {
     case 0: bad = MWB_K2_ATTR(256, 3, true); break;
     case 1: bad = MWB_K2_ATTR(320, 3, true); break;
-    default: bad = MWB_K2_ATTR(288, 3, true); break;
+    default: bad = MWB_K2_ATTR(512, 2, true); break;
   }
 #undef MWB_K2_ATTR
   if (bad) return -1;
@@ -745,7 +745,7 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   // quad capacity is kept even so that every env's block starts 16-byte aligned
   {
     // tuning knob: 0 = 320 threads x 3 blocks/SM, warps stride over the half-tiles; 1 = same, warps claim
-    // half-tiles from a shared counter (default: -9 % kernel time on B200); 2 = 288 threads x 3 blocks/SM (72 registers)
+    // half-tiles from a shared counter (default: -9 % kernel time on B200); 2 = 512 threads x 2 blocks/SM
     const char* v = getenv("MWB_K2_VARIANT");
     h->k2_variant = v ? atoi(v) : MWB_K2_DEFAULT_VARIANT;
     if (h->k2_variant < 0 || h->k2_variant > 2) h->k2_variant = MWB_K2_DEFAULT_VARIANT;
@@ -765,9 +765,9 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
       case 1: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, true>)
                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 320, 3, true>)
                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 320, 3, true>); break;
-      default: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 288, 3, true>)
-                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 288, 3, true>)
-                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 288, 3, true>); break;
+      default: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 512, 2, true>)
+                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 512, 2, true>)
+                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 512, 2, true>); break;
     }
     if (e == cudaSuccess) {
       h->k2_static_smem = (int)fa.sharedSizeBytes;
@@ -786,13 +786,13 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     switch (h->k2_variant) {
       case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 3, true>, 320, smem); break;
       case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, true>, 320, smem); break;
-      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 288, 3, true>, 288, smem); break;
+      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 512, 2, true>, 512, smem); break;
     }
     const int launch_smem = k2_smem_bytes(h);
     switch (h->k2_variant) {
       case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 256, 3, true>, 256, launch_smem); break;
       case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 320, 3, true>, 320, launch_smem); break;
-      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 288, 3, true>, 288, launch_smem); break;
+      default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<8, 512, 2, true>, 512, launch_smem); break;
     }
     fprintf(stderr, "[mwb] K2 variant %d: dynamic smem %d B (local destination), parts %d, resident blocks/SM (8x MSAA) %d\n",
             h->k2_variant, launch_smem, h->k2_parts, nb);
@@ -1497,7 +1497,7 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
   switch (h->k2_variant) {
     case 0: MWB_LAUNCH_K2_MSAA(256, 3, true); break;
     case 1: MWB_LAUNCH_K2_MSAA(320, 3, true); break;
-    default: MWB_LAUNCH_K2_MSAA(288, 3, true); break;
+    default: MWB_LAUNCH_K2_MSAA(512, 2, true); break;
   }
   prof_mark(h, h->ev_k2, s);
   h->launches++;
