@@ -527,6 +527,7 @@ static void hostsim_render(const DevState& S, const RenderAssets& A, const ViewS
     obs = tmp.data();
   }
   if (S.msaa == 1) hostsim_render_t<1>(S, A, view, obs, depth);
+  else if (S.msaa == 16) hostsim_render_t<16>(S, A, view, obs, depth);
   else if (S.msaa == 4) hostsim_render_t<4>(S, A, view, obs, depth);
   else hostsim_render_t<8>(S, A, view, obs, depth);
   if (obs_out && fmt != MWB_OBS_HWC_U8) {
@@ -580,7 +581,8 @@ static int ensure_k2_smem(mwb_handle* h, int smem) {
 #define MWB_K2_ATTR(T, B, D)                                                                                               \
   (cudaFuncSetAttribute(render_kernel<1, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||    \
    cudaFuncSetAttribute(render_kernel<4, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||    \
-   cudaFuncSetAttribute(render_kernel<8, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+   cudaFuncSetAttribute(render_kernel<8, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||    \
+   cudaFuncSetAttribute(render_kernel<16, T, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
   bool bad;
   switch (h->k2_variant) {
     case 0: bad = MWB_K2_ATTR(256, 3, true); break;
@@ -601,8 +603,8 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
   if (!cfg || !out) return fail(MWB_EINVAL, "null argument");
   if (cfg->abi_version != MWB_ABI_VERSION) return fail(MWB_EABI, "abi_version mismatch");
   if (cfg->num_envs <= 0 || cfg->obs_width <= 0 || cfg->obs_height <= 0) return fail(MWB_EINVAL, "bad sizes");
-  if (cfg->msaa_samples != 1 && cfg->msaa_samples != 4 && cfg->msaa_samples != 8)
-    return fail(MWB_EINVAL, "msaa_samples must be 1, 4 or 8");
+  if (cfg->msaa_samples != 1 && cfg->msaa_samples != 4 && cfg->msaa_samples != 8 && cfg->msaa_samples != 16)
+    return fail(MWB_EINVAL, "msaa_samples must be 1, 4, 8 or 16");
   if (cfg->max_ents <= 0 || cfg->max_ents > MWB_MAX_ENTS_CAP) return fail(MWB_ECAPACITY, "max_ents out of range");
   if (cfg->max_rooms <= 0 || cfg->max_quads <= 0 || cfg->max_segs <= 0) return fail(MWB_EINVAL, "bad capacities");
 #ifndef MWB_HOSTSIM
@@ -759,13 +761,16 @@ extern "C" int mwb_create(const mwb_config* cfg, mwb_handle** out) {
     cudaFuncAttributes fa;
     cudaError_t e;
     switch (h->k2_variant) {
-      case 0: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 256, 3, true>)
+      case 0: e = cfg->msaa_samples == 16 ? cudaFuncGetAttributes(&fa, render_kernel<16, 256, 3, true>)
+                : cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 256, 3, true>)
                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 256, 3, true>)
                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 256, 3, true>); break;
-      case 1: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, true>)
+      case 1: e = cfg->msaa_samples == 16 ? cudaFuncGetAttributes(&fa, render_kernel<16, 320, 3, true>)
+                : cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 320, 3, true>)
                 : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 320, 3, true>)
                                          : cudaFuncGetAttributes(&fa, render_kernel<1, 320, 3, true>); break;
-      default: e = cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 512, 2, true>)
+      default: e = cfg->msaa_samples == 16 ? cudaFuncGetAttributes(&fa, render_kernel<16, 512, 2, true>)
+                : cfg->msaa_samples == 8 ? cudaFuncGetAttributes(&fa, render_kernel<8, 512, 2, true>)
                  : cfg->msaa_samples == 4 ? cudaFuncGetAttributes(&fa, render_kernel<4, 512, 2, true>)
                                           : cudaFuncGetAttributes(&fa, render_kernel<1, 512, 2, true>); break;
     }
@@ -1492,6 +1497,7 @@ static int launch_k2(mwb_handle* h, uint8_t* obs, float* depth, int env0, int co
   switch (h->S.msaa) {                              \
     case 1: MWB_LAUNCH_K2(1, T, B, D); break;       \
     case 4: MWB_LAUNCH_K2(4, T, B, D); break;       \
+    case 16: MWB_LAUNCH_K2(16, T, B, D); break;     \
     default: MWB_LAUNCH_K2(8, T, B, D); break;      \
   }
   switch (h->k2_variant) {
@@ -1692,6 +1698,7 @@ extern "C" int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream) {
   switch (h->S.msaa) {
     case 1: visible_ents_kernel<1><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
     case 4: visible_ents_kernel<4><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
+    case 16: visible_ents_kernel<16><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
     default: visible_ents_kernel<8><<<N, 256, 0, s>>>(h->S, h->A, h->vis_tris, cap, box0, d_mask); break;
   }
   h->launches++;
@@ -1720,7 +1727,8 @@ extern "C" int mwb_visible_ents(mwb_handle* h, uint32_t* mask, void* stream) {
       for (int px = 0; px < W; ++px)
         for (int sm = 0; sm < M; ++sm) {
           float ox, oy;
-          if (M == 8) sample_xy_dyn<8>(sm, ox, oy);
+          if (M == 16) sample_xy_dyn<16>(sm, ox, oy);
+          else if (M == 8) sample_xy_dyn<8>(sm, ox, oy);
           else if (M == 4) sample_xy_dyn<4>(sm, ox, oy);
           else sample_xy_dyn<1>(sm, ox, oy);
           vis |= visible_at_sample(tris, n_room, box0, n_query, ent_slot, px, py, (float)px + ox, (float)py + oy);

@@ -60,12 +60,13 @@ struct RenderAssets {
   int32_t num_meshes;
 };
 
-// D3D standard sample patterns, offsets from the pixel's top-left corner, image space
+// D3D standard sample patterns (1, 4, 8 and 16 samples), offsets from the pixel's top-left corner, image space
 // (x right, y down).  All are multiples of 1/16: sample coordinates are exact in float32.
 // Indexed with compile-time (unrolled) s so the offsets fold into immediates.
 template <int MSAA>
 MWB_DEV float sample_x(int s) {
   if (MSAA == 1) return 0.5f;
+  if (MSAA == 16) return s == 0 ? 0.5625f : s == 1 ? 0.4375f : s == 2 ? 0.3125f : s == 3 ? 0.7500f : s == 4 ? 0.1875f : s == 5 ? 0.6250f : s == 6 ? 0.8125f : s == 7 ? 0.6875f : s == 8 ? 0.3750f : s == 9 ? 0.5000f : s == 10 ? 0.2500f : s == 11 ? 0.1250f : s == 12 ? 0.0000f : s == 13 ? 0.9375f : s == 14 ? 0.8750f : 0.0625f;
   if (MSAA == 4) return s == 0 ? 0.375f : s == 1 ? 0.875f : s == 2 ? 0.125f : 0.625f;
   return s == 0 ? 0.5625f : s == 1 ? 0.4375f : s == 2 ? 0.8125f : s == 3 ? 0.3125f
        : s == 4 ? 0.1875f : s == 5 ? 0.0625f : s == 6 ? 0.6875f : 0.9375f;
@@ -73,6 +74,7 @@ MWB_DEV float sample_x(int s) {
 template <int MSAA>
 MWB_DEV float sample_y(int s) {
   if (MSAA == 1) return 0.5f;
+  if (MSAA == 16) return s == 0 ? 0.5625f : s == 1 ? 0.3125f : s == 2 ? 0.6250f : s == 3 ? 0.4375f : s == 4 ? 0.3750f : s == 5 ? 0.8125f : s == 6 ? 0.6875f : s == 7 ? 0.1875f : s == 8 ? 0.8750f : s == 9 ? 0.0625f : s == 10 ? 0.1250f : s == 11 ? 0.7500f : s == 12 ? 0.5000f : s == 13 ? 0.2500f : s == 14 ? 0.9375f : 0.0000f;
   if (MSAA == 4) return s == 0 ? 0.125f : s == 1 ? 0.375f : s == 2 ? 0.625f : 0.875f;
   return s == 0 ? 0.3125f : s == 1 ? 0.6875f : s == 2 ? 0.5625f : s == 3 ? 0.1875f
        : s == 4 ? 0.8125f : s == 5 ? 0.4375f : s == 6 ? 0.9375f : 0.0625f;
@@ -81,10 +83,10 @@ MWB_DEV float sample_y(int s) {
 // the same offsets for a run-time sample index: sixteenths packed four bits per sample
 template <int MSAA>
 MWB_DEV void sample_xy_dyn(int s, float& x, float& y) {
-  const uint32_t XN = MSAA == 8 ? 0xfb135d79u : (MSAA == 4 ? 0xa2e6u : 0x8u);
-  const uint32_t YN = MSAA == 8 ? 0x1f7d39b5u : (MSAA == 4 ? 0xea62u : 0x8u);
-  x = (float)((XN >> (4 * s)) & 15u) * 0.0625f;
-  y = (float)((YN >> (4 * s)) & 15u) * 0.0625f;
+  const uint64_t XN = MSAA == 16 ? 0x1ef02486bda3c579ull : MSAA == 8 ? 0xfb135d79ull : (MSAA == 4 ? 0xa2e6ull : 0x8ull);
+  const uint64_t YN = MSAA == 16 ? 0xf48c21e3bd67a59ull : MSAA == 8 ? 0x1f7d39b5ull : (MSAA == 4 ? 0xea62ull : 0x8ull);
+  x = (float)(uint32_t)((XN >> (4 * s)) & 15ull) * 0.0625f;
+  y = (float)(uint32_t)((YN >> (4 * s)) & 15ull) * 0.0625f;
 }
 
 struct Camera {
@@ -97,6 +99,7 @@ struct Camera {
   float halfw, halfh;
   float light[3], lamb[3], ldif[3], sky[3];   // light = DIRECTION towards LIGHT0 (see camera_common)
   float linv;                    // 1 / |light|
+  float sample_ext;              // largest |offset| of a sample from the pixel centre: 7/16 (1, 4, 8 samples), 8/16 (16)
   int ortho;                     // 1: render_top_view's orthographic map projection
   float osx, otx, osy, oty;      // x_clip = osx x + otx, y_clip = osy (-z) + oty, z_clip = -0.01 y, w = 1
 };
@@ -128,6 +131,7 @@ MWB_DEV void camera_common(const DevState& S, int i, Camera& c) {
   const size_t N = S.N;
   c.halfw = 0.5f * (float)S.obs_w;
   c.halfh = 0.5f * (float)S.obs_h;
+  c.sample_ext = S.msaa == 16 ? 0.5f : 0.4375f;
   for (int k = 0; k < 3; ++k) {
     c.sky[k] = (float)S.envp[(0 + k) * N + i];
     c.light[k] = (float)d_add(S.envp[(3 + k) * N + i], 1.0);
@@ -310,7 +314,8 @@ MWB_DEV void edge_rn(const HVert& a, const HVert& b, float& A, float& B, float& 
 // (y down) front faces have negative signed area, so edges are built on (v0, v2, v1): then
 // det > 0 <=> front-facing and the interior is E_k >= 0.  Returns false if culled.
 MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, const VertAttr& a0,
-                            const VertAttr& a1, const VertAttr& a2, int tex, int W, int H, TriRec& t) {
+                            const VertAttr& a1, const VertAttr& a2, int tex, int W, int H, TriRec& t,
+                            float ext = 0.4375f /* Camera.sample_ext */) {
   if (frustum_reject(g0, g1, g2)) return false;
   const HVert& v0 = g0;
   const HVert& v1 = g2;
@@ -323,13 +328,13 @@ MWB_DEV bool setup_triangle(const HVert& g0, const HVert& g1, const HVert& g2, c
   t.Za = f_div(f_add(f_add(f_mul(v0.zeta, t.A[0]), f_mul(v1.zeta, t.A[1])), f_mul(v2.zeta, t.A[2])), det);
   t.Zb = f_div(f_add(f_add(f_mul(v0.zeta, t.B[0]), f_mul(v1.zeta, t.B[1])), f_mul(v2.zeta, t.B[2])), det);
   t.Zc = f_div(f_add(f_add(f_mul(v0.zeta, t.C[0]), f_mul(v1.zeta, t.C[1])), f_mul(v2.zeta, t.C[2])), det);
-  // |z(sample) - z(centre)| <= 0.4375 (|Za| + |Zb|); plus a bound on evaluation rounding
-  t.Zr = 0.4375f * (fabsf(t.Za) + fabsf(t.Zb)) + 4e-6f * (fabsf(t.Za) * (float)W + fabsf(t.Zb) * (float)H + fabsf(t.Zc)) + 1e-6f;
+  // |z(sample) - z(centre)| <= ext (|Za| + |Zb|); plus a bound on evaluation rounding
+  t.Zr = ext * (fabsf(t.Za) + fabsf(t.Zb)) + 4e-6f * (fabsf(t.Za) * (float)W + fabsf(t.Zb) * (float)H + fabsf(t.Zc)) + 1e-6f;
   t.Kz = t.Zc - t.Zr + 8.0f * fminf(t.Za, 0.0f) + 4.0f * fminf(t.Zb, 0.0f);
   for (int k = 0; k < 3; ++k) {
     float aa = fabsf(t.A[k]), ab = fabsf(t.B[k]);
-    // |E(sample) - E(centre)| <= 0.4375 (|A| + |B|); plus a bound on evaluation rounding
-    t.R[k] = 0.4375f * (aa + ab) + 4e-6f * (aa * (float)W + ab * (float)H + fabsf(t.C[k])) + 1e-30f;
+    // |E(sample) - E(centre)| <= ext (|A| + |B|); plus a bound on evaluation rounding
+    t.R[k] = ext * (aa + ab) + 4e-6f * (aa * (float)W + ab * (float)H + fabsf(t.C[k])) + 1e-30f;
     // tie rule: the edge with A > 0, or A == 0 and B > 0, owns samples with E == 0
     t.T[k] = (t.A[k] > 0.0f || (t.A[k] == 0.0f && t.B[k] > 0.0f)) ? 0.0f : 1.401298464e-45f;
     t.K[k] = t.C[k] + t.R[k] + 8.0f * fmaxf(t.A[k], 0.0f) + 4.0f * fmaxf(t.B[k], 0.0f);
@@ -866,7 +871,7 @@ MWB_DEV bool finish_triangle(const Camera& cam, const TriInput& in, int W, int H
     at[k].g = col[1];
     at[k].b = col[2];
   }
-  return setup_triangle(hv[0], hv[1], hv[2], at[0], at[1], at[2], in.tex, W, H, out);
+  return setup_triangle(hv[0], hv[1], hv[2], at[0], at[1], at[2], in.tex, W, H, out, cam.sample_ext);
 }
 
 // half `half` (fan (0,1,2) / (0,2,3)) of static quad q of env i

@@ -195,6 +195,7 @@ class MiniWorldEnv(gym.Env):
         self.obs_width, self.obs_height = obs_width, obs_height
         self.window_width, self.window_height = window_width, window_height
         self.msaa_samples = msaa_samples
+        self.vis_samples = 16 if msaa_samples == 8 else msaa_samples     # obs_fb 8 / vis_fb 16 like the reference
         self.device = device
         self._engine = None
         self._vis_engine = None
@@ -483,14 +484,15 @@ class MiniWorldEnv(gym.Env):
             raise RuntimeError("MiniWorldEnv was built with device=None (world generation only)")
         if self._vis_engine is None:
             from .engine import SingleEnvEngine
-            self._vis_engine = SingleEnvEngine(self.window_width, self.window_height, self.msaa_samples, self.device)
+            # FrameBuffer(window_width, window_height, 16) (miniworld.py:518): the human-view buffer asks for 16 samples
+            self._vis_engine = SingleEnvEngine(self.window_width, self.window_height, self.vis_samples, self.device)
         return self._vis_engine
 
     def render(self):
         """render_mode="rgb_array": the human-view frame at window_width x window_height (the
         reference's vis_fb image, miniworld.py:1340-1362) -- the agent's view, or the map when
-        view="top".  Samples per pixel follow msaa_samples (the reference asks for 16 and takes what the
-        driver grants).  The interactive pyglet window (render_mode="human") is not part of this package."""
+        view="top".  16 samples per pixel like the reference's vis_fb (which takes what its GL driver grants);
+        an explicit msaa_samples other than 8 applies to both buffers.  The interactive pyglet window (render_mode="human") is not part of this package."""
         if self.render_mode != "rgb_array":
             return None
         if self.view != "agent":

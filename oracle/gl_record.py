@@ -108,7 +108,7 @@ class RecGL:
     """The GL context: state + recording.  One instance stands for the process-wide context the reference creates
     with its hidden pyglet window."""
 
-    def __init__(self, max_samples=8):
+    def __init__(self, max_samples=16):
         self.max_samples = max_samples         # what glGetIntegerv(GL_MAX_SAMPLES) reports (opengl.py:223-231)
         self.active = True                     # False: draw calls / read-backs are ignored (physics-only runs: fast)
         self.enabled = set()
@@ -584,7 +584,7 @@ class _Noop:
         return _Noop(item)
 
 
-def install(max_samples=8):
+def install(max_samples=16):
     """Inject the recording `pyglet` into sys.modules (before the reference is imported).  Returns the context."""
     ctx = RecGL(max_samples)
     pyglet = types.ModuleType("pyglet")

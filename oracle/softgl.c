@@ -147,6 +147,8 @@ static const float PAT4[4][2] = {{0.375f, 0.125f}, {0.875f, 0.375f}, {0.125f, 0.
 static const float PAT8[8][2] = {{0.5625f, 0.3125f}, {0.4375f, 0.6875f}, {0.8125f, 0.5625f}, {0.3125f, 0.1875f},
                                  {0.1875f, 0.8125f}, {0.0625f, 0.4375f}, {0.6875f, 0.9375f}, {0.9375f, 0.0625f}};
 
+static const float PAT16[16][2] = {{0.5625f, 0.5625f}, {0.4375f, 0.3125f}, {0.3125f, 0.6250f}, {0.7500f, 0.4375f}, {0.1875f, 0.3750f}, {0.6250f, 0.8125f}, {0.8125f, 0.6875f}, {0.6875f, 0.1875f}, {0.3750f, 0.8750f}, {0.5000f, 0.0625f}, {0.2500f, 0.1250f}, {0.1250f, 0.7500f}, {0.0000f, 0.5000f}, {0.9375f, 0.2500f}, {0.8750f, 0.9375f}, {0.0625f, 0.0000f}};
+
 typedef struct {
   float X, Y, W, Z; /* window-homogeneous position: X/W column, Y/W row, Z/W window depth */
   float cx, cy, cz; /* clip coordinates */
@@ -173,8 +175,8 @@ static void bilerp(const Tex* t, int level, float u, float v, float out[3]) {
 
 int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* depth_out, uint16_t* code_out) {
   const int W = sc->width, H = sc->height, NS = sc->samples;
-  const float(*pat)[2] = NS == 1 ? PAT1 : (NS == 4 ? PAT4 : PAT8);
-  if (NS != 1 && NS != 4 && NS != 8) return -1;
+  const float(*pat)[2] = NS == 1 ? PAT1 : (NS == 4 ? PAT4 : (NS == 8 ? PAT8 : PAT16));
+  if (NS != 1 && NS != 4 && NS != 8 && NS != 16) return -1;
 
   /* --- camera: cam_pos = pos + fwd_disp * dir_vec + (0, h, 0); cam_dir = X rotated by pitch
    * then heading; gluLookAt basis f, s = f x up (normalised), u = s x f, evaluated in float64
@@ -330,7 +332,7 @@ int softgl_render(const Scene* sc, const TexSet* ts, uint8_t* rgb_out, float* de
     for (int py = by0; py <= by1; ++py)
       for (int px = bx0; px <= bx1; ++px) {
         unsigned pass = 0;
-        uint16_t codes[8];
+        uint16_t codes[16];
         for (int s = 0; s < NS; ++s) {
           float xs = (float)px + pat[s][0], ys = (float)py + pat[s][1];
           int inside = 1;

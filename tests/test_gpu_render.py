@@ -77,7 +77,7 @@ def test_rollout_frames_match_oracle(libmwb_path, softgl_lib, name):
     env.close()
 
 
-@pytest.mark.parametrize("msaa", [1, 4, 8])
+@pytest.mark.parametrize("msaa", [1, 4, 8, 16])
 def test_sample_counts(libmwb_path, softgl_lib, msaa):
     from miniworld_b200.assets import Texture
     from miniworld_b200.envs import LEVELS
@@ -92,6 +92,26 @@ def test_sample_counts(libmwb_path, softgl_lib, msaa):
         assert np.abs(rgb.astype(int) - obs[i].astype(int)).max() <= 1
     ts.close()
     env.close()
+
+
+def test_human_view_is_rendered_with_16_samples(libmwb_path, softgl_lib):
+    """render() of the drop-in class = the reference's vis_fb frame: FrameBuffer(window_width, window_height, 16)
+    (miniworld.py:518), agent view and map view, against the oracle with the 16-sample pattern (which the reference's own
+    render() equals under the recording GL: tests/test_stream_oracle.py)."""
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.envs import Hallway
+    for view in ("agent", "top"):
+        env = Hallway(render_mode="rgb_array", window_width=200, window_height=150, view=view)
+        env.reset(seed=3)
+        env.step(2)
+        frame = env.render()
+        ts = softgl_lib.TextureSet([t.texels for t in Texture.registry])
+        want = (softgl_lib.render(env, ts, lambda tex: tex.tex_id, 200, 150, 16)[0] if view == "agent"
+                else softgl_lib.render_top_view(env, ts, lambda tex: tex.tex_id, 200, 150, 16))
+        ts.close()
+        d = np.abs(frame.astype(int) - want.astype(int))
+        assert frame.shape == (150, 200, 3) and d.max() <= 1 and (d == 0).mean() > 0.995
+        env.close()
 
 
 def test_obs_160x120(libmwb_path, softgl_lib):

@@ -80,6 +80,25 @@ def test_single_env_levels_follow_reference(hostsim_path, name):
     run_single_env_trajectory(name, golden(name), hostsim_path, envs=2, steps=40 if name == "pickup" else 100)
 
 
+def test_human_view_16_samples_matches_oracle(hostsim_path, softgl_lib):
+    """render() = the reference's vis_fb frame, 16 samples per pixel (miniworld.py:518): kernels' arithmetic on the CPU
+    with the 16-sample pattern vs the oracle, agent view and map view."""
+    from miniworld_b200.assets import Texture
+    from miniworld_b200.envs import Hallway
+    for view in ("agent", "top"):
+        env = Hallway(render_mode="rgb_array", window_width=120, window_height=90, view=view)
+        env.reset(seed=3)
+        env.step(2)
+        frame = env.render()
+        ts = softgl_lib.TextureSet([t.texels for t in Texture.registry])
+        want = (softgl_lib.render(env, ts, lambda tex: tex.tex_id, 120, 90, 16)[0] if view == "agent"
+                else softgl_lib.render_top_view(env, ts, lambda tex: tex.tex_id, 120, 90, 16))
+        ts.close()
+        d = np.abs(frame.astype(int) - want.astype(int))
+        assert frame.shape == (90, 120, 3) and d.max() <= 1 and (d == 0).mean() > 0.995
+        env.close()
+
+
 def test_render_mode_and_wrappers_on_host_sim(hostsim_path):
     """reference tests/test_miniworld.py:17-64 (render vs obs mean, wrapper shapes), kernels on the CPU."""
     from miniworld_b200.envs import Hallway

@@ -56,6 +56,23 @@ def test_reference_other_views_equal_mirror(softgl_lib, level):
 
 
 @needs_reference
+def test_reference_human_view_is_16_samples_and_equals_mirror(softgl_lib):
+    """render() with render_mode="rgb_array": the reference's vis_fb = FrameBuffer(window_width, window_height, 16)
+    (miniworld.py:518); under the recording GL (GL_MAX_SAMPLES = 16) the frame it returns is a 16-sample frame and
+    equals the mirror rendered with the D3D 16-sample pattern -- agent view and map view."""
+    from oracle.stream_check import Pair
+    for view in ("agent", "top"):
+        p = Pair("MiniWorld-Hallway-v0", False, render_mode="rgb_array", window_width=160, window_height=120, view=view)
+        p.reset(5)
+        p.step(2)
+        got = p.ref.render()
+        fr = ref_stub.recorder.frames[-1]
+        assert fr.samples == 16 and got.shape == (120, 160, 3)
+        want = p.mirror_frame(160, 120, 16)[0] if view == "agent" else p.mirror_top_view(160, 120, 16)
+        assert np.array_equal(got, want)
+
+
+@needs_reference
 def test_reference_light_is_directional():
     """(GLfloat * 4)(*self.light_pos + [1]) with an ndarray light_pos passes THREE values, each + 1, and leaves w = 0
     (miniworld.py:1031, params.py:45-46): LIGHT0 is a directional light along light_pos + 1."""

@@ -22,6 +22,8 @@ for level, kw in [("MiniWorld-FourRooms-v0", dict(want_depth=True)), ("MiniWorld
     blob = env.snapshot()
     env.restore(blob)
     torch.cuda.synchronize()
+    if isinstance(obs, dict):                 # Sign's dict observation
+        obs = obs["obs"]
     print(level, float(obs.float().mean()), float(top.float().mean()), int(vis.sum()), env.engine.overflow_count())
     env.close()
 e = LEVELS["MiniWorld-ThreeRooms-v0"](domain_rand=True)
@@ -33,6 +35,11 @@ PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard" gpurun_out/sanitizer_$tool.log | head -8
+  # the same rollouts with the whole-frame / band stage forced on (the store shape used towards a peer GPU)
+  MWB_K2_FLAGS=11 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_${tool}_staged.log 2>&1; echo "$tool staged rc=$?"
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard" gpurun_out/sanitizer_${tool}_staged.log | head -8
 done
+if [ -n "$MWB_SANITIZE_EXTRAS" ]; then
 timeout 600 ncu --set full --clock-control none -k regex:step_kernel -s 6 -c 1 -f -o gpurun_out/prof_k1 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_k1.log 2>&1; echo "ncu k1 rc=$?"
 timeout 600 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; cut -c1-330 gpurun_out/configs.jsonl
+fi
