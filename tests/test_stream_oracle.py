@@ -73,6 +73,26 @@ def test_reference_human_view_is_16_samples_and_equals_mirror(softgl_lib):
 
 
 @needs_reference
+def test_reference_own_render_test_holds_on_the_recorded_stream():
+    """The one pixel-level statement the reference's test suite makes (tests/test_miniworld.py:17-38, Hallway,
+    render_mode="rgb_array"): 0 < mean(obs) < 255, |mean(80x60 observation) - mean(800x600 human view)| < 5, and the
+    observation shapes -- evaluated on what the unmodified reference returns under the recording GL."""
+    env = ref_stub.make_reference_env("MiniWorld-Hallway-v0", record=True, render_mode="rgb_array")
+    for seed in (0, 1):
+        env.reset(seed=seed)
+        for _ in range(3):
+            obs, _, _, _, _ = env.step(0)
+        first_obs, _ = env.reset(seed=seed + 10)
+        first_render = env.render()
+        assert first_render.shape == (600, 800, 3) and ref_stub.recorder.frames[-1].samples == 16
+        m0, m1 = first_obs.mean(), first_render.mean()
+        assert 0 < m0 < 255
+        assert abs(m0 - m1) < 5, (m0, m1)
+        second_obs, _, _, _, _ = env.step(0)
+        assert first_obs.shape == env.observation_space.shape == second_obs.shape
+
+
+@needs_reference
 def test_reference_light_is_directional():
     """(GLfloat * 4)(*self.light_pos + [1]) with an ndarray light_pos passes THREE values, each + 1, and leaves w = 0
     (miniworld.py:1031, params.py:45-46): LIGHT0 is a directional light along light_pos + 1."""
